@@ -1,0 +1,115 @@
+/* rtpp_gpu.h — C ABI of librtpp_gpu.so, the B200 (sm_100a) implementation of the data-parallel hot
+ * path shared by the four planners of TZY-H/RTPP (RT-RRT*, RT-FMT, AM-RRT*, CDRT-RRT*).
+ *
+ * The reference has no plugin/FFI seam: its hot path is a set of member functions of the planner
+ * classes.  This header is the seam a maintainer would bind; every entry point names the
+ * reference routine (file:line, relative to the reference root) whose work it takes over.
+ * INTEGRATION.md shows the planner-side call sites.
+ *
+ * Conventions
+ *   - extern "C", opaque rtpp_ctx*, plain pointers and sizes, no C++/torch types.
+ *   - every call returns 0 (RTPP_OK) or a negative rtpp_status; rtpp_last_error() has the text.
+ *     Nothing throws; nothing falls back to the CPU: without a CUDA device rtpp_create fails.
+ *   - one ctx per host thread; calls on one ctx are ordered on the ctx stream.
+ *   - functions without suffix take HOST buffers (copy in, run, copy out, synchronise);
+ *     functions ending in _dev take DEVICE pointers, are stream-ordered and do not synchronise.
+ *   - coordinates are pixels, x = column in [0,W), y = row in [0,H); finite, |v| < 2^20.
+ *   - "blocked bits": edge i -> bit (i & 31) of word (i >> 5); 1 = the reference's
+ *     CrashDetection would return true.  Unused high bits of the last word are 0.
+ *   - arithmetic is bit-exact with the reference's scalar code (binary32/binary64, round to
+ *     nearest even, no FMA contraction, truncating float->int), see DESIGN.md.
+ */
+#ifndef RTPP_GPU_H
+#define RTPP_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RTPP_API __attribute__((visibility("default")))
+#else
+#define RTPP_API
+#endif
+
+typedef struct rtpp_ctx rtpp_ctx;
+
+enum rtpp_status {
+    RTPP_OK = 0,
+    RTPP_ERR_INVALID = -1,     /* bad argument */
+    RTPP_ERR_CUDA = -2,        /* CUDA runtime error (text in rtpp_last_error) */
+    RTPP_ERR_NOMEM = -3,       /* device or host allocation failed */
+    RTPP_ERR_STATE = -4,       /* call order: e.g. edge check before any plane was set */
+    RTPP_ERR_CAPACITY = -5     /* a fixed-capacity store (nodes, queue) is full */
+};
+
+/* plane ids; also the bits of a plane_mask */
+enum { RTPP_PLANE_STATIC = 1, RTPP_PLANE_DYNAMIC = 2 };
+
+#define RTPP_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- lifecycle ------------------ */
+RTPP_API int rtpp_abi_version(void);
+RTPP_API const char *rtpp_status_string(int status);
+RTPP_API int rtpp_create(int device, rtpp_ctx **out);
+RTPP_API int rtpp_destroy(rtpp_ctx *ctx);
+RTPP_API const char *rtpp_last_error(rtpp_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream. */
+RTPP_API int rtpp_set_stream(rtpp_ctx *ctx, void *cuda_stream);
+RTPP_API int rtpp_sync(rtpp_ctx *ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+RTPP_API long long rtpp_kernel_launches(rtpp_ctx *ctx);
+RTPP_API int rtpp_device_sm_count(rtpp_ctx *ctx, int *sm_count);
+
+/* device / pinned-host buffers for resident workflows (bench.py, planner host code) */
+RTPP_API int rtpp_dev_alloc(rtpp_ctx *ctx, size_t bytes, void **dptr);
+RTPP_API int rtpp_dev_free(rtpp_ctx *ctx, void *dptr);
+RTPP_API int rtpp_host_alloc(rtpp_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+RTPP_API int rtpp_host_free(rtpp_ctx *ctx, void *hptr);
+RTPP_API int rtpp_h2d(rtpp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the ctx stream */
+RTPP_API int rtpp_d2h(rtpp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on the ctx stream */
+
+/* ---------------------------------------------------------------- maps ----------------------- */
+/* Replaces the cv::Mat planes the planners probe: Obsmap (RTRRT.cpp:69-79) = RTPP_PLANE_STATIC,
+ * DObsmap (RTRRT.cpp:138-169, rebuilt every tick) = RTPP_PLANE_DYNAMIC.  `rowmajor` is the H*W
+ * uint8 plane (non-zero = obstacle).  The device keeps bit-packed 32x32-pixel tiles (one 128-byte
+ * line per tile) for S, D and the merged S|D.  Both planes must have the same W,H. */
+RTPP_API int rtpp_map_set_plane(rtpp_ctx *ctx, int plane, const uint8_t *rowmajor, int W, int H);
+RTPP_API int rtpp_map_set_plane_dev(rtpp_ctx *ctx, int plane, const uint8_t *d_rowmajor, int W, int H);
+/* DObsmap = cv::Mat::zeros (RTRRT.cpp:140) without an upload. */
+RTPP_API int rtpp_map_clear_plane(rtpp_ctx *ctx, int plane);
+/* Unpack the plane selected by plane_mask (1 = S, 2 = D, 3 = S|D) back to H*W bytes (0/1). */
+RTPP_API int rtpp_map_get_plane(rtpp_ctx *ctx, int plane_mask, uint8_t *out_rowmajor);
+RTPP_API int rtpp_map_shape(rtpp_ctx *ctx, int *W, int *H);
+
+/* ---------------------------------------------------------------- edge checks (K1) ----------- */
+/* E1 RTRRTplanner::CrashDetection RTRRT.cpp:202-222, RTFMTplanner::CrashDetection RTFMT.cpp:242-262
+ *    (divisor 5, plane_mask 3);
+ * E2 RTFMTplanner::CrashDetectionNDObs RTFMT.cpp:264-283 (divisor 5, plane_mask 1);
+ * E3 AMRRTplanner::CrashDetection AMRRT.cpp:266-286 (divisor 2, plane_mask 3).
+ * xyxy: n edges as (ps.x, ps.y, pe.x, pe.y) binary32. */
+RTPP_API int rtpp_edges_check(rtpp_ctx *ctx, const float *xyxy, size_t n, int divisor, int plane_mask,
+                              uint32_t *blocked_bits);
+RTPP_API int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divisor, int plane_mask,
+                                  uint32_t *d_blocked_bits);
+/* E5b, the ray-march inside BImap::RTRT_CrashDetection CDRT.cpp:584-601: binary64 points,
+ * binary32 interpolation parameter, divisor 10, plane_mask 2 in the reference. */
+RTPP_API int rtpp_edges_check_f64(rtpp_ctx *ctx, const double *xyxy, size_t n, int divisor, int plane_mask,
+                                  uint32_t *blocked_bits);
+RTPP_API int rtpp_edges_check_f64_dev(rtpp_ctx *ctx, const double *d_xyxy, size_t n, int divisor, int plane_mask,
+                                      uint32_t *d_blocked_bits);
+/* E4 AMRRTplanner::CrashDetectionStart AMRRT.cpp:287-308 (linear march, spacing len/2+2, both
+ * planes): blocked bit + the last free point pstart (2 floats per edge). */
+RTPP_API int rtpp_edges_first_hit(rtpp_ctx *ctx, const float *xyxy, size_t n, uint32_t *blocked_bits,
+                                  float *pstart_xy);
+RTPP_API int rtpp_edges_first_hit_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, uint32_t *d_blocked_bits,
+                                      float *d_pstart_xy);
+/* C2 RTpoint::operator% RTRRT.h:47-52 on n point pairs (exposed for parity tests). */
+RTPP_API int rtpp_dist(rtpp_ctx *ctx, const float *xyxy, size_t n, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTPP_GPU_H */

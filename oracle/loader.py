@@ -342,3 +342,147 @@ def synthetic_map(size=4096, seed=42, n_rect=400, n_disc=200):
         sub = (yy[y0:y1] - y) ** 2 + (xx[:, x0:x1] - x) ** 2 <= r * r
         m[y0:y1, x0:x1][sub] = 255
     return m
+
+
+class OrcRTFMT(_TreePlanner):
+    def __init__(self, S):
+        S = _c(S, np.uint8)
+        super().__init__(lib(), "orc_rtfmt", lib().orc_rtfmt_create(_ptr(S), S.shape[0], S.shape[1]), S.shape)
+
+    def start(self, r, sample_n):
+        r = _c(r, np.int32)
+        return int(self.L.orc_rtfmt_start(self.h, _ptr(r), C.c_longlong(len(r)), sample_n))
+
+    def expand(self, iters, with_rewire=True):
+        self.L.orc_rtfmt_expand(self.h, iters, int(with_rewire))
+
+    def dump(self):
+        n = self.num_nodes()
+        xy = np.zeros((n, 2), np.float32)
+        par = np.zeros(n, np.int32)
+        cost = np.zeros(n, np.float32)
+        col = np.zeros(n, np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._f("dump")(self.h, _ptr(xy), _ptr(par), _ptr(cost), _ptr(col), _ptr(st))
+        return xy, par, cost, col, st
+
+    def z(self):
+        xy = np.zeros(2, np.float32)
+        self._f("z")(self.h, _ptr(xy))
+        return xy
+
+    def counters(self):
+        out = np.zeros(3, np.int64)
+        self.L.orc_rtfmt_counters(self.h, _ptr(out))
+        return dict(zip(["expand", "edge_checks", "knn"], out.tolist()))
+
+    def get_path(self, cap=2048):
+        xy = np.zeros((cap, 2), np.float32)
+        n = self._f("get_path")(self.h, _ptr(xy), cap)
+        return xy[: min(n, cap)]
+
+
+class RefRTFMT(OrcRTFMT):
+    """The reference's own RTFMTplanner (oracle/_ref); Start() draws 2000 samples per call."""
+
+    def __init__(self, S):
+        L = ref_lib("rtfmt")
+        if L is None:
+            raise FileNotFoundError("oracle/_ref/libref_rtfmt.so not built")
+        S = _c(S, np.uint8)
+        _TreePlanner.__init__(self, L, "ref_rtfmt", L.ref_rtfmt_create(_ptr(S), S.shape[0], S.shape[1]), S.shape)
+
+    def start(self, r, sample_n):
+        assert sample_n % 2000 == 0
+        self._rand = _c(r, np.int32)
+        self.L.ref_set_rand(_ptr(self._rand), C.c_longlong(len(self._rand)))
+        for _ in range(sample_n // 2000):
+            self.L.ref_rtfmt_start(self.h)
+        return int(self.L.ref_rand_pos())
+
+    def expand(self, iters, with_rewire=True):
+        self.L.ref_rtfmt_expand(self.h, iters, int(with_rewire))
+
+    def crash(self, xyxy, ndobs=False):
+        xyxy = _c(xyxy, np.float32).reshape(-1, 4)
+        out = np.zeros(len(xyxy), np.uint8)
+        self.L.ref_rtfmt_crash(self.h, _ptr(xyxy), C.c_longlong(len(xyxy)), int(ndobs), _ptr(out))
+        return out
+
+    def counters(self):
+        return {}
+
+
+class OrcAMRRT(_TreePlanner):
+    def __init__(self, S):
+        S = _c(S, np.uint8)
+        super().__init__(lib(), "orc_amrrt", lib().orc_amrrt_create(_ptr(S), S.shape[0], S.shape[1]), S.shape)
+
+    def set_clock(self, dt_ns, n0=0):
+        self.L.orc_amrrt_set_clock(self.h, C.c_longlong(dt_ns), C.c_longlong(n0))
+
+    def set_rand(self, r):
+        r = _c(r, np.int32)
+        self.L.orc_amrrt_set_rand(self.h, _ptr(r), C.c_longlong(len(r)))
+
+    def rand_pos(self):
+        return int(self.L.orc_amrrt_rand_pos(self.h))
+
+    def set_diffusion(self, cells_ij, matrix, ratio):
+        cells = _c(cells_ij, np.int32).reshape(-1, 2)
+        m = _c(matrix, np.float32).reshape(len(cells), -1)
+        self._f("set_diffusion")(self.h, _ptr(cells), len(cells), _ptr(m), m.shape[1], C.c_float(ratio))
+
+    def diffusivity(self, a, b):
+        f = self._f("diffusivity")
+        f.restype = C.c_float
+        return float(f(self.h, C.c_float(a[0]), C.c_float(a[1]), C.c_float(b[0]), C.c_float(b[1])))
+
+    def expand(self):
+        self._f("expand")(self.h)
+
+    def rewire_root(self):
+        self._f("rewire_root")(self.h)
+
+    def main_task(self):
+        self._f("main_task")(self.h)
+
+    def get_path(self, cap=2048):
+        xy = np.zeros((cap, 2), np.float32)
+        col, cost = C.c_int(), C.c_float()
+        n = self._f("get_path")(self.h, _ptr(xy), cap, C.byref(col), C.byref(cost))
+        return xy[: min(n, cap)], bool(col.value), cost.value
+
+
+class RefAMRRT(OrcAMRRT):
+    """The reference's own AMRRTplanner (oracle/_ref)."""
+
+    def __init__(self, S):
+        L = ref_lib("amrrt")
+        if L is None:
+            raise FileNotFoundError("oracle/_ref/libref_amrrt.so not built")
+        S = _c(S, np.uint8)
+        _TreePlanner.__init__(self, L, "ref_amrrt", L.ref_amrrt_create(_ptr(S), S.shape[0], S.shape[1]), S.shape)
+
+    def set_clock(self, dt_ns, n0=0):
+        self.L.ref_set_clock(C.c_longlong(dt_ns), C.c_longlong(n0))
+
+    def set_rand(self, r):
+        self._rand = _c(r, np.int32)
+        self.L.ref_set_rand(_ptr(self._rand), C.c_longlong(len(self._rand)))
+
+    def rand_pos(self):
+        return int(self.L.ref_rand_pos())
+
+    def crash(self, xyxy):
+        xyxy = _c(xyxy, np.float32).reshape(-1, 4)
+        out = np.zeros(len(xyxy), np.uint8)
+        self.L.ref_amrrt_crash(self.h, _ptr(xyxy), C.c_longlong(len(xyxy)), _ptr(out))
+        return out
+
+    def crash_start(self, xyxy):
+        xyxy = _c(xyxy, np.float32).reshape(-1, 4)
+        out = np.zeros(len(xyxy), np.uint8)
+        ps = np.zeros((len(xyxy), 2), np.float32)
+        self.L.ref_amrrt_crash_start(self.h, _ptr(xyxy), C.c_longlong(len(xyxy)), _ptr(out), _ptr(ps))
+        return out, ps

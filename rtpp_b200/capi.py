@@ -1,0 +1,164 @@
+"""ctypes mirror of include/rtpp_gpu.h (one method per entry point, same names minus `rtpp_`).
+
+Host-buffer methods take/return numpy arrays; *_dev methods take raw device pointers (ints), e.g.
+torch.Tensor.data_ptr().  Fails loudly when librtpp_gpu.so is missing or no GPU is present.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PLANE_STATIC, PLANE_DYNAMIC = 1, 2
+
+
+class RtppError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(HERE, "librtpp_gpu.so")
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into rtpp_b200/librtpp_gpu.so (nvcc cross-compiles)."""
+    out = subprocess.run(["make", "-C", os.path.join(HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode:
+        raise RtppError("building librtpp_gpu.so failed")
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path()):
+            raise RtppError(f"{lib_path()} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        _lib = C.CDLL(lib_path())
+        _lib.rtpp_status_string.restype = C.c_char_p
+        _lib.rtpp_last_error.restype = C.c_char_p
+        _lib.rtpp_kernel_launches.restype = C.c_longlong
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Ctx:
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.rtpp_create(int(device), C.byref(h))
+        if rc:
+            raise RtppError(f"rtpp_create(device={device}) failed: {self.L.rtpp_status_string(rc).decode()} "
+                            "(a CUDA device is required; there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.rtpp_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc:
+            raise RtppError(f"{self.L.rtpp_status_string(rc).decode()}: {self.L.rtpp_last_error(self.h).decode()}")
+
+    def call(self, name, *args):
+        self._ck(getattr(self.L, "rtpp_" + name)(self.h, *args))
+
+    # ---- lifecycle
+    def set_stream(self, stream_ptr):
+        self.call("set_stream", C.c_void_p(stream_ptr))
+
+    def sync(self):
+        self.call("sync")
+
+    def kernel_launches(self):
+        return int(self.L.rtpp_kernel_launches(self.h))
+
+    def sm_count(self):
+        n = C.c_int()
+        self.call("device_sm_count", C.byref(n))
+        return n.value
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.call("dev_alloc", C.c_size_t(nbytes), C.byref(p))
+        return p.value
+
+    def dev_free(self, ptr):
+        self.call("dev_free", C.c_void_p(ptr))
+
+    def h2d(self, dst, src_np):
+        self.call("h2d", C.c_void_p(dst), _p(src_np), C.c_size_t(src_np.nbytes))
+
+    def d2h(self, dst_np, src):
+        self.call("d2h", _p(dst_np), C.c_void_p(src), C.c_size_t(dst_np.nbytes))
+
+    # ---- maps
+    def map_set_plane(self, plane, rowmajor):
+        a = _c(rowmajor, np.uint8)
+        self.call("map_set_plane", int(plane), _p(a), a.shape[1], a.shape[0])
+
+    def map_clear_plane(self, plane):
+        self.call("map_clear_plane", int(plane))
+
+    def map_get_plane(self, mask):
+        w, h = C.c_int(), C.c_int()
+        self.call("map_shape", C.byref(w), C.byref(h))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.call("map_get_plane", int(mask), _p(out))
+        return out
+
+    # ---- edges
+    @staticmethod
+    def unpack_bits(bits, n):
+        return np.unpackbits(bits.view(np.uint8), bitorder="little")[:n]
+
+    def edges_check(self, xyxy, divisor, mask):
+        e = _c(xyxy, np.float32).reshape(-1, 4)
+        bits = np.zeros((len(e) + 31) // 32, np.uint32)
+        self.call("edges_check", _p(e), C.c_size_t(len(e)), int(divisor), int(mask), _p(bits))
+        return self.unpack_bits(bits, len(e))
+
+    def edges_check_f64(self, xyxy, divisor, mask):
+        e = _c(xyxy, np.float64).reshape(-1, 4)
+        bits = np.zeros((len(e) + 31) // 32, np.uint32)
+        self.call("edges_check_f64", _p(e), C.c_size_t(len(e)), int(divisor), int(mask), _p(bits))
+        return self.unpack_bits(bits, len(e))
+
+    def edges_first_hit(self, xyxy):
+        e = _c(xyxy, np.float32).reshape(-1, 4)
+        bits = np.zeros((len(e) + 31) // 32, np.uint32)
+        ps = np.zeros((len(e), 2), np.float32)
+        self.call("edges_first_hit", _p(e), C.c_size_t(len(e)), _p(bits), _p(ps))
+        return self.unpack_bits(bits, len(e)), ps
+
+    def edges_check_dev(self, d_xyxy, n, divisor, mask, d_bits):
+        self.call("edges_check_dev", C.c_void_p(d_xyxy), C.c_size_t(n), int(divisor), int(mask), C.c_void_p(d_bits))
+
+    def dist(self, xyxy):
+        e = _c(xyxy, np.float32).reshape(-1, 4)
+        out = np.zeros(len(e), np.float32)
+        self.call("dist", _p(e), C.c_size_t(len(e)), _p(out))
+        return out

@@ -1,0 +1,143 @@
+// common.cuh — context, error plumbing and the exact device arithmetic shared by every kernel of
+// librtpp_gpu.so (sm_100a).  No CPU fallback anywhere: if a call cannot run on the GPU it fails.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/rtpp_gpu.h"
+
+// ------------------------------------------------------------------------------------------------
+// Bit-packed occupancy planes
+// ------------------------------------------------------------------------------------------------
+// A plane is stored as 32x32-pixel tiles; a tile is 32 consecutive uint32 (one 128-byte line):
+// word r of a tile holds row r of the tile, bit c = pixel column c.  A probe is therefore one
+// 4-byte load; every probe of a short edge normally lands in the same 128-byte line.
+// Pixels outside [0,W)x[0,H) inside the padded tiles are 0.
+struct PlaneView {
+    const uint32_t *__restrict__ w;
+    int W, H;      // pixels
+    int tilesX;    // tiles per tile-row
+};
+
+// ------------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------------
+struct NodeStore; // grid.cu
+struct rtpp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::string err;
+
+    // planes: [0] = S, [1] = D, [2] = S|D   (uint32 tiles)
+    uint32_t *plane[3] = {nullptr, nullptr, nullptr};
+    bool plane_set[2] = {false, false};
+    int W = 0, H = 0, tilesX = 0, tilesY = 0;
+    size_t plane_words = 0;
+
+    // grow-only device scratch for the host-buffer entry points
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
+
+    NodeStore *nodes = nullptr;
+};
+
+#define RTPP_CK(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+            return e__ == cudaErrorMemoryAllocation ? RTPP_ERR_NOMEM : RTPP_ERR_CUDA;               \
+        }                                                                                           \
+    } while (0)
+
+#define RTPP_FAIL(ctx, code, msg)                                                                   \
+    do {                                                                                            \
+        (ctx)->err = (msg);                                                                         \
+        return (code);                                                                              \
+    } while (0)
+
+// count + check a kernel launch
+#define RTPP_LAUNCHED(ctx)                                                                          \
+    do {                                                                                            \
+        (ctx)->launches++;                                                                          \
+        RTPP_CK(ctx, cudaGetLastError());                                                           \
+    } while (0)
+
+int rtpp_scratch(rtpp_ctx *ctx, int slot, size_t bytes, void **out);
+int rtpp_select_plane(rtpp_ctx *ctx, int plane_mask, PlaneView *pv);
+
+// ------------------------------------------------------------------------------------------------
+// Exact arithmetic (bit-equal to the reference's scalar C++ built without FMA contraction)
+// ------------------------------------------------------------------------------------------------
+// RTpoint::operator% (reference RTRRT.h:47-52): sqrtf32(dx*dx + dy*dy), each op rounded once.
+__device__ __forceinline__ float rt_dist(float ax, float ay, float bx, float by) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by);
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+}
+// BIpoint::operator% (reference CDRT.h:73-78), binary64.
+__device__ __forceinline__ double rt_dist64(double ax, double ay, double bx, double by) {
+    double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+// "int32_t MaximumDiscrete = len / D + 2" (reference RTRRT.cpp:209): binary32 divide, add, truncate.
+__device__ __forceinline__ int rt_march_M(float len, float divisor) {
+    return __float2int_rz(__fadd_rn(__fdiv_rn(len, divisor), 2.0f));
+}
+// Largest power of two <= M (M >= 2): the last value of the reference's "denominator" loop
+// (RTRRT.cpp:210).  Interior probes are t = j/P, j = 1..P-1 (the dyadic fractions i/2^k are
+// exact in binary32, so the reduced and unreduced forms give the same t).
+__device__ __forceinline__ int rt_pow2_floor(int M) { return M < 2 ? 1 : (1 << (31 - __clz(M))); }
+
+// One pixel probe = cv::Mat::at<uint8_t>(row, col) != 0 on a continuous Mat.  Coordinates that
+// leave the row but stay inside the buffer wrap exactly as base[row*cols+col] does; reads outside
+// the buffer (undefined in the reference) are DEFINED as blocked — same rule as the oracle.
+// (W*H < 2^31 is enforced when a plane is set, so the wrapped index fits 32 bits.)
+__device__ __forceinline__ bool rt_probe(const PlaneView &p, int row, int col) {
+    if (!((unsigned)col < (unsigned)p.W && (unsigned)row < (unsigned)p.H)) { // cold path
+        const long long lin = (long long)row * p.W + col;
+        if (lin < 0 || lin >= (long long)p.W * p.H) return true;
+        const unsigned l32 = (unsigned)lin;
+        row = (int)(l32 / (unsigned)p.W);
+        col = (int)(l32 - (unsigned)row * (unsigned)p.W);
+    }
+    const uint32_t word = __ldg(p.w + ((((unsigned)(row >> 5) * p.tilesX + (col >> 5)) << 5) + (row & 31)));
+    return (word >> (col & 31)) & 1u;
+}
+
+// Interior probe j of P for the dyadic march (reference RTRRT.cpp:214-217):
+//   t = j/P;  x = (int)(ps.x*t + (1-t)*pe.x);  y likewise;  unfused, truncating.
+__device__ __forceinline__ bool rt_probe_interior(const PlaneView &p, float psx, float psy, float pex, float pey,
+                                                  float t) {
+    float omt = __fsub_rn(1.0f, t);
+    int x = __float2int_rz(__fadd_rn(__fmul_rn(psx, t), __fmul_rn(omt, pex)));
+    int y = __float2int_rz(__fadd_rn(__fmul_rn(psy, t), __fmul_rn(omt, pey)));
+    return rt_probe(p, y, x);
+}
+
+// Whole edge by one thread (used inside the planner engines and the relax kernels, where edges
+// are short).  Returns the reference's CrashDetection verdict.
+__device__ __forceinline__ bool rt_edge_blocked(const PlaneView &p, float psx, float psy, float pex, float pey,
+                                                float divisor) {
+    bool hit = rt_probe(p, __float2int_rz(psy), __float2int_rz(psx)) | rt_probe(p, __float2int_rz(pey), __float2int_rz(pex));
+    if (hit) return true;
+    int P = rt_pow2_floor(rt_march_M(rt_dist(psx, psy, pex, pey), divisor));
+    float inv = 1.0f / (float)P; // exact: P is a power of two
+    for (int j = 1; j < P; j++) hit |= rt_probe_interior(p, psx, psy, pex, pey, __fmul_rn((float)j, inv));
+    return hit;
+}
+
+// streaming 16-byte load that does not allocate in L1 (edge lists are read once; L1 is kept for
+// the bit-plane lines)
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *ptr) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(ptr));
+    return r;
+}

@@ -1,0 +1,298 @@
+// edges.cu — K1: batched edge collision checks by warp-cooperative dyadic ray marching.
+//
+// Replaces (bit-exactly) the reference's scalar routines
+//   E1 RTRRTplanner::CrashDetection        RTRRT.cpp:202-222  (= RTFMT.cpp:242-262), divisor 5
+//   E2 RTFMTplanner::CrashDetectionNDObs   RTFMT.cpp:264-283, static plane only
+//   E3 AMRRTplanner::CrashDetection        AMRRT.cpp:266-286, divisor 2
+//   E4 AMRRTplanner::CrashDetectionStart   AMRRT.cpp:287-308, linear march + last free point
+//   E5b BImap::RTRT_CrashDetection         CDRT.cpp:584-601, binary64 points, divisor 10
+//
+// Mapping: a warp owns 32 consecutive edges.  Each lane loads its edge with one streaming 16-byte
+// load, tests the two end pixels and marches its own interior probes while the edge is short
+// (<= 15 interior probes: the k-NN / tree-edge case).  Edges with >= 31 interior probes are then
+// marched by the whole warp, lane-strided over the probes and OR-reduced with __any_sync.  The 32
+// verdicts leave as one ballot word (4 coalesced bytes per warp).  The verdict is a pure OR over
+// the probe set, so probe order is free (the reference's early exit cannot change it).
+//
+// Roofline: algorithmic bytes per edge = 16 + 4*n_probes + 1/8; the edge list streams
+// from HBM, the bit-plane (0.9-2 MB) is L2/L1 resident.
+#include "common.cuh"
+
+static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 32 -> warp marches
+
+__global__ void __launch_bounds__(256)
+edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, float divisor,
+                      uint32_t *__restrict__ out_bits) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t nwords = (n + 31) >> 5;
+    for (size_t w = warp0; w < nwords; w += nwarps) {
+        const size_t i = (w << 5) + lane;
+        bool blocked = false;
+        int P = 1;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            e = ld_stream_f4(edges + i);
+            blocked = rt_probe(pl, __float2int_rz(e.y), __float2int_rz(e.x)) |
+                      rt_probe(pl, __float2int_rz(e.w), __float2int_rz(e.z));
+            P = rt_pow2_floor(rt_march_M(rt_dist(e.x, e.y, e.z, e.w), divisor));
+        }
+        if (!blocked && P > 1 && P <= kShortMaxP) {
+            const float inv = 1.0f / (float)P;
+#pragma unroll 4
+            for (int j = 1; j < P; j++) blocked |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+        }
+        unsigned longmask = __ballot_sync(full, !blocked && P > kShortMaxP);
+        while (longmask) {
+            const int src = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const float sx = __shfl_sync(full, e.x, src), sy = __shfl_sync(full, e.y, src);
+            const float tx = __shfl_sync(full, e.z, src), ty = __shfl_sync(full, e.w, src);
+            const int Ps = __shfl_sync(full, P, src);
+            const float inv = 1.0f / (float)Ps;
+            bool hit = false;
+            for (int j0 = 1; j0 < Ps; j0 += 32) { // warp-uniform trip count, early exit per chunk
+                const int j = j0 + lane;
+                if (j < Ps) hit = rt_probe_interior(pl, sx, sy, tx, ty, __fmul_rn((float)j, inv));
+                if (__any_sync(full, hit)) {
+                    hit = true;
+                    break;
+                }
+            }
+            if (lane == src) blocked = hit;
+        }
+        const unsigned bits = __ballot_sync(full, blocked);
+        if (lane == 0) out_bits[w] = bits;
+    }
+}
+
+// E5b: binary64 end points, binary32 interpolation parameter (CDRT.cpp:586-600).
+__device__ __forceinline__ bool probe_interior_f64(const PlaneView &p, double psx, double psy, double pex, double pey,
+                                                   float t) {
+    const float omt = __fsub_rn(1.0f, t);
+    const double td = (double)t, od = (double)omt;
+    int x = __double2int_rz(__dadd_rn(__dmul_rn(psx, td), __dmul_rn(od, pex)));
+    int y = __double2int_rz(__dadd_rn(__dmul_rn(psy, td), __dmul_rn(od, pey)));
+    return rt_probe(p, y, x);
+}
+
+__global__ void __launch_bounds__(256)
+edge_check_f64_kernel(PlaneView pl, const double4 *__restrict__ edges, size_t n, float divisor,
+                      uint32_t *__restrict__ out_bits) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t nwords = (n + 31) >> 5;
+    for (size_t w = warp0; w < nwords; w += nwarps) {
+        const size_t i = (w << 5) + lane;
+        bool blocked = false;
+        int P = 1;
+        double4 e = make_double4(0., 0., 0., 0.);
+        if (i < n) {
+            e = edges[i];
+            blocked = rt_probe(pl, __double2int_rz(e.y), __double2int_rz(e.x)) |
+                      rt_probe(pl, __double2int_rz(e.w), __double2int_rz(e.z));
+            const float len = __double2float_rn(rt_dist64(e.x, e.y, e.z, e.w)); // "float len = ps % pe"
+            P = rt_pow2_floor(rt_march_M(len, divisor));
+        }
+        if (!blocked && P > 1 && P <= kShortMaxP) {
+            const float inv = 1.0f / (float)P;
+            for (int j = 1; j < P; j++) blocked |= probe_interior_f64(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+        }
+        unsigned longmask = __ballot_sync(full, !blocked && P > kShortMaxP);
+        while (longmask) {
+            const int src = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const double sx = __shfl_sync(full, e.x, src), sy = __shfl_sync(full, e.y, src);
+            const double tx = __shfl_sync(full, e.z, src), ty = __shfl_sync(full, e.w, src);
+            const int Ps = __shfl_sync(full, P, src);
+            const float inv = 1.0f / (float)Ps;
+            bool hit = false;
+            for (int j0 = 1; j0 < Ps; j0 += 32) {
+                const int j = j0 + lane;
+                if (j < Ps) hit = probe_interior_f64(pl, sx, sy, tx, ty, __fmul_rn((float)j, inv));
+                if (__any_sync(full, hit)) {
+                    hit = true;
+                    break;
+                }
+            }
+            if (lane == src) blocked = hit;
+        }
+        const unsigned bits = __ballot_sync(full, blocked);
+        if (lane == 0) out_bits[w] = bits;
+    }
+}
+
+// E4: linear march i = 1..M-1, t = (float)i/M weighting pe; needs the FIRST blocked index
+// (a min-reduction, not an OR).  One warp per edge: lanes take 32 consecutive i, the first chunk
+// with a hit gives f = base + ffs(ballot) - 1; pstart = point(f-1) (or ps when f == 1).
+__device__ __forceinline__ float2 first_hit_point(float psx, float psy, float pex, float pey, int i, float Mf) {
+    const float t = __fdiv_rn((float)i, Mf);
+    const float omt = __fsub_rn(1.0f, t);
+    float2 r;
+    r.x = __fadd_rn(__fmul_rn(pex, t), __fmul_rn(omt, psx));
+    r.y = __fadd_rn(__fmul_rn(pey, t), __fmul_rn(omt, psy));
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+edge_first_hit_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, uint32_t *__restrict__ out_bits,
+                      float2 *__restrict__ pstart) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t nwords = (n + 31) >> 5;
+    for (size_t w = warp0; w < nwords; w += nwarps) {
+        unsigned bits = 0;
+        const size_t base = w << 5;
+        const int cnt = (int)min((size_t)32, n - base);
+        // lane k preloads edge base+k; the warp then walks the 32 edges one at a time
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < cnt) mine = ld_stream_f4(edges + base + lane);
+        for (int k = 0; k < cnt; k++) {
+            const float psx = __shfl_sync(full, mine.x, k), psy = __shfl_sync(full, mine.y, k);
+            const float pex = __shfl_sync(full, mine.z, k), pey = __shfl_sync(full, mine.w, k);
+            bool blocked = rt_probe(pl, __float2int_rz(psy), __float2int_rz(psx)) |
+                           rt_probe(pl, __float2int_rz(pey), __float2int_rz(pex));
+            float2 ps = make_float2(psx, psy);
+            if (!blocked) {
+                const int M = rt_march_M(rt_dist(psx, psy, pex, pey), 2.0f);
+                const float Mf = (float)M;
+                int f = 0; // first blocked index, 0 = none
+                for (int i0 = 1; i0 < M; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool hit = false;
+                    if (i < M) {
+                        const float2 q = first_hit_point(psx, psy, pex, pey, i, Mf);
+                        hit = rt_probe(pl, __float2int_rz(q.y), __float2int_rz(q.x));
+                    }
+                    const unsigned hm = __ballot_sync(full, hit);
+                    if (hm) {
+                        f = i0 + __ffs(hm) - 1;
+                        break;
+                    }
+                }
+                if (f) {
+                    blocked = true;
+                    if (f > 1) ps = first_hit_point(psx, psy, pex, pey, f - 1, Mf);
+                } else
+                    ps = make_float2(pex, pey);
+            }
+            if (blocked) bits |= 1u << k;
+            if (lane == 0) pstart[base + k] = ps;
+        }
+        if (lane == 0) out_bits[w] = bits;
+    }
+}
+
+__global__ void __launch_bounds__(256) dist_kernel(const float4 *__restrict__ e, size_t n, float *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = e[i];
+        out[i] = rt_dist(v.x, v.y, v.z, v.w);
+    }
+}
+
+// grid sizing: a multiple of the SM count, enough resident warps to cover L2 latency
+static int edge_grid(rtpp_ctx *ctx, size_t n, int per_block) {
+    size_t need = (n + per_block - 1) / per_block;
+    size_t cap = (size_t)ctx->sm_count * 8;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+extern "C" {
+
+int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divisor, int plane_mask, uint32_t *d_bits) {
+    if (!ctx || (n && (!d_xyxy || !d_bits))) return RTPP_ERR_INVALID;
+    if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    PlaneView pv;
+    int rc = rtpp_select_plane(ctx, plane_mask, &pv);
+    if (rc) return rc;
+    if (n == 0) return RTPP_OK;
+    edge_check_f32_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, (float)divisor, d_bits);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+int rtpp_edges_check_f64_dev(rtpp_ctx *ctx, const double *d_xyxy, size_t n, int divisor, int plane_mask, uint32_t *d_bits) {
+    if (!ctx || (n && (!d_xyxy || !d_bits))) return RTPP_ERR_INVALID;
+    if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    PlaneView pv;
+    int rc = rtpp_select_plane(ctx, plane_mask, &pv);
+    if (rc) return rc;
+    if (n == 0) return RTPP_OK;
+    edge_check_f64_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const double4 *)d_xyxy, n, (float)divisor, d_bits);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+int rtpp_edges_first_hit_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, uint32_t *d_bits, float *d_pstart) {
+    if (!ctx || (n && (!d_xyxy || !d_bits || !d_pstart))) return RTPP_ERR_INVALID;
+    PlaneView pv;
+    int rc = rtpp_select_plane(ctx, 3, &pv);
+    if (rc) return rc;
+    if (n == 0) return RTPP_OK;
+    edge_first_hit_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, d_bits, (float2 *)d_pstart);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+// ---- host-buffer entry points: copy in, run, copy out, synchronise ----
+static int edges_host(rtpp_ctx *ctx, const void *xyxy, size_t n, size_t elem, int divisor, int plane_mask,
+                      uint32_t *bits, float *pstart, int kind) {
+    if (!ctx || (n && (!xyxy || !bits))) return RTPP_ERR_INVALID;
+    if (n == 0) return RTPP_OK;
+    RTPP_CK(ctx, cudaSetDevice(ctx->device));
+    void *d_e = nullptr, *d_b = nullptr, *d_p = nullptr;
+    const size_t nwords = (n + 31) / 32;
+    int rc = rtpp_scratch(ctx, 0, n * 4 * elem, &d_e);
+    if (rc) return rc;
+    rc = rtpp_scratch(ctx, 1, nwords * 4, &d_b);
+    if (rc) return rc;
+    RTPP_CK(ctx, cudaMemcpyAsync(d_e, xyxy, n * 4 * elem, cudaMemcpyHostToDevice, ctx->stream));
+    if (kind == 0) rc = rtpp_edges_check_dev(ctx, (const float *)d_e, n, divisor, plane_mask, (uint32_t *)d_b);
+    else if (kind == 1) rc = rtpp_edges_check_f64_dev(ctx, (const double *)d_e, n, divisor, plane_mask, (uint32_t *)d_b);
+    else {
+        rc = rtpp_scratch(ctx, 2, n * 8, &d_p);
+        if (rc) return rc;
+        rc = rtpp_edges_first_hit_dev(ctx, (const float *)d_e, n, (uint32_t *)d_b, (float *)d_p);
+    }
+    if (rc) return rc;
+    RTPP_CK(ctx, cudaMemcpyAsync(bits, d_b, nwords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kind == 2) RTPP_CK(ctx, cudaMemcpyAsync(pstart, d_p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+int rtpp_edges_check(rtpp_ctx *ctx, const float *xyxy, size_t n, int divisor, int plane_mask, uint32_t *bits) {
+    return edges_host(ctx, xyxy, n, sizeof(float), divisor, plane_mask, bits, nullptr, 0);
+}
+int rtpp_edges_check_f64(rtpp_ctx *ctx, const double *xyxy, size_t n, int divisor, int plane_mask, uint32_t *bits) {
+    return edges_host(ctx, xyxy, n, sizeof(double), divisor, plane_mask, bits, nullptr, 1);
+}
+int rtpp_edges_first_hit(rtpp_ctx *ctx, const float *xyxy, size_t n, uint32_t *bits, float *pstart) {
+    if (n && !pstart) return RTPP_ERR_INVALID;
+    return edges_host(ctx, xyxy, n, sizeof(float), 2, 3, bits, pstart, 2);
+}
+
+int rtpp_dist(rtpp_ctx *ctx, const float *xyxy, size_t n, float *out) {
+    if (!ctx || (n && (!xyxy || !out))) return RTPP_ERR_INVALID;
+    if (n == 0) return RTPP_OK;
+    void *d_e = nullptr, *d_o = nullptr;
+    int rc = rtpp_scratch(ctx, 0, n * 16, &d_e);
+    if (rc) return rc;
+    rc = rtpp_scratch(ctx, 1, n * 4, &d_o);
+    if (rc) return rc;
+    RTPP_CK(ctx, cudaMemcpyAsync(d_e, xyxy, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    dist_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>((const float4 *)d_e, n, (float *)d_o);
+    RTPP_LAUNCHED(ctx);
+    RTPP_CK(ctx, cudaMemcpyAsync(out, d_o, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,94 @@
+"""K1 parity: CUDA edge checks (through the C ABI) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import dyn_plane, edge_mix
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def game0(oracle, ctx):
+    S = oracle.load_map("GAME0")
+    D = dyn_plane(S.shape, np.random.default_rng(7))
+    ctx.map_set_plane(1, S)
+    ctx.map_set_plane(2, D)
+    return S, D
+
+
+def test_plane_roundtrip(ctx, game0):
+    S, D = game0
+    assert np.array_equal(ctx.map_get_plane(1), (S != 0).astype(np.uint8))
+    assert np.array_equal(ctx.map_get_plane(2), (D != 0).astype(np.uint8))
+    assert np.array_equal(ctx.map_get_plane(3), ((S != 0) | (D != 0)).astype(np.uint8))
+
+
+@pytest.mark.parametrize("divisor,mask", [(5, 3), (5, 1), (2, 3), (10, 2), (2, 1)])
+def test_edges_check_bit_exact(ctx, oracle, game0, divisor, mask):
+    S, D = game0
+    H, W = S.shape
+    e = edge_mix(np.random.default_rng(100 + divisor + mask), 1_000_003, W, H)
+    got = ctx.edges_check(e, divisor, mask)
+    want = oracle.edges_check(S, D, e, divisor, mask, nthreads=8)
+    assert got.shape == want.shape
+    assert int((got != want).sum()) == 0
+    assert 0.02 < want.mean() < 0.98  # the batch exercises both verdicts
+
+
+def test_edges_symmetric_and_edge_cases(ctx, oracle, game0):
+    S, D = game0
+    H, W = S.shape
+    e = edge_mix(np.random.default_rng(5), 200_000, W, H)
+    fwd = ctx.edges_check(e, 5, 3)
+    rev = ctx.edges_check(e[:, [2, 3, 0, 1]], 5, 3)
+    assert np.array_equal(fwd, rev)  # the verdict is symmetric
+    # empty, single, ragged (n not a multiple of 32), zero-length edges, far corners
+    assert ctx.edges_check(np.zeros((0, 4), np.float32), 5, 3).size == 0
+    special = np.array([[10, 10, 10, 10], [0, 0, W - 1, H - 1], [W - 0.5, H - 0.5, 0.25, 0.25],
+                        [W - 1, 0, 0, H - 1], [550, 550, 551, 551]], np.float32)
+    for n in (1, 2, 5):
+        got = ctx.edges_check(special[:n], 5, 3)
+        assert np.array_equal(got, oracle.edges_check(S, D, special[:n], 5, 3))
+    # out-of-row / out-of-buffer coordinates follow the linear-index rule of cv::Mat::at
+    oob = np.array([[W + 3.0, 10, W + 40.0, 12], [5, H + 2.0, 6, H + 9.0], [-3.5, 4, 20, 4], [W, H - 1, W, H - 1]], np.float32)
+    assert np.array_equal(ctx.edges_check(oob, 5, 3), oracle.edges_check(S, D, oob, 5, 3))
+
+
+def test_edges_first_hit_bit_exact(ctx, oracle, game0):
+    S, D = game0
+    H, W = S.shape
+    e = edge_mix(np.random.default_rng(11), 300_001, W, H, short_px=150.0)
+    gb, gp = ctx.edges_first_hit(e)
+    wb, wp = oracle.edges_first_hit(S, D, e, nthreads=8)
+    assert int((gb != wb).sum()) == 0
+    assert np.array_equal(gp.view(np.uint32), wp.view(np.uint32))
+
+
+def test_edges_f64_bit_exact(ctx, oracle, game0):
+    S, D = game0
+    H, W = S.shape
+    rng = np.random.default_rng(13)
+    e = edge_mix(rng, 300_000, W, H, short_px=200.0).astype(np.float64)
+    e += rng.random(e.shape) * 1e-3  # genuine binary64 coordinates
+    e = np.clip(e, 0, min(W, H) - 1e-9)
+    got = ctx.edges_check_f64(e, 10, 2)
+    want = oracle.edges_check_f64(S, D, e, 10, 2, nthreads=8)
+    assert int((got != want).sum()) == 0
+    assert want.any() and not want.all()
+
+
+def test_dist_bit_exact(ctx, oracle):
+    e = edge_mix(np.random.default_rng(17), 100_000, 4096, 4096)
+    assert np.array_equal(ctx.dist(e).view(np.uint32), oracle.dist(e).view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["FLOOR5", "MAZE0", "MESS6", "Trap"])
+def test_edges_other_maps(ctx, oracle, name):
+    S = oracle.load_map(name)
+    H, W = S.shape
+    ctx.map_set_plane(1, S)
+    ctx.map_clear_plane(2)
+    e = edge_mix(np.random.default_rng(23), 200_000, W, H)
+    for divisor in (5, 2):
+        got = ctx.edges_check(e, divisor, 3)
+        assert np.array_equal(got, oracle.edges_check(S, None, e, divisor, 1, nthreads=8))
