@@ -109,6 +109,34 @@ RTPP_API int rtpp_edges_first_hit_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t
 /* C2 RTpoint::operator% RTRRT.h:47-52 on n point pairs (exposed for parity tests). */
 RTPP_API int rtpp_dist(rtpp_ctx *ctx, const float *xyxy, size_t n, float *out);
 
+/* ---------------------------------------------------------------- nodes + k-NN (K2/K3) ------- */
+/* The node store replaces `Kd_tree NeighborSearchTree` + the coordinate keys of
+ * `std::map<RTpoint, ...> Node_Map` (RTRRT.h:129-130): nodes are float2 points, node id = insertion
+ * index.  The spatial hash uses 2^cell_log2-pixel cells over [0,domain_w) x [0,domain_h) (points
+ * outside are binned into the border cells).  reset drops all nodes. */
+RTPP_API int rtpp_nodes_reset(rtpp_ctx *ctx, int cell_log2, size_t capacity, int domain_w, int domain_h);
+/* Kd_tree::insert (CGAL/Kd_tree.h:461-466; RTRRT.cpp:29,291, RTFMT.cpp:29,417, AMRRT.cpp:31,474,
+ * CDRT.cpp:918): append n points (x,y float pairs); *first_id receives the id of the first one.
+ * Later queries see every point appended so far. */
+RTPP_API int rtpp_nodes_append(rtpp_ctx *ctx, const float *xy, size_t n, int32_t *first_id);
+RTPP_API int rtpp_nodes_append_dev(rtpp_ctx *ctx, const float *d_xy, size_t n, int32_t *first_id);
+RTPP_API int rtpp_nodes_count(rtpp_ctx *ctx, size_t *n);
+/* Force the re-sort of the spatial hash now (otherwise lazy). */
+RTPP_API int rtpp_nodes_build(rtpp_ctx *ctx);
+/* Device pointer to the resident coordinates (float2 by node id). */
+RTPP_API int rtpp_nodes_xy_dev(rtpp_ctx *ctx, const float **d_xy);
+/* Orthogonal_k_neighbor_search(tree, q, k) (CGAL/Orthogonal_k_neighbor_search.h:51-79; call sites
+ * RTRRT.cpp:96,265,304,333,368; RTFMT.cpp:97,291,427,440,477,549,677; AMRRT.cpp:160,316,444,449,496,
+ * 546; CDRT.cpp:206,231,261,890): the min(k,N) nodes of smallest squared distance evaluated in
+ * binary64, ascending; ties by ascending node id.  qxy: nq (x,y) binary64 pairs.  Rows of k:
+ * idx (-1 padded), d2 (+inf padded; may be NULL), count = min(k,N) (may be NULL).  1 <= k <= 32. */
+RTPP_API int rtpp_knn(rtpp_ctx *ctx, const double *qxy, size_t nq, int k, int32_t *idx, double *d2, int32_t *count);
+RTPP_API int rtpp_knn_dev(rtpp_ctx *ctx, const double *d_qxy, size_t nq, int k, int32_t *d_idx, double *d_d2,
+                          int32_t *d_count);
+/* All-k-NN table of the node set itself, row i = neighbours of node i (includes i at d2 = 0, as
+ * the reference's queries at tree nodes do: RTRRT.cpp:304, RTFMT.cpp:440). */
+RTPP_API int rtpp_knn_nodes_dev(rtpp_ctx *ctx, int k, int32_t *d_idx, double *d_d2);
+
 #ifdef __cplusplus
 }
 #endif

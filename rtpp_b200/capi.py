@@ -162,3 +162,40 @@ class Ctx:
         out = np.zeros(len(e), np.float32)
         self.call("dist", _p(e), C.c_size_t(len(e)), _p(out))
         return out
+
+    # ---- nodes + k-NN
+    def nodes_reset(self, cell_log2, capacity, domain_w, domain_h):
+        self.call("nodes_reset", int(cell_log2), C.c_size_t(capacity), int(domain_w), int(domain_h))
+
+    def nodes_append(self, xy):
+        a = _c(xy, np.float32).reshape(-1, 2)
+        first = C.c_int32()
+        self.call("nodes_append", _p(a), C.c_size_t(len(a)), C.byref(first))
+        return first.value
+
+    def nodes_count(self):
+        n = C.c_size_t()
+        self.call("nodes_count", C.byref(n))
+        return n.value
+
+    def nodes_build(self):
+        self.call("nodes_build")
+
+    def nodes_xy_dev(self):
+        p = C.c_void_p()
+        self.call("nodes_xy_dev", C.byref(p))
+        return p.value
+
+    def knn(self, qxy, k):
+        q = _c(qxy, np.float64).reshape(-1, 2)
+        idx = np.zeros((len(q), k), np.int32)
+        d2 = np.zeros((len(q), k), np.float64)
+        cnt = np.zeros(len(q), np.int32)
+        self.call("knn", _p(q), C.c_size_t(len(q)), int(k), _p(idx), _p(d2), _p(cnt))
+        return idx, d2, cnt
+
+    def knn_dev(self, d_q, nq, k, d_idx, d_d2=0, d_count=0):
+        self.call("knn_dev", C.c_void_p(d_q), C.c_size_t(nq), int(k), C.c_void_p(d_idx), C.c_void_p(d_d2), C.c_void_p(d_count))
+
+    def knn_nodes_dev(self, k, d_idx, d_d2=0):
+        self.call("knn_nodes_dev", int(k), C.c_void_p(d_idx), C.c_void_p(d_d2))
