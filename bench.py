@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the planner hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[3], the largest single-GPU configuration): AM-RRT* on a synthetic
+4096x4096 occupancy map (PCG64 seed 42: 400 rectangles + 200 discs, plus 6 dynamic obstacles) with
+1e6 tree nodes.  One STEP = one batched collision pass over every candidate edge of one rewire
+tick: the 999 999 tree edges (R3 re-cost, AMRRT.cpp:185-199) + the 25e6 rewire edges node ->
+25-NN (AMRRT.cpp:496-500), divisor 2, both planes; 26.0e6 edges, 416 MB of end points (> L2).
+metric = edge collision checks / s.  `value`: edge list resident in HBM, K launches timed with
+CUDA events on the launching stream.  `e2e`: the same batch through the host-buffer C-ABI call
+(rtpp_edges_check) from pinned host memory, H2D + kernel + D2H of the verdict words every step.
+Extras (k-NN queries/s, tick latencies, replan iterations/s) are measured outside the timed region.
+
+--impl reference: the reference's own AMRRTplanner::CrashDetection (compiled in place into
+oracle/_ref; the oracle port if that library is absent) over the same edges on all host threads.
+N > 1 (torchrun): every rank owns an independent instance of the workload (different seed), no
+data-path collective; weak scaling; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAP_SIZE = 4096
+N_NODES = 1_000_000
+KNN = 25
+DIVISOR = 2
+METRIC = "edge_collision_checks_per_s"
+UNIT = "edges/s"
+
+
+# ------------------------------------------------------------------------------------ workload
+def c4_map(seed=42):
+    """Synthetic C4 planes: static (seed 42) + a few dynamic discs/boxes (value 127)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    S = np.zeros((MAP_SIZE, MAP_SIZE), np.uint8)
+    for _ in range(400):
+        w, h = rng.integers(16, 257, 2)
+        x, y = rng.integers(0, MAP_SIZE - 16, 2)
+        S[y:y + h, x:x + w] = 255
+    yy, xx = np.ogrid[:MAP_SIZE, :MAP_SIZE]
+
+    def disc(img, x, y, r, v):
+        y0, y1, x0, x1 = max(0, y - r), min(MAP_SIZE, y + r + 1), max(0, x - r), min(MAP_SIZE, x + r + 1)
+        sub = (yy[y0:y1] - y) ** 2 + (xx[:, x0:x1] - x) ** 2 <= r * r
+        img[y0:y1, x0:x1][sub] = v
+
+    for _ in range(200):
+        r = int(rng.integers(8, 97))
+        x, y = (int(v) for v in rng.integers(0, MAP_SIZE, 2))
+        disc(S, x, y, r, 255)
+    D = np.zeros_like(S)
+    for _ in range(6):
+        r = int(rng.integers(40, 120))
+        x, y = (int(v) for v in rng.integers(0, MAP_SIZE, 2))
+        disc(D, x, y, r, 127)
+    return S, D
+
+
+def c4_nodes(S, seed, n=N_NODES):
+    """n uniform free-space points, float32 like rand()/float(RAND_MAX)*shape."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    have = 0
+    while have < n:
+        p = (rng.random((n, 2), dtype=np.float32) * np.float32(MAP_SIZE)).astype(np.float32)
+        ok = S[p[:, 1].astype(np.int32), p[:, 0].astype(np.int32)] == 0
+        out.append(p[ok])
+        have += int(ok.sum())
+    return np.ascontiguousarray(np.concatenate(out)[:n])
+
+
+class Workload:
+    """Resident C4 state on one GPU + the candidate-edge batch."""
+
+    def __init__(self, device, seed):
+        import torch
+
+        import rtpp_b200
+
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
+        torch.cuda.set_device(self.dev)
+        self.stream = torch.cuda.Stream(self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.ctx = rtpp_b200.Ctx(device)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        self.S, self.D = c4_map(42)
+        self.ctx.map_set_plane(1, self.S)
+        self.ctx.map_set_plane(2, self.D)
+        self.xy = c4_nodes(self.S, 1000 + seed)
+        n = len(self.xy)
+        self.ctx.nodes_reset(4, n, MAP_SIZE, MAP_SIZE)
+        self.ctx.nodes_append(self.xy)
+        self.ctx.nodes_build()
+        self.knn_idx = torch.empty((n, KNN), dtype=torch.int32, device=self.dev)
+        self.ctx.knn_nodes_dev(KNN, self.knn_idx.data_ptr())
+        self.ctx.sync()
+        xy_t = torch.from_numpy(self.xy).to(self.dev)
+        idx = self.knn_idx.long()
+        # random-tree order: parent = nearest neighbour with a smaller id, node 0 = root
+        ar = torch.arange(n, device=self.dev)[:, None]
+        earlier = (idx < ar) & (idx >= 0)
+        first = torch.argmax(earlier.int(), dim=1)
+        par = torch.where(earlier.any(1), idx[ar[:, 0], first], torch.zeros_like(first))
+        par[0] = -1
+        self.parent = par.int().cpu().numpy()
+        tree = torch.cat([xy_t[par[1:]], xy_t[1:]], 1)                       # (parent, child)
+        rew = torch.cat([xy_t[:, None, :].expand(n, KNN, 2), xy_t[idx]], 2).reshape(-1, 4)  # (x, knn[x][j])
+        self.edges = torch.cat([tree, rew], 0).contiguous()
+        self.n_edges = int(self.edges.shape[0])
+        self.bits = torch.zeros((self.n_edges + 31) // 32, dtype=torch.int32, device=self.dev)
+        del xy_t, idx, earlier, rew, tree
+        torch.cuda.synchronize()
+
+    def step(self):
+        self.ctx.edges_check_dev(self.edges.data_ptr(), self.n_edges, DIVISOR, 3, self.bits.data_ptr())
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.stop_flag = [], False
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        nv = self.nv
+        while self.ok and not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self, t0, t1):
+        nv = self.nv
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": mx,
+                "reasons": sorted(v for k, v in names.items() if mask & k), "samples": len(inside)}
+
+
+# ------------------------------------------------------------------------------------ CPU side
+def cpu_edge_rate(S, D, edges, threads, budget_s=20.0):
+    """Reference CPU implementation of the step on `threads` host threads -> (edges/s, kind, sample)."""
+    from oracle import loader as orc
+
+    kind = "port"
+    fn = lambda e: orc.edges_check(S, D, e, DIVISOR, 3, nthreads=threads)
+    try:
+        ref = orc.RefAMRRT(S)
+        ref.set_dobs(D)
+        fn = lambda e: ref.crash_mt(e, threads)
+        kind = "reference"
+    except Exception:
+        pass
+    probe = edges[: min(len(edges), 2_000_000)]
+    t = time.perf_counter()
+    fn(probe)
+    rate = len(probe) / (time.perf_counter() - t)
+    n = int(min(len(edges), max(1_000_000, rate * budget_s / 3)))
+    best = 0.0
+    for _ in range(3):
+        t = time.perf_counter()
+        fn(edges[:n])
+        best = max(best, n / (time.perf_counter() - t))
+    return best, kind, f"{n} of the {len(edges)} step edges x3, best", fn
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU CrashDetection over the step's edges (rank 0 only)."""
+    if rank != 0:
+        return
+    S, D = c4_map(42)
+    xy = c4_nodes(S, 1000)
+    threads = os.cpu_count() or 1
+    # the same edge population as the GPU arm, rebuilt on the CPU for a bounded sample of nodes:
+    # tree edge + 25 rewire edges of the first `m` nodes (neighbours by the oracle's exact k-NN)
+    from oracle import loader as orc
+
+    m = 40_000
+    idx, _, _ = orc.knn(xy, xy[:m].astype(np.float64), KNN, grid=(MAP_SIZE, MAP_SIZE, 16), nthreads=threads)
+    src = np.repeat(xy[:m], KNN, axis=0)
+    edges = np.ascontiguousarray(np.concatenate([src, xy[idx.reshape(-1)]], 1), np.float32)
+    rate, kind, _, fn = cpu_edge_rate(S, D, edges, threads, budget_s=6.0)
+    total = args.steps + args.warmup
+    n = int(min(len(edges), max(100_000, rate * 100.0 / max(total, 1))))
+    for _ in range(args.warmup):
+        fn(edges[:n])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(edges[:n])
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{n} rewire edges (node -> 25-NN of the first nodes) per step"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_edges):
+    return {"workload": "C4: AM-RRT* on synthetic 4096x4096 map, 1e6 tree nodes; step = collision pass over "
+                        "999999 tree edges + 25e6 rewire (node -> 25-NN) edges, divisor 2, planes S|D",
+            "map": "4096x4096 seed 42", "nodes": N_NODES, "k": KNN, "divisor": DIVISOR, "edges_per_step": int(n_edges),
+            "l2_policy": "inputs larger than L2 (416 MB edge list per step)"}
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = Workload(local_rank, seed=rank)
+    ctx = wl.ctx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        wl.step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = ctx.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    ev0.record(wl.stream)
+    for _ in range(args.steps):
+        wl.step()
+    ev1.record(wl.stream)
+    barrier()
+    t_host1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches() - launches0
+    # keep the GPU busy a little longer if the timed region was too short for NVML's sampling period
+    if t_host1 - t_host0 < 0.25:
+        t_b0 = time.perf_counter()
+        while time.perf_counter() - t_b0 < 0.3:
+            for _ in range(50):
+                wl.step()
+            torch.cuda.synchronize()
+        t_host0, t_host1 = t_b0, time.perf_counter()
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary(t_host0, t_host1)
+
+    # max over ranks
+    t = torch.tensor([ms_total], dtype=torch.float64, device=wl.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = wl.n_edges * world / (ms_step * 1e-3)
+
+    # ---- e2e: host-buffer C-ABI call from pinned memory, H2D + kernel + D2H every step
+    e2e_steps = max(3, min(args.steps, 10))
+    h_edges = torch.empty((wl.n_edges, 4), dtype=torch.float32, pin_memory=True)
+    h_edges.copy_(wl.edges)
+    h_bits = torch.empty((wl.n_edges + 31) // 32, dtype=torch.int32, pin_memory=True)
+    import ctypes as C
+
+    def e2e_step():
+        ctx.call("edges_check", C.c_void_p(h_edges.data_ptr()), C.c_size_t(wl.n_edges), DIVISOR, 3, C.c_void_p(h_bits.data_ptr()))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous: returns after the verdict words are back on the host
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=wl.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    same = bool((h_bits.to(wl.dev) == wl.bits).all().item())
+    e2e = {"value": wl.n_edges * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": wl.n_edges * 16,
+           "d2h_bytes_per_step": int(h_bits.numel() * 4), "steps": e2e_steps, "matches_resident_run": same,
+           "api": "rtpp_edges_check (host buffers, pinned)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (only) kernel of the step
+    from oracle import loader as orc
+
+    edges_host = h_edges.numpy()
+    sample = edges_host[:: max(1, wl.n_edges // 2_000_000)]
+    probes_per_edge = orc.edges_nprobes_sum(sample, DIVISOR) / len(sample)
+    alg_bytes = wl.n_edges * (16 + 4 * probes_per_edge + 0.125)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_dram_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "edge_check_f32_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, burst)" if peaks else "fallback 6650",
+                "algorithmic_bytes_per_edge": 16 + 4 * probes_per_edge + 0.125, "mean_probes_per_edge": probes_per_edge,
+                "stream_only_GBs": wl.n_edges * 16.125 / (ms_step * 1e-3) / 1e9}
+
+    # ---- CPU baseline on this box's host cores (bounded sample of the same edges)
+    threads = os.cpu_count() or 1
+    cpu_rate, kind, sample_desc, fn = cpu_edge_rate(wl.S, wl.D, edges_host, threads)
+    # parity spot check of the timed path against the same CPU routine
+    chk = edges_host[:1_000_000]
+    got = np.unpackbits(wl.bits[: len(chk) // 32 + 1].cpu().numpy().view(np.uint8), bitorder="little")[: len(chk)]
+    parity_ok = bool(np.array_equal(got, fn(chk)))
+    cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample_desc,
+                    "verdicts_match_gpu": parity_ok}
+
+    extras = {}
+    if not args.no_extras:
+        extras = measure_extras(wl, torch)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(wl.n_edges), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_extras(wl, torch):
+    """Neighbour queries/s and tick latencies on the resident C4 state (outside the timed region)."""
+    ctx = wl.ctx
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(wl.stream)
+        for _ in range(reps):
+            fn()
+        e1.record(wl.stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n = len(wl.xy)
+    ms = timed(lambda: ctx.knn_nodes_dev(KNN, wl.knn_idx.data_ptr()), 5)
+    out["knn_queries_per_s"] = n / (ms * 1e-3)
+    out["knn_all_nodes_ms"] = ms
+    cost0 = np.full(n, 3.4e38, np.float32)
+    col0 = np.ones(n, np.uint8)
+    cost0[0], col0[0] = 0.0, 0
+    ctx.tree_set(wl.parent, cost0, col0)
+    ms = timed(lambda: ctx.tree_propagate_dev(0, DIVISOR, 3), 5)
+    out["propagate_1e6_tree_edges_ms"] = ms
+    out["propagate_edges_per_s"] = (n - 1) / (ms * 1e-3)
+    t0 = time.perf_counter()
+    sweeps = ctx.relax_dev(wl.knn_idx.data_ptr(), KNN, DIVISOR, 3, free_only=True)
+    torch.cuda.synchronize()
+    out["rewire_to_quiescence_ms"] = (time.perf_counter() - t0) * 1e3
+    out["rewire_sweeps"] = sweeps
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

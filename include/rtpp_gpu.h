@@ -137,6 +137,31 @@ RTPP_API int rtpp_knn_dev(rtpp_ctx *ctx, const double *d_qxy, size_t nq, int k, 
  * the reference's queries at tree nodes do: RTRRT.cpp:304, RTFMT.cpp:440). */
 RTPP_API int rtpp_knn_nodes_dev(rtpp_ctx *ctx, int k, int32_t *d_idx, double *d_d2);
 
+/* ---------------------------------------------------------------- tree costs (K4/K5) --------- */
+/* Per-node cost and parent link: RTrrt_NodeAttribute {cost, par} (RTRRT.h:108-113) with
+ * RTrrt_Cost {bool collision; float cost} (RTRRT.h:55-91), kept on the device as one 64-bit word
+ * per node (collision | cost bits | parent id) so that a relaxation is one atomicMin.
+ * set/get copy entries 0..n-1 (parent -1 = none). */
+RTPP_API int rtpp_tree_set(rtpp_ctx *ctx, const int32_t *parent, const float *cost, const uint8_t *collision, size_t n);
+RTPP_API int rtpp_tree_get(rtpp_ctx *ctx, int32_t *parent, float *cost, uint8_t *collision, size_t n);
+RTPP_API int rtpp_tree_words_dev(rtpp_ctx *ctx, unsigned long long **d_words);
+/* UpdateTree part (a), RTRRT.cpp:98-119: make new_root the root by reversing the parent chain
+ * new_root -> ... -> old_root; cost[new_root] = {0,0}. */
+RTPP_API int rtpp_tree_reroot(rtpp_ctx *ctx, int old_root, int new_root);
+/* UpdateTree part (b), RTRRT.cpp:121-135 (RTFMT.cpp:152-174, AMRRT.cpp:185-199, CDRT.cpp:764-796):
+ * BFS from root, cost[child] = cost[parent] + {CrashDetection(parent,child), |parent-child|} for
+ * every tree edge.  flags (n bytes, may be NULL): bit0 = collision went 0->1 (RT-FMT N_b,
+ * RTFMT.cpp:170-171), bit1 = cost grew, bit2 = cost shrank (CDRT.cpp:781-790).  *reached (may be
+ * NULL) = nodes reached from root. */
+RTPP_API int rtpp_tree_propagate(rtpp_ctx *ctx, int root, int divisor, int plane_mask, uint8_t *flags, int *reached);
+RTPP_API int rtpp_tree_propagate_dev(rtpp_ctx *ctx, int root, int divisor, int plane_mask, uint8_t *d_flags, int *reached);
+/* Rewire relaxations RTRRT.cpp:305-319,334-346 (AMRRT.cpp:497-510 with free_only = 1) over the
+ * directed edges x -> knn[x][j] of a resident k-NN table (n*k ids, -1 = none), repeated as
+ * Bellman-Ford sweeps until no cost word changes (at most max_sweeps).  The reference relaxes one
+ * queue element at a time; both reach the same collision-free costs at quiescence. */
+RTPP_API int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, int plane_mask, int free_only,
+                            int max_sweeps, int *sweeps_done);
+
 #ifdef __cplusplus
 }
 #endif

@@ -480,6 +480,12 @@ class RefAMRRT(OrcAMRRT):
         self.L.ref_amrrt_crash(self.h, _ptr(xyxy), C.c_longlong(len(xyxy)), _ptr(out))
         return out
 
+    def crash_mt(self, xyxy, nthreads):
+        xyxy = _c(xyxy, np.float32).reshape(-1, 4)
+        out = np.zeros(len(xyxy), np.uint8)
+        self.L.ref_amrrt_crash_mt(self.h, _ptr(xyxy), C.c_longlong(len(xyxy)), _ptr(out), int(nthreads))
+        return out
+
     def crash_start(self, xyxy):
         xyxy = _c(xyxy, np.float32).reshape(-1, 4)
         out = np.zeros(len(xyxy), np.uint8)

@@ -199,3 +199,32 @@ class Ctx:
 
     def knn_nodes_dev(self, k, d_idx, d_d2=0):
         self.call("knn_nodes_dev", int(k), C.c_void_p(d_idx), C.c_void_p(d_d2))
+
+    # ---- tree costs
+    def tree_set(self, parent, cost, col):
+        p, c, l = _c(parent, np.int32), _c(cost, np.float32), _c(col, np.uint8)
+        self.call("tree_set", _p(p), _p(c), _p(l), C.c_size_t(len(p)))
+
+    def tree_get(self, n=None):
+        n = self.nodes_count() if n is None else n
+        p, c, l = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self.call("tree_get", _p(p), _p(c), _p(l), C.c_size_t(n))
+        return p, c, l
+
+    def tree_reroot(self, old_root, new_root):
+        self.call("tree_reroot", int(old_root), int(new_root))
+
+    def tree_propagate(self, root, divisor, mask, want_flags=False):
+        n = self.nodes_count()
+        flags = np.zeros(n, np.uint8) if want_flags else None
+        reached = C.c_int()
+        self.call("tree_propagate", int(root), int(divisor), int(mask), _p(flags), C.byref(reached))
+        return reached.value, flags
+
+    def tree_propagate_dev(self, root, divisor, mask):
+        self.call("tree_propagate_dev", int(root), int(divisor), int(mask), None, None)
+
+    def relax_dev(self, d_knn_idx, k, divisor, mask, free_only=False, max_sweeps=10000):
+        sw = C.c_int()
+        self.call("relax_dev", C.c_void_p(d_knn_idx), int(k), int(divisor), int(mask), int(free_only), int(max_sweeps), C.byref(sw))
+        return sw.value

@@ -11,20 +11,9 @@
 #include <math_constants.h>
 
 #include "knn.cuh"
+#include "nodes.cuh"
 
 static constexpr int kTailMax = 512;
-
-struct NodeStore {
-    int shift = 4, gw = 0, gh = 0;
-    size_t capacity = 0;
-    int n = 0, n_sorted = 0;
-    float2 *xy = nullptr;     // [capacity]
-    float2 *sxy = nullptr;    // [capacity]
-    int *sid = nullptr;       // [capacity]
-    int *cell_of = nullptr;   // [capacity] scratch
-    int *cell_start = nullptr; // [gw*gh + 1]
-    int *cursor = nullptr;    // [gw*gh + 1]
-};
 
 __global__ void __launch_bounds__(256) grid_count_kernel(const float2 *__restrict__ xy, int n, int shift, int gw, int gh,
                                                         int *__restrict__ cell_of, int *__restrict__ count) {
@@ -122,6 +111,7 @@ void rtpp_nodes_destroy(rtpp_ctx *ctx) {
     NodeStore *s = ctx->nodes;
     if (!s) return;
     cudaFree(s->xy), cudaFree(s->sxy), cudaFree(s->sid), cudaFree(s->cell_of), cudaFree(s->cell_start), cudaFree(s->cursor);
+    cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
     delete s;
     ctx->nodes = nullptr;
 }
@@ -186,6 +176,8 @@ int rtpp_nodes_reset(rtpp_ctx *ctx, int cell_log2, size_t capacity, int domain_w
     RTPP_CK(ctx, cudaMalloc(&s->cell_of, capacity * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cell_start, m * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cursor, m * sizeof(int)));
+    RTPP_CK(ctx, cudaMalloc(&s->cp, capacity * sizeof(unsigned long long)));
+    RTPP_CK(ctx, cudaMemsetAsync(s->cp, 0xff, capacity * sizeof(unsigned long long), ctx->stream));
     RTPP_CK(ctx, cudaMemsetAsync(s->cell_start, 0, m * sizeof(int), ctx->stream));
     return RTPP_OK;
 }

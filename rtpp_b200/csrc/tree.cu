@@ -1,0 +1,363 @@
+// tree.cu — K4/K5: cost/parent words, tree re-rooting, level-synchronous cost propagation and the
+// wave-synchronous rewire relaxation.
+//
+// Replaces (reference file:line)
+//   R3  UpdateTree          RTRRT.cpp:92-136, RTFMT.cpp:92-176 (+N_b capture :167-171),
+//                           AMRRT.cpp:156-200, CDRT.cpp:764-796 (larger/smaller sets)
+//   R2  rewire relaxations  RTRRT.cpp:300-320,323-353; AMRRT.cpp:483-519 (free edges only)
+//   C1  RTrrt_Cost algebra  RTRRT.h:55-91
+//
+// propagate: (A) every tree edge (parent -> child) gets its weight {E(parent,child), |parent-child|}
+// in one fully parallel pass (verdicts do not depend on costs); (B) children lists are built by a
+// counting sort on the parent ids; (C) one cooperative, persistent kernel walks the tree level by
+// level, cost[child] = cost[parent] + w[child] strictly parent-before-child, so the binary32 sums
+// follow the tree order exactly as the reference's BFS does.
+// relax: edge weights of the k-NN graph once, then Bellman-Ford sweeps with one 64-bit atomicMin
+// per improving edge until no word changes.
+#include <cooperative_groups.h>
+#include <math_constants.h>
+
+#include "nodes.cuh"
+namespace cg = cooperative_groups;
+
+static int grid_for(rtpp_ctx *ctx, size_t n, int per_block = 256) {
+    size_t need = (n + per_block - 1) / per_block;
+    size_t cap = (size_t)ctx->sm_count * 8;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+__global__ void __launch_bounds__(256) tree_pack_kernel(const int *__restrict__ parent, const float *__restrict__ cost,
+                                                       const uint8_t *__restrict__ col, int n, cpword *__restrict__ cp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        cp[i] = cp_make(cost_pack(col[i] != 0, cost[i]), parent[i]);
+}
+__global__ void __launch_bounds__(256) tree_unpack_kernel(const cpword *__restrict__ cp, int n, int *__restrict__ parent,
+                                                         float *__restrict__ cost, uint8_t *__restrict__ col) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cpword w = cp[i];
+        parent[i] = cp_parent(w);
+        cost[i] = cost_val(cp_hi(w));
+        col[i] = cost_col(cp_hi(w));
+    }
+}
+
+// (A) + child counting.  w[i] = {E(parent,i), |parent - i|} packed like a cost.
+__global__ void __launch_bounds__(256)
+tree_edge_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const cpword *__restrict__ cp, int n, int root,
+                         float divisor, uint32_t *__restrict__ w, int *__restrict__ child_count) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = cp_parent(cp[i]);
+        uint32_t wi = 0;
+        if (i != root && p >= 0 && p < n) {
+            const float2 a = xy[p], b = xy[i];
+            wi = cost_pack(rt_edge_blocked(pl, a.x, a.y, b.x, b.y, divisor), rt_dist(a.x, a.y, b.x, b.y));
+            atomicAdd(&child_count[p], 1);
+        }
+        w[i] = wi;
+    }
+}
+
+__global__ void __launch_bounds__(1024) tree_scan_kernel(const int *count, int m, int *start, int *cursor) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x, per = (m + 1023) / 1024;
+    const int a = min(m, t * per), b = min(m, a + per);
+    int s = 0;
+    for (int i = a; i < b; i++) s += count[i];
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - s;
+    for (int i = a; i < b; i++) {
+        const int c = count[i];
+        start[i] = run;
+        cursor[i] = run;
+        run += c;
+    }
+    if (t == 1023) start[m] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) tree_children_kernel(const cpword *__restrict__ cp, int n, int root,
+                                                           int *__restrict__ cursor, int *__restrict__ children) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = cp_parent(cp[i]);
+        if (i != root && p >= 0 && p < n) children[atomicAdd(&cursor[p], 1)] = i;
+    }
+}
+
+// (C) persistent level-synchronous walk.  counters[0..2] rotate: level L reads [L%3], appends to
+// [(L+1)%3] and clears [(L+2)%3].  flags (optional): bit0 = collision went 0 -> 1 (RT-FMT's N_b,
+// RTFMT.cpp:170-171), bit1 = cost grew, bit2 = cost shrank (CDRT's larger/smaller sets,
+// CDRT.cpp:781-790).  counters[3] = number of nodes reached.
+__global__ void __launch_bounds__(256)
+tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int *__restrict__ children,
+                const uint32_t *__restrict__ w, cpword *__restrict__ cp, int *__restrict__ frontier, int capacity,
+                int *__restrict__ counters, uint8_t *__restrict__ flags) {
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (tid == 0) {
+        frontier[0] = root;
+        counters[0] = 1, counters[1] = 0, counters[2] = 0, counters[3] = 1;
+    }
+    grid.sync();
+    for (int level = 0;; level++) {
+        const int cur_n = counters[level % 3];
+        if (cur_n == 0) break;
+        int *cnt_next = &counters[(level + 1) % 3];
+        const int *cur = frontier + (size_t)(level & 1) * capacity;
+        int *nxt = frontier + (size_t)((level + 1) & 1) * capacity;
+        if (tid == 0) counters[(level + 2) % 3] = 0;
+        for (int f = tid; f < cur_n; f += nth) {
+            const int p = cur[f];
+            const uint32_t hp = cp_hi(cp[p]);
+            const int s = child_start[p], e = child_start[p + 1];
+            for (int j = s; j < e; j++) {
+                const int c = children[j];
+                const uint32_t hn = cost_add(hp, w[c]);
+                if (flags) {
+                    const uint32_t ho = cp_hi(cp[c]);
+                    flags[c] = (uint8_t)(((hn >> 31) & ~(ho >> 31) & 1u) | ((hn > ho) ? 2u : 0u) | ((hn < ho) ? 4u : 0u));
+                }
+                cp[c] = cp_make(hn, p);
+                nxt[atomicAdd(cnt_next, 1)] = c;
+            }
+            if (e > s) atomicAdd(&counters[3], e - s);
+        }
+        grid.sync();
+    }
+}
+
+// re-root (RTRRT.cpp:98-119): reverse the parent chain new_root -> ... -> old_root; cost[new_root] = {0,0}
+__global__ void tree_reroot_kernel(cpword *__restrict__ cp, int n, int old_root, int new_root) {
+    if (threadIdx.x || blockIdx.x) return;
+    int x = new_root, x_old = -1;
+    int guard = 0;
+    while (x != old_root && x >= 0 && guard++ < n) {
+        const cpword w = cp[x];
+        const int par = cp_parent(w);
+        cp[x] = cp_make(cp_hi(w), x_old);
+        x_old = x;
+        x = par;
+    }
+    if (x >= 0) cp[x] = cp_make(cp_hi(cp[x]), x_old);
+    cp[new_root] = cp_make(cost_pack(false, 0.0f), -1);
+}
+
+// relax phase 1: weights of the directed k-NN edges x -> knn[x][j]; 0xffffffff = no edge
+__global__ void __launch_bounds__(256)
+relax_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const int *__restrict__ knn, size_t n_edges, int k,
+                     float divisor, uint32_t *__restrict__ w) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(e / k), s = knn[e];
+        uint32_t we = 0xffffffffu;
+        if (s >= 0 && s != x) {
+            const float2 a = xy[x], b = xy[s];
+            we = cost_pack(rt_edge_blocked(pl, a.x, a.y, b.x, b.y, divisor), rt_dist(a.x, a.y, b.x, b.y));
+        }
+        w[e] = we;
+    }
+}
+
+// relax phase 2: one Bellman-Ford sweep.  c_new = cost[x] + w; if c_new < cost[s] (strict,
+// lexicographic: RTRRT.cpp:311) the word {c_new, x} replaces cost|parent of s by atomicMin.
+// free_only: AM-RRT* RewireRoot relaxes only over free edges and never to a colliding cost
+// (AMRRT.cpp:500-504).
+__global__ void __launch_bounds__(256)
+relax_sweep_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, size_t n_edges, int k, int free_only,
+                   cpword *cp, int *__restrict__ changed) {
+    bool any = false;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t we = w[e];
+        if (we == 0xffffffffu) continue;
+        if (free_only && (we >> 31)) continue;
+        const int x = (int)(e / k), s = knn[e];
+        const uint32_t hx = cp_hi(((volatile cpword *)cp)[x]);
+        if (hx == 0xffffffffu) continue; // x has no cost yet
+        const uint32_t hn = cost_add(hx, we);
+        if (free_only && (hn >> 31)) continue;
+        if (hn < cp_hi(((volatile cpword *)cp)[s])) {
+            const cpword neww = cp_make(hn, x);
+            const cpword prev = atomicMin(&cp[s], neww);
+            if (prev > neww && cp_hi(prev) > hn) any = true;
+        }
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) *changed = 1;
+}
+
+static int ensure_tree_scratch(rtpp_ctx *ctx, NodeStore *s) {
+    if (s->edge_w) return RTPP_OK;
+    RTPP_CK(ctx, cudaMalloc(&s->edge_w, s->capacity * 4));
+    RTPP_CK(ctx, cudaMalloc(&s->child_start, (s->capacity + 2) * 4));
+    RTPP_CK(ctx, cudaMalloc(&s->children, s->capacity * 4));
+    RTPP_CK(ctx, cudaMalloc(&s->frontier, 2 * s->capacity * 4));
+    RTPP_CK(ctx, cudaMalloc(&s->counters, 8 * 4));
+    return RTPP_OK;
+}
+
+extern "C" {
+
+int rtpp_tree_set(rtpp_ctx *ctx, const int32_t *parent, const float *cost, const uint8_t *collision, size_t n) {
+    if (!ctx || (n && (!parent || !cost || !collision))) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    if (n > (size_t)s->n) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "more tree entries than nodes");
+    if (n == 0) return RTPP_OK;
+    void *dp = nullptr, *dc = nullptr, *dl = nullptr;
+    int rc = rtpp_scratch(ctx, 0, n * 4, &dp);
+    if (rc) return rc;
+    rc = rtpp_scratch(ctx, 1, n * 4, &dc);
+    if (rc) return rc;
+    rc = rtpp_scratch(ctx, 2, n, &dl);
+    if (rc) return rc;
+    RTPP_CK(ctx, cudaMemcpyAsync(dp, parent, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RTPP_CK(ctx, cudaMemcpyAsync(dc, cost, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RTPP_CK(ctx, cudaMemcpyAsync(dl, collision, n, cudaMemcpyHostToDevice, ctx->stream));
+    tree_pack_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>((const int *)dp, (const float *)dc, (const uint8_t *)dl, (int)n, s->cp);
+    RTPP_LAUNCHED(ctx);
+    RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+int rtpp_tree_get(rtpp_ctx *ctx, int32_t *parent, float *cost, uint8_t *collision, size_t n) {
+    if (!ctx || (n && (!parent || !cost || !collision))) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    if (n > (size_t)s->n) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "more tree entries than nodes");
+    if (n == 0) return RTPP_OK;
+    void *dp = nullptr, *dc = nullptr, *dl = nullptr;
+    int rc = rtpp_scratch(ctx, 0, n * 4, &dp);
+    if (rc) return rc;
+    rc = rtpp_scratch(ctx, 1, n * 4, &dc);
+    if (rc) return rc;
+    rc = rtpp_scratch(ctx, 2, n, &dl);
+    if (rc) return rc;
+    tree_unpack_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(s->cp, (int)n, (int *)dp, (float *)dc, (uint8_t *)dl);
+    RTPP_LAUNCHED(ctx);
+    RTPP_CK(ctx, cudaMemcpyAsync(parent, dp, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RTPP_CK(ctx, cudaMemcpyAsync(cost, dc, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RTPP_CK(ctx, cudaMemcpyAsync(collision, dl, n, cudaMemcpyDeviceToHost, ctx->stream));
+    RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+int rtpp_tree_words_dev(rtpp_ctx *ctx, unsigned long long **d_words) {
+    if (!ctx || !d_words) return RTPP_ERR_INVALID;
+    if (!ctx->nodes) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    *d_words = ctx->nodes->cp;
+    return RTPP_OK;
+}
+
+int rtpp_tree_reroot(rtpp_ctx *ctx, int old_root, int new_root) {
+    if (!ctx) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    if (old_root < 0 || old_root >= s->n || new_root < 0 || new_root >= s->n) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad root id");
+    if (old_root == new_root) return RTPP_OK;
+    tree_reroot_kernel<<<1, 32, 0, ctx->stream>>>(s->cp, s->n, old_root, new_root);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+int rtpp_tree_propagate_dev(rtpp_ctx *ctx, int root, int divisor, int plane_mask, uint8_t *d_flags, int *reached) {
+    if (!ctx) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    if (root < 0 || root >= s->n) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad root id");
+    if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    PlaneView pv;
+    int rc = rtpp_select_plane(ctx, plane_mask, &pv);
+    if (rc) return rc;
+    rc = ensure_tree_scratch(ctx, s);
+    if (rc) return rc;
+    const int n = s->n;
+    // child_start doubles as the count array, then the scan turns it into starts; children cursor = frontier tail
+    int *cursor = s->frontier; // scratch before the BFS uses it
+    RTPP_CK(ctx, cudaMemsetAsync(s->child_start, 0, (size_t)(n + 2) * 4, ctx->stream));
+    if (d_flags) RTPP_CK(ctx, cudaMemsetAsync(d_flags, 0, n, ctx->stream));
+    tree_edge_weights_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pv, s->xy, s->cp, n, root, (float)divisor, s->edge_w, s->child_start);
+    RTPP_LAUNCHED(ctx);
+    tree_scan_kernel<<<1, 1024, 0, ctx->stream>>>(s->child_start, n, s->child_start, cursor);
+    RTPP_LAUNCHED(ctx);
+    tree_children_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(s->cp, n, root, cursor, s->children);
+    RTPP_LAUNCHED(ctx);
+    // persistent cooperative walk: one block for small trees (cheap syncs), else all SMs
+    int blocks = 1;
+    if (n > 16384) {
+        int per_sm = 0;
+        RTPP_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_bfs_kernel, 256, 0));
+        blocks = ctx->sm_count * (per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm));
+    }
+    int cap = (int)s->capacity;
+    const int *cs = s->child_start, *ch = s->children;
+    const uint32_t *w = s->edge_w;
+    cpword *cp = s->cp;
+    int *fr = s->frontier, *cn = s->counters;
+    int nn = n, rr = root;
+    void *args[] = {&nn, &rr, &cs, &ch, &w, &cp, &fr, &cap, &cn, &d_flags};
+    RTPP_CK(ctx, cudaLaunchCooperativeKernel((void *)tree_bfs_kernel, dim3(blocks), dim3(256), args, 0, ctx->stream));
+    ctx->launches++;
+    if (reached) {
+        RTPP_CK(ctx, cudaMemcpyAsync(reached, s->counters + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return RTPP_OK;
+}
+
+int rtpp_tree_propagate(rtpp_ctx *ctx, int root, int divisor, int plane_mask, uint8_t *flags, int *reached) {
+    if (!ctx) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    void *df = nullptr;
+    if (flags) {
+        int rc = rtpp_scratch(ctx, 3, (size_t)s->n + 1, &df);
+        if (rc) return rc;
+    }
+    int r = 0;
+    int rc = rtpp_tree_propagate_dev(ctx, root, divisor, plane_mask, (uint8_t *)df, &r);
+    if (rc) return rc;
+    if (reached) *reached = r;
+    if (flags) {
+        RTPP_CK(ctx, cudaMemcpyAsync(flags, df, s->n, cudaMemcpyDeviceToHost, ctx->stream));
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return RTPP_OK;
+}
+
+int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, int plane_mask, int free_only,
+                   int max_sweeps, int *sweeps_done) {
+    if (!ctx || !d_knn_idx) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    if (k < 1 || divisor <= 0 || max_sweeps < 1) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad relax arguments");
+    PlaneView pv;
+    int rc = rtpp_select_plane(ctx, plane_mask, &pv);
+    if (rc) return rc;
+    rc = ensure_tree_scratch(ctx, s);
+    if (rc) return rc;
+    const size_t ne = (size_t)s->n * k;
+    void *dw = nullptr;
+    rc = rtpp_scratch(ctx, 3, ne * 4, &dw);
+    if (rc) return rc;
+    relax_weights_kernel<<<grid_for(ctx, ne), 256, 0, ctx->stream>>>(pv, s->xy, d_knn_idx, ne, k, (float)divisor, (uint32_t *)dw);
+    RTPP_LAUNCHED(ctx);
+    int sweeps = 0;
+    for (; sweeps < max_sweeps;) {
+        RTPP_CK(ctx, cudaMemsetAsync(s->counters + 4, 0, 4, ctx->stream));
+        relax_sweep_kernel<<<grid_for(ctx, ne), 256, 0, ctx->stream>>>(d_knn_idx, (const uint32_t *)dw, ne, k, free_only, s->cp, s->counters + 4);
+        RTPP_LAUNCHED(ctx);
+        sweeps++;
+        int changed = 0;
+        RTPP_CK(ctx, cudaMemcpyAsync(&changed, s->counters + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!changed) break;
+    }
+    if (sweeps_done) *sweeps_done = sweeps;
+    return RTPP_OK;
+}
+
+} // extern "C"

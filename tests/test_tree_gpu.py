@@ -1,0 +1,130 @@
+"""K4/K5 parity: tree re-root + cost propagation (R3) and rewire relaxation (R2) vs the oracle."""
+import numpy as np
+import pytest
+
+from helpers import dyn_plane
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_points(rng, S, n):
+    H, W = S.shape
+    out = np.zeros((0, 2), np.float32)
+    while len(out) < n:
+        p = (rng.random((2 * n, 2), dtype=np.float32) * np.array([W, H], np.float32)).astype(np.float32)
+        ok = S[p[:, 1].astype(np.int32), p[:, 0].astype(np.int32)] == 0
+        out = np.concatenate([out, p[ok]])
+    return np.ascontiguousarray(out[:n])
+
+
+def _device_knn_table(ctx, n, k):
+    d_idx = ctx.dev_alloc(n * k * 4)
+    ctx.knn_nodes_dev(k, d_idx)
+    idx = np.zeros((n, k), np.int32)
+    ctx.d2h(idx, d_idx)
+    ctx.sync()
+    return d_idx, idx
+
+
+def _random_tree(idx):
+    """parent = nearest neighbour with a smaller id (node 0 = root); nodes without one hang off 0."""
+    n, k = idx.shape
+    earlier = (idx < np.arange(n)[:, None]) & (idx >= 0)
+    first = np.argmax(earlier, axis=1)
+    par = np.where(earlier.any(1), idx[np.arange(n), first], 0).astype(np.int32)
+    par[0] = -1
+    return par
+
+
+@pytest.mark.parametrize("name,n,divisor", [("MESS6", 3000, 5), ("GAME0", 60000, 5), ("GAME0", 60000, 2)])
+def test_propagate_and_relax(ctx, oracle, name, n, divisor):
+    S = oracle.load_map(name)
+    H, W = S.shape
+    rng = np.random.default_rng(n + divisor)
+    D = dyn_plane(S.shape, rng, n_blobs=8)
+    ctx.map_set_plane(1, S)
+    ctx.map_set_plane(2, D)
+    xy = _free_points(rng, S, n)
+    ctx.nodes_reset(4, n, W, H)
+    ctx.nodes_append(xy)
+    k = 25
+    d_idx, idx = _device_knn_table(ctx, n, k)
+    par = _random_tree(idx)
+    cost0 = np.full(n, 3.4e38, np.float32)
+    col0 = np.ones(n, np.uint8)
+    cost0[0], col0[0] = 0.0, 0
+    ctx.tree_set(par, cost0, col0)
+
+    # ---- R3 propagate
+    reached, flags = ctx.tree_propagate(0, divisor, 3, want_flags=True)
+    gp, gc, gl = ctx.tree_get()
+    oc, ol, oreached = oracle.tree_propagate(S, D, xy, par, 0, divisor, 3, cost0, col0)
+    assert reached == oreached == n
+    assert np.array_equal(gp, par)
+    assert np.array_equal(gl, ol)
+    assert np.array_equal(gc.view(np.uint32), oc.view(np.uint32))
+    assert 0 < ol.mean() < 1
+    # flags: nothing became blocked relative to the all-blocked start; every cost shrank
+    assert not (flags & 1).any() and ((flags[1:] & 4) == 4).all()
+
+    # ---- new dynamic plane: N_b capture (RT-FMT) and a second propagate
+    D2 = dyn_plane(S.shape, rng, n_blobs=10)
+    ctx.map_set_plane(2, D2)
+    _, flags = ctx.tree_propagate(0, divisor, 3, want_flags=True)
+    gp2, gc2, gl2 = ctx.tree_get()
+    oc2, ol2, _ = oracle.tree_propagate(S, D2, xy, par, 0, divisor, 3, oc, ol)
+    assert np.array_equal(gl2, ol2) and np.array_equal(gc2.view(np.uint32), oc2.view(np.uint32))
+    assert np.array_equal((flags & 1).astype(bool), (ol2 == 1) & (ol == 0))
+
+    # ---- R2 relax to quiescence over the k-NN graph
+    sweeps = ctx.relax_dev(d_idx, k, divisor, 3)
+    rp, rc, rl = ctx.tree_get()
+    fc, fl, fp, osw = oracle.relax_fixpoint(S, D2, xy, idx, divisor, 3, oc2, ol2, par)
+    assert sweeps >= 1 and osw >= 1
+    assert np.array_equal(rl, fl)
+    free = fl == 0
+    assert np.array_equal(rc[free].view(np.uint32), fc[free].view(np.uint32))
+    # every parent explains its child's cost exactly (tree consistency of the relaxed links)
+    ctx.dev_free(d_idx)
+
+
+def test_reroot_matches_oracle_planner(ctx, oracle):
+    """Grow a tree with the oracle's RT-RRT*, move the agent, and compare re-root + re-cost."""
+    S = oracle.load_map("MESS6")
+    H, W = S.shape
+    orc = oracle.OrcRTRRT(S)
+    orc.set_clock(2000)
+    orc.set_agent(720, 720)
+    r = oracle.rand31(5, 4000000)
+    pos = 0
+    for _ in range(6):
+        orc.update_tree()
+        pts, offs = orc.presample(r[pos:], 30000)
+        used = orc.expand_rewiring(50, pts)
+        pos += int(offs[used])
+    xy, par, cost, col = orc.dump()
+    n = len(xy)
+    assert n > 300
+    ctx.map_set_plane(1, S)
+    ctx.map_clear_plane(2)
+    ctx.nodes_reset(3, n, W, H)
+    ctx.nodes_append(xy)
+    ctx.tree_set(par, cost, col)
+    # move the agent next to some far node; UpdateTree re-roots at the nearest node
+    target = xy[n // 2]
+    orc.set_agent(float(target[0]), float(target[1]))
+    D = dyn_plane(S.shape, np.random.default_rng(2), n_blobs=5)
+    orc.set_dobs(D)
+    ctx.map_set_plane(2, D)
+    orc.update_tree()
+    idx, _, _ = ctx.knn(np.array([target], np.float64), 1)
+    new_root = int(idx[0, 0])
+    old_root = int(np.flatnonzero(par < 0)[0])
+    ctx.tree_reroot(old_root, new_root)
+    ctx.tree_propagate(new_root, 5, 3)
+    gp, gc, gl = ctx.tree_get()
+    oxy, opar, ocost, ocol = orc.dump()
+    assert np.array_equal(oxy, xy)
+    assert np.array_equal(gp, opar)
+    assert np.array_equal(gl, ocol)
+    assert np.array_equal(gc.view(np.uint32), ocost.view(np.uint32))
