@@ -71,6 +71,8 @@ struct rtpp_ctx {
 
 int rtpp_scratch(rtpp_ctx *ctx, int slot, size_t bytes, void **out);
 int rtpp_select_plane(rtpp_ctx *ctx, int plane_mask, PlaneView *pv);
+struct MarchThresholds;
+void rtpp_march_thresholds(int divisor, MarchThresholds *out);
 
 // ------------------------------------------------------------------------------------------------
 // Exact arithmetic (bit-equal to the reference's scalar C++ built without FMA contraction)
@@ -110,6 +112,39 @@ __device__ __forceinline__ bool rt_probe(const PlaneView &p, int row, int col) {
     return (word >> (col & 31)) & 1u;
 }
 
+// Probe with no bounds test: only for coordinates proven to be inside the plane.
+__device__ __forceinline__ uint32_t rt_probe_word(const PlaneView &p, int row, int col) {
+    return __ldg(p.w + ((((unsigned)(row >> 5) * p.tilesX + (col >> 5)) << 5) + (row & 31))) >> (col & 31);
+}
+// An edge is "safe" when both end points lie in [0, W-1) x [0, H-1): every interpolated point
+// fl(fl(a*t) + fl((1-t)*b)) then stays below the plane size (W, H <= 2^20), so its probes need no
+// bounds test.
+__device__ __forceinline__ bool rt_edge_safe(const PlaneView &p, float ax, float ay, float bx, float by) {
+    const float wx = (float)(p.W - 1), wy = (float)(p.H - 1);
+    return ax >= 0.f && ay >= 0.f && bx >= 0.f && by >= 0.f && ax < wx && bx < wx && ay < wy && by < wy;
+}
+
+// The march resolution P = rt_pow2_floor(rt_march_M(sqrt(s), divisor)) is a monotone step function
+// of the squared length s = dx*dx + dy*dy (sqrt, divide, add and truncate are all monotone), so for
+// short edges it is read off four thresholds computed once on the host with the same IEEE
+// arithmetic: P = 2 below t[0], 4 below t[1], 8 below t[2], 16 below t[3]; longer edges take the
+// exact sqrt/divide path.  This removes the sqrt and divide sequences (and their slow paths for
+// zero-length edges, e.g. a node against itself) from the common case.
+struct MarchThresholds {
+    float t[4];
+    float divisor;
+};
+__device__ __forceinline__ int rt_march_P(const MarchThresholds &mt, float s) {
+    if (s < mt.t[3]) return s < mt.t[1] ? (s < mt.t[0] ? 2 : 4) : (s < mt.t[2] ? 8 : 16);
+    return rt_pow2_floor(rt_march_M(__fsqrt_rn(s), mt.divisor));
+}
+// 1/P exactly for P = 2^e: exponent field 127 - e
+__device__ __forceinline__ float rt_inv_pow2(int P) { return __int_as_float((127 - (31 - __clz(P))) << 23); }
+__device__ __forceinline__ float rt_sqlen(float ax, float ay, float bx, float by) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
 // Interior probe j of P for the dyadic march (reference RTRRT.cpp:214-217):
 //   t = j/P;  x = (int)(ps.x*t + (1-t)*pe.x);  y likewise;  unfused, truncating.
 __device__ __forceinline__ bool rt_probe_interior(const PlaneView &p, float psx, float psy, float pex, float pey,
@@ -123,11 +158,21 @@ __device__ __forceinline__ bool rt_probe_interior(const PlaneView &p, float psx,
 // Whole edge by one thread (used inside the planner engines and the relax kernels, where edges
 // are short).  Returns the reference's CrashDetection verdict.
 __device__ __forceinline__ bool rt_edge_blocked(const PlaneView &p, float psx, float psy, float pex, float pey,
-                                                float divisor) {
+                                                const MarchThresholds &mt) {
     bool hit = rt_probe(p, __float2int_rz(psy), __float2int_rz(psx)) | rt_probe(p, __float2int_rz(pey), __float2int_rz(pex));
     if (hit) return true;
-    int P = rt_pow2_floor(rt_march_M(rt_dist(psx, psy, pex, pey), divisor));
-    float inv = 1.0f / (float)P; // exact: P is a power of two
+    const int P = rt_march_P(mt, rt_sqlen(psx, psy, pex, pey));
+    const float inv = rt_inv_pow2(P);
+    if (rt_edge_safe(p, psx, psy, pex, pey)) {
+        uint32_t acc = 0;
+        for (int j = 1; j < P; j++) {
+            const float t = __fmul_rn((float)j, inv), omt = __fsub_rn(1.0f, t);
+            const int x = __float2int_rz(__fadd_rn(__fmul_rn(psx, t), __fmul_rn(omt, pex)));
+            const int y = __float2int_rz(__fadd_rn(__fmul_rn(psy, t), __fmul_rn(omt, pey)));
+            acc |= rt_probe_word(p, y, x);
+        }
+        return acc & 1u;
+    }
     for (int j = 1; j < P; j++) hit |= rt_probe_interior(p, psx, psy, pex, pey, __fmul_rn((float)j, inv));
     return hit;
 }

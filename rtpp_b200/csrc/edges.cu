@@ -21,7 +21,7 @@
 static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 32 -> warp marches
 
 __global__ void __launch_bounds__(256)
-edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, float divisor,
+edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, MarchThresholds mt,
                       uint32_t *__restrict__ out_bits) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -30,28 +30,45 @@ edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, 
     const size_t nwords = (n + 31) >> 5;
     for (size_t w = warp0; w < nwords; w += nwarps) {
         const size_t i = (w << 5) + lane;
-        bool blocked = false;
+        uint32_t acc = 0; // bit 0 = blocked
         int P = 1;
+        bool safe = true;
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) {
             e = ld_stream_f4(edges + i);
-            blocked = rt_probe(pl, __float2int_rz(e.y), __float2int_rz(e.x)) |
+            safe = rt_edge_safe(pl, e.x, e.y, e.z, e.w);
+            if (safe)
+                acc = rt_probe_word(pl, __float2int_rz(e.y), __float2int_rz(e.x)) |
+                      rt_probe_word(pl, __float2int_rz(e.w), __float2int_rz(e.z));
+            else
+                acc = rt_probe(pl, __float2int_rz(e.y), __float2int_rz(e.x)) |
                       rt_probe(pl, __float2int_rz(e.w), __float2int_rz(e.z));
-            P = rt_pow2_floor(rt_march_M(rt_dist(e.x, e.y, e.z, e.w), divisor));
+            P = rt_march_P(mt, rt_sqlen(e.x, e.y, e.z, e.w));
         }
-        if (!blocked && P > 1 && P <= kShortMaxP) {
-            const float inv = 1.0f / (float)P;
+        acc &= 1u;
+        if (!acc && P <= kShortMaxP) {
+            const float inv = rt_inv_pow2(P);
+            if (safe) {
 #pragma unroll 4
-            for (int j = 1; j < P; j++) blocked |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+                for (int j = 1; j < P; j++) {
+                    const float t = __fmul_rn((float)j, inv), omt = __fsub_rn(1.0f, t);
+                    const int x = __float2int_rz(__fadd_rn(__fmul_rn(e.x, t), __fmul_rn(omt, e.z)));
+                    const int y = __float2int_rz(__fadd_rn(__fmul_rn(e.y, t), __fmul_rn(omt, e.w)));
+                    acc |= rt_probe_word(pl, y, x);
+                }
+                acc &= 1u;
+            } else {
+                for (int j = 1; j < P; j++) acc |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+            }
         }
-        unsigned longmask = __ballot_sync(full, !blocked && P > kShortMaxP);
+        unsigned longmask = __ballot_sync(full, !acc && P > kShortMaxP);
         while (longmask) {
             const int src = __ffs(longmask) - 1;
             longmask &= longmask - 1;
             const float sx = __shfl_sync(full, e.x, src), sy = __shfl_sync(full, e.y, src);
             const float tx = __shfl_sync(full, e.z, src), ty = __shfl_sync(full, e.w, src);
             const int Ps = __shfl_sync(full, P, src);
-            const float inv = 1.0f / (float)Ps;
+            const float inv = rt_inv_pow2(Ps);
             bool hit = false;
             for (int j0 = 1; j0 < Ps; j0 += 32) { // warp-uniform trip count, early exit per chunk
                 const int j = j0 + lane;
@@ -61,9 +78,9 @@ edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, 
                     break;
                 }
             }
-            if (lane == src) blocked = hit;
+            if (lane == src) acc = hit;
         }
-        const unsigned bits = __ballot_sync(full, blocked);
+        const unsigned bits = __ballot_sync(full, acc != 0);
         if (lane == 0) out_bits[w] = bits;
     }
 }
@@ -196,6 +213,33 @@ __global__ void __launch_bounds__(256) dist_kernel(const float4 *__restrict__ e,
     }
 }
 
+// March thresholds (see common.cuh): smallest squared length s with M(s) >= 4, 8, 16, 32, found by
+// bisection over the float bit patterns with the same IEEE binary32 operations as the kernels
+// (host code is built without FMA contraction or fast-math).
+static int host_march_M(float s, int divisor) {
+    volatile float len = sqrtf(s);
+    volatile float q = len / (float)divisor;
+    volatile float v = q + 2.0f;
+    return (int)v;
+}
+void rtpp_march_thresholds(int divisor, MarchThresholds *out) {
+    for (int m = 0; m < 4; m++) {
+        const int target = 4 << m;
+        const float s_hi = 1.0e12f; // len 1e6: M is far above every target and still fits an int
+        uint32_t lo = 0, hi;        // invariant: M(lo) < target <= M(hi)
+        memcpy(&hi, &s_hi, 4);
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            float s;
+            memcpy(&s, &mid, 4);
+            if (host_march_M(s, divisor) >= target) hi = mid;
+            else lo = mid;
+        }
+        memcpy(&out->t[m], &hi, 4);
+    }
+    out->divisor = (float)divisor;
+}
+
 // grid sizing: a multiple of the SM count, enough resident warps to cover L2 latency
 static int edge_grid(rtpp_ctx *ctx, size_t n, int per_block) {
     size_t need = (n + per_block - 1) / per_block;
@@ -213,7 +257,9 @@ int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divis
     int rc = rtpp_select_plane(ctx, plane_mask, &pv);
     if (rc) return rc;
     if (n == 0) return RTPP_OK;
-    edge_check_f32_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, (float)divisor, d_bits);
+    MarchThresholds mt;
+    rtpp_march_thresholds(divisor, &mt);
+    edge_check_f32_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }

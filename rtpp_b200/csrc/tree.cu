@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) tree_unpack_kernel(const cpword *__restri
 // (A) + child counting.  w[i] = {E(parent,i), |parent - i|} packed like a cost.
 __global__ void __launch_bounds__(256)
 tree_edge_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const cpword *__restrict__ cp, int n, int root,
-                         float divisor, uint32_t *__restrict__ w, int *__restrict__ child_count) {
+                         MarchThresholds divisor, uint32_t *__restrict__ w, int *__restrict__ child_count) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int p = cp_parent(cp[i]);
         uint32_t wi = 0;
@@ -151,7 +151,7 @@ __global__ void tree_reroot_kernel(cpword *__restrict__ cp, int n, int old_root,
 // relax phase 1: weights of the directed k-NN edges x -> knn[x][j]; 0xffffffff = no edge
 __global__ void __launch_bounds__(256)
 relax_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const int *__restrict__ knn, size_t n_edges, int k,
-                     float divisor, uint32_t *__restrict__ w) {
+                     MarchThresholds divisor, uint32_t *__restrict__ w) {
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(e / k), s = knn[e];
         uint32_t we = 0xffffffffu;
@@ -275,11 +275,13 @@ int rtpp_tree_propagate_dev(rtpp_ctx *ctx, int root, int divisor, int plane_mask
     rc = ensure_tree_scratch(ctx, s);
     if (rc) return rc;
     const int n = s->n;
+    MarchThresholds mt;
+    rtpp_march_thresholds(divisor, &mt);
     // child_start doubles as the count array, then the scan turns it into starts; children cursor = frontier tail
     int *cursor = s->frontier; // scratch before the BFS uses it
     RTPP_CK(ctx, cudaMemsetAsync(s->child_start, 0, (size_t)(n + 2) * 4, ctx->stream));
     if (d_flags) RTPP_CK(ctx, cudaMemsetAsync(d_flags, 0, n, ctx->stream));
-    tree_edge_weights_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pv, s->xy, s->cp, n, root, (float)divisor, s->edge_w, s->child_start);
+    tree_edge_weights_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pv, s->xy, s->cp, n, root, mt, s->edge_w, s->child_start);
     RTPP_LAUNCHED(ctx);
     tree_scan_kernel<<<1, 1024, 0, ctx->stream>>>(s->child_start, n, s->child_start, cursor);
     RTPP_LAUNCHED(ctx);
@@ -340,10 +342,12 @@ int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, 
     rc = ensure_tree_scratch(ctx, s);
     if (rc) return rc;
     const size_t ne = (size_t)s->n * k;
+    MarchThresholds mt;
+    rtpp_march_thresholds(divisor, &mt);
     void *dw = nullptr;
     rc = rtpp_scratch(ctx, 3, ne * 4, &dw);
     if (rc) return rc;
-    relax_weights_kernel<<<grid_for(ctx, ne), 256, 0, ctx->stream>>>(pv, s->xy, d_knn_idx, ne, k, (float)divisor, (uint32_t *)dw);
+    relax_weights_kernel<<<grid_for(ctx, ne), 256, 0, ctx->stream>>>(pv, s->xy, d_knn_idx, ne, k, mt, (uint32_t *)dw);
     RTPP_LAUNCHED(ctx);
     int sweeps = 0;
     for (; sweeps < max_sweeps;) {
