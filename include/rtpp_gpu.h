@@ -162,6 +162,38 @@ RTPP_API int rtpp_tree_propagate_dev(rtpp_ctx *ctx, int root, int divisor, int p
 RTPP_API int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, int plane_mask, int free_only,
                             int max_sweeps, int *sweeps_done);
 
+/* ---------------------------------------------------------------- planner engines ----------- */
+/* Sequential-exact replanning loops on the GPU: one warp runs one planner instance with the
+ * reference's own queue order (lanes = the 25 neighbours of the popped node), thousands of
+ * instances (map x start/goal x seed scenarios) run side by side.  planner_kind 1 = RT-RRT*:
+ *   rtpp_engine_init_instances  = SetAgent on an empty planner + SetGoal   RTRRT.cpp:11-55
+ *   rtpp_engine_set_inputs      = SetAgent/SetGoal on a live planner + the sample points the
+ *                                 host-side sampler (RTRRT.cpp:234-262) drew for the next call
+ *   rtpp_engine_tick            = UpdateTree RTRRT.cpp:92-136, ExpandRewiring(run_ms)
+ *                                 RTRRT.cpp:226-355, GetPath RTRRT.cpp:356-400 (each optional)
+ * The wall-clock gates of the reference become a virtual clock: the k-th clock read of an instance
+ * returns k*dt_ns (the oracle uses the same rule, so runs are reproducible and comparable).
+ * Each instance owns node_capacity nodes, a 2^cell_log2-pixel hash over domain_w x domain_h, its
+ * queues and max_samples sample slots.  Up to 16 map slots hold the planes. */
+typedef struct rtpp_engine rtpp_engine;
+RTPP_API int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int node_capacity, int cell_log2,
+                                int domain_w, int domain_h, int max_samples, rtpp_engine **out);
+RTPP_API int rtpp_engine_destroy(rtpp_engine *e);
+/* plane 1 = static (Obsmap), 2 = dynamic (DObsmap; src NULL = all free) of map slot 0..15 */
+RTPP_API int rtpp_engine_set_map(rtpp_engine *e, int slot, int plane, const uint8_t *rowmajor, int W, int H);
+RTPP_API int rtpp_engine_init_instances(rtpp_engine *e, const int32_t *map_slot, const float *agent_xy, const float *goal_xy);
+RTPP_API int rtpp_engine_set_inputs(rtpp_engine *e, const float *agent_xy, const float *goal_xy, const float *samples_xy,
+                                    const int32_t *n_samples);
+RTPP_API int rtpp_engine_tick(rtpp_engine *e, int do_update_tree, long run_ms, long long dt_ns, int do_get_path);
+/* 16 int64 per instance: n_nodes, root, samples_used, clock_reads, iterations, pops_r, pops_s,
+ * qr_size, qs_size, status (0 ok, 1 node store full, 2 queue overflow), path_len, path_collision,
+ * path_cost (float bits), c_base (float bits), 0, 0 */
+RTPP_API int rtpp_engine_read_stats(rtpp_engine *e, long long *out16);
+RTPP_API int rtpp_engine_read_tree(rtpp_engine *e, int inst, int max_nodes, float *xy, int32_t *parent, float *cost,
+                                   uint8_t *collision, int *n_out);
+/* path of the last GetPath: node ids root..entry then -2 for the goal point; *len_out = length */
+RTPP_API int rtpp_engine_read_path(rtpp_engine *e, int inst, int max_len, int32_t *ids, int *len_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -435,7 +435,11 @@ struct RTRRT {
     Pt sample(RandStream &rs) {
         float p0 = rs.u();
         float rx, ry;
-        if (p0 < 0.1f || c_base < 0) {
+        // Guard: when c_base < |goal - root| (e.g. the agent moved since the last
+        // GetPath) the reference's ellipse has b = sqrt(negative) = NaN and its rejection loop never
+        // terminates.  Defined behaviour here and in the product's host sampler: sample uniformly.
+        const bool degenerate = c_base >= 0 && c_base < dist(goal, root);
+        if (p0 < 0.1f || c_base < 0 || degenerate) {
             rx = rs.u() * map.W;
             ry = rs.u() * map.H;
         } else {

@@ -228,3 +228,75 @@ class Ctx:
         sw = C.c_int()
         self.call("relax_dev", C.c_void_p(d_knn_idx), int(k), int(divisor), int(mask), int(free_only), int(max_sweeps), C.byref(sw))
         return sw.value
+
+
+class Engine:
+    """ctypes mirror of the rtpp_engine_* entry points (planner_kind 1 = RT-RRT*)."""
+
+    def __init__(self, ctx, n_instances, node_capacity, cell_log2, domain_w, domain_h, max_samples, kind=1):
+        self.ctx, self.L = ctx, ctx.L
+        self.n, self.cap, self.max_samples = n_instances, node_capacity, max_samples
+        h = C.c_void_p()
+        ctx._ck(self.L.rtpp_engine_create(ctx.h, kind, n_instances, node_capacity, cell_log2, domain_w, domain_h, max_samples, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.rtpp_engine_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        self.ctx._ck(rc)
+
+    def set_map(self, slot, plane, rowmajor, shape=None):
+        if rowmajor is None:
+            self._ck(self.L.rtpp_engine_set_map(self.h, slot, plane, None, 0, 0))
+        else:
+            a = _c(rowmajor, np.uint8)
+            self._ck(self.L.rtpp_engine_set_map(self.h, slot, plane, _p(a), a.shape[1], a.shape[0]))
+
+    def init_instances(self, map_slot, agent_xy, goal_xy):
+        s, a, g = _c(map_slot, np.int32), _c(agent_xy, np.float32).reshape(-1, 2), _c(goal_xy, np.float32).reshape(-1, 2)
+        assert len(s) == len(a) == len(g) == self.n
+        self._ck(self.L.rtpp_engine_init_instances(self.h, _p(s), _p(a), _p(g)))
+
+    def set_inputs(self, agent_xy=None, goal_xy=None, samples=None, n_samples=None):
+        a = None if agent_xy is None else _c(agent_xy, np.float32).reshape(self.n, 2)
+        g = None if goal_xy is None else _c(goal_xy, np.float32).reshape(self.n, 2)
+        sm = None if samples is None else _c(samples, np.float32).reshape(self.n, self.max_samples, 2)
+        ns = None if n_samples is None else _c(n_samples, np.int32)
+        self._ck(self.L.rtpp_engine_set_inputs(self.h, _p(a), _p(g), _p(sm), _p(ns)))
+
+    def tick(self, update_tree=True, run_ms=50, dt_ns=100000, get_path=False):
+        self._ck(self.L.rtpp_engine_tick(self.h, int(update_tree), C.c_long(run_ms), C.c_longlong(dt_ns), int(get_path)))
+
+    STAT = ["n_nodes", "root", "samples_used", "clock_reads", "iters", "pops_r", "pops_s", "qr_size", "qs_size", "status",
+            "path_len", "path_col", "path_cost_bits", "c_base_bits"]
+
+    def stats(self):
+        out = np.zeros((self.n, 16), np.int64)
+        self._ck(self.L.rtpp_engine_read_stats(self.h, _p(out)))
+        return out
+
+    def stats_dict(self, inst=0):
+        row = self.stats()[inst]
+        d = dict(zip(self.STAT, row.tolist()))
+        d["path_cost"] = float(np.array([d.pop("path_cost_bits")], np.uint32).view(np.float32)[0])
+        d["c_base"] = float(np.array([d.pop("c_base_bits")], np.uint32).view(np.float32)[0])
+        return d
+
+    def read_tree(self, inst=0):
+        n = C.c_int()
+        self._ck(self.L.rtpp_engine_read_tree(self.h, inst, 0, None, None, None, None, C.byref(n)))
+        n = n.value
+        xy, par = np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+        cost, col = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        m = C.c_int()
+        self._ck(self.L.rtpp_engine_read_tree(self.h, inst, n, _p(xy), _p(par), _p(cost), _p(col), C.byref(m)))
+        return xy, par, cost, col
+
+    def read_path(self, inst=0, cap=2048):
+        ids = np.zeros(cap, np.int32)
+        n = C.c_int()
+        self._ck(self.L.rtpp_engine_read_path(self.h, inst, cap, _p(ids), C.byref(n)))
+        return ids[: min(n.value, cap)]

@@ -177,6 +177,23 @@ __device__ __forceinline__ bool rt_edge_blocked(const PlaneView &p, float psx, f
     return hit;
 }
 
+// Whole edge by one warp (all lanes pass the same edge): lanes stride over the interior probes and
+// OR-reduce; for long edges such as goal <-> root (reference RTRRT.cpp:362).
+__device__ __forceinline__ bool rt_edge_blocked_warp(const PlaneView &p, float psx, float psy, float pex, float pey,
+                                                     const MarchThresholds &mt) {
+    const int lane = threadIdx.x & 31;
+    if (rt_probe(p, __float2int_rz(psy), __float2int_rz(psx)) | rt_probe(p, __float2int_rz(pey), __float2int_rz(pex))) return true;
+    const int P = rt_march_P(mt, rt_sqlen(psx, psy, pex, pey));
+    const float inv = rt_inv_pow2(P);
+    for (int j0 = 1; j0 < P; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        if (j < P) hit = rt_probe_interior(p, psx, psy, pex, pey, __fmul_rn((float)j, inv));
+        if (__any_sync(0xffffffffu, hit)) return true;
+    }
+    return false;
+}
+
 // streaming 16-byte load that does not allocate in L1 (edge lists are read once; L1 is kept for
 // the bit-plane lines)
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *ptr) {

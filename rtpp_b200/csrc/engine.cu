@@ -1,0 +1,726 @@
+// engine.cu — sequential-exact planner engines: one warp runs one planner instance.
+//
+// The reference's replanning loops are sequential queues of tiny work items (pop a node, 25-NN,
+// 25 edge checks, 25 relaxations: RTRRT.cpp:226-355).  Batching them changes intermediate states,
+// so for drop-in parity the loops keep their order and the GPU parallelises *inside* a work item
+// (lanes = the 25 neighbours / the k-NN scan / the ray march) and *across* planner instances
+// (map x start/goal x seed scenarios: thousands of warps).  Results are bit-identical to the
+// reference run under the same virtual clock and injected samples (tests/test_engine_gpu.py).
+//
+// RT-RRT* engine (planner_kind 1):
+//   SetAgent/SetGoal   RTRRT.cpp:11-55        -> rtpp_engine_init_instances / rtpp_engine_set_agents
+//   UpdateTree         RTRRT.cpp:92-136       -> update_tree()   (re-root + BFS re-cost, R3)
+//   ExpandRewiring     RTRRT.cpp:226-355      -> expand_rewiring() (R1 choose-parent, R2 rewires)
+//   GetPath            RTRRT.cpp:356-400      -> get_path()      (P1, goal-entry branch)
+// The uniform/informed sampler (RTRRT.cpp:234-262) stays on the host (glibc transcendentals); the
+// engine consumes pre-drawn sample points.  Wall-clock gates (RTRRT.cpp:228-230,300,329) become
+// the virtual clock "k-th read returns k*dt" shared with the oracle.
+#include <float.h>
+#include <math_constants.h>
+
+#include "nodes.cuh"
+
+#define FULL 0xffffffffu
+
+struct EngInst {
+    int map_slot;
+    int n, n_sorted;
+    int root;
+    float2 agent, goal;
+    float c_base;
+    int qr_head, qr_tail, qs_head, qs_tail, qs_epoch;
+    long long clk_n;
+    int samp_pos, samp_n;
+    long long iters, pops_r, pops_s;
+    int status; // 0 ok; 1 node store full; 2 queue overflow
+    int path_len, path_col;
+    float path_cost;
+};
+
+struct EngView {
+    int n_inst, cap, qr_cap, max_samples, path_cap;
+    int gw, gh, shift, ncells;
+    EngInst *inst;
+    float2 *xy, *sxy;
+    cpword *cp;
+    int *sid, *cell_of, *cell_start, *cursor;
+    int *qr, *qs, *qs_mark;
+    int *child_start, *children, *frontier;
+    float2 *samples;
+    int *path;
+    PlaneView planes[16]; // merged S|D plane per map slot
+    int divisor;
+};
+
+struct rtpp_engine {
+    rtpp_ctx *ctx;
+    EngView v;
+    uint32_t *plane_s[16], *plane_d[16], *plane_sd[16];
+    int W[16], H[16];
+    size_t plane_words[16];
+    MarchThresholds mt;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-instance views
+// ---------------------------------------------------------------------------------------------
+struct Inst {
+    EngInst s; // register copy, uniform across the warp
+    float2 *xy, *sxy;
+    cpword *cp;
+    int *sid, *cell_of, *cell_start, *cursor, *qr, *qs, *qs_mark, *child_start, *children, *frontier;
+    const float2 *samples;
+    int *path;
+    PlaneView pl;
+};
+
+__device__ __forceinline__ GridView inst_grid(const EngView &ev, const Inst &in) {
+    GridView g;
+    g.sxy = in.sxy, g.sid = in.sid, g.cell_start = in.cell_start, g.xy = in.xy;
+    g.gw = ev.gw, g.gh = ev.gh, g.shift = ev.shift, g.n_sorted = in.s.n_sorted, g.n = in.s.n;
+    return g;
+}
+
+// counting sort of all nodes by cell, done by the instance's own warp
+__device__ void grid_rebuild_warp(const EngView &ev, Inst &in) {
+    const int lane = threadIdx.x & 31;
+    const int n = in.s.n, m = ev.ncells;
+    for (int c = lane; c <= m; c += 32) in.cursor[c] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const float2 p = in.xy[i];
+        const int c = grid_cell_of((double)p.y, ev.shift, ev.gh - 1) * ev.gw + grid_cell_of((double)p.x, ev.shift, ev.gw - 1);
+        in.cell_of[i] = c;
+        atomicAdd(&in.cursor[c], 1);
+    }
+    __syncwarp();
+    int carry = 0;
+    for (int base = 0; base <= m; base += 32) {
+        const int c = base + lane;
+        const int v = c <= m ? in.cursor[c] : 0;
+        int x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, off);
+            if (lane >= off) x += y;
+        }
+        if (c <= m) {
+            in.cell_start[c] = carry + x - v;
+            in.cursor[c] = carry + x - v;
+        }
+        carry += __shfl_sync(FULL, x, 31);
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const int pos = atomicAdd(&in.cursor[in.cell_of[i]], 1);
+        in.sxy[pos] = in.xy[i];
+        in.sid[pos] = i;
+    }
+    __syncwarp();
+    in.s.n_sorted = n;
+}
+
+__device__ __forceinline__ void maybe_rebuild(const EngView &ev, Inst &in) {
+    // small trees are scanned linearly (cheaper than walking a sparse grid); afterwards the hash
+    // is re-sorted whenever the unsorted tail reaches max(512, n/8)
+    const int tail = in.s.n - in.s.n_sorted;
+    if (in.s.n_sorted == 0 ? tail >= 2048 : (tail >= 512 && tail * 8 >= in.s.n_sorted)) grid_rebuild_warp(ev, in);
+}
+
+// virtual clock: the k-th read returns k*dt (orc::VClock)
+__device__ __forceinline__ long long clk_now(Inst &in, long long dt) { return dt * (in.s.clk_n++); }
+
+// ---------------------------------------------------------------------------------------------
+// UpdateTree (RTRRT.cpp:92-136)
+// ---------------------------------------------------------------------------------------------
+__device__ void update_tree(const EngView &ev, Inst &in, const MarchThresholds &mt) {
+    const int lane = threadIdx.x & 31;
+    const int n = in.s.n;
+    const float2 rootp = in.xy[in.s.root];
+    if (in.s.agent.x != rootp.x || in.s.agent.y != rootp.y) {
+        KnnEntry e;
+        knn_warp(inst_grid(ev, in), (double)in.s.agent.x, (double)in.s.agent.y, 1, e);
+        const int near = __shfl_sync(FULL, e.id, 0);
+        if (near != in.s.root) { // reverse the parent chain near -> ... -> root
+            if (lane == 0) {
+                int x = near, x_old = -1, guard = 0;
+                while (x != in.s.root && x >= 0 && guard++ < n) {
+                    const cpword w = in.cp[x];
+                    in.cp[x] = cp_make(cp_hi(w), x_old);
+                    x_old = x;
+                    x = cp_parent(w);
+                }
+                if (x >= 0) in.cp[x] = cp_make(cp_hi(in.cp[x]), x_old);
+                in.cp[near] = cp_make(cost_pack(false, 0.0f), -1);
+            }
+            __syncwarp();
+            in.s.root = near;
+        }
+    }
+    // children lists (counting sort on the parent id)
+    for (int i = lane; i <= n; i += 32) in.child_start[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const int p = cp_parent(in.cp[i]);
+        if (i != in.s.root && p >= 0) atomicAdd(&in.child_start[p], 1);
+    }
+    __syncwarp();
+    int carry = 0;
+    for (int base = 0; base <= n; base += 32) {
+        const int c = base + lane;
+        const int v = c <= n ? in.child_start[c] : 0;
+        int x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, off);
+            if (lane >= off) x += y;
+        }
+        if (c <= n) in.child_start[c] = carry + x - v;
+        carry += __shfl_sync(FULL, x, 31);
+    }
+    __syncwarp();
+    int *fill = in.cell_of; // per-parent fill counters (scratch; rebuilt by grid_rebuild_warp when needed)
+    for (int i = lane; i < n; i += 32) fill[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const int p = cp_parent(in.cp[i]);
+        if (i != in.s.root && p >= 0) in.children[in.child_start[p] + atomicAdd(&fill[p], 1)] = i;
+    }
+    __syncwarp();
+    // BFS by levels: cost[child] = cost[parent] + {E(parent,child), |parent-child|}
+    int *cur = in.frontier, *nxt = in.frontier + ev.cap;
+    if (lane == 0) cur[0] = in.s.root;
+    int cur_n = 1;
+    __syncwarp();
+    while (cur_n > 0) {
+        int nxt_n = 0;
+        for (int f0 = 0; f0 < cur_n; f0 += 32) {
+            const int f = f0 + lane;
+            int s = 0, e = 0, p = -1;
+            uint32_t hp = 0;
+            float2 pp = make_float2(0.f, 0.f);
+            if (f < cur_n) {
+                p = cur[f];
+                s = in.child_start[p], e = in.child_start[p + 1];
+                hp = cp_hi(in.cp[p]);
+                pp = in.xy[p];
+            }
+            // exclusive prefix of the child counts gives each lane its slot range in the next frontier
+            const int cnt = e - s;
+            int x = cnt;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(FULL, x, off);
+                if (lane >= off) x += y;
+            }
+            const int slot = nxt_n + x - cnt;
+            for (int j = 0; j < cnt; j++) {
+                const int c = in.children[s + j];
+                const float2 pc = in.xy[c];
+                const uint32_t w = cost_pack(rt_edge_blocked(in.pl, pp.x, pp.y, pc.x, pc.y, mt), rt_dist(pp.x, pp.y, pc.x, pc.y));
+                in.cp[c] = cp_make(cost_add(hp, w), p);
+                nxt[slot + j] = c;
+            }
+            nxt_n += __shfl_sync(FULL, x, 31);
+        }
+        __syncwarp();
+        int *t = cur;
+        cur = nxt, nxt = t;
+        cur_n = nxt_n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ExpandRewiring (RTRRT.cpp:226-355)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void qr_push(const EngView &ev, Inst &in, bool want, int id) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(FULL, want);
+    if (want) in.qr[(unsigned)(in.s.qr_tail + __popc(m & ((1u << lane) - 1))) % (unsigned)ev.qr_cap] = id;
+    in.s.qr_tail += __popc(m);
+    if (in.s.qr_tail - in.s.qr_head > ev.qr_cap) in.s.status = 2;
+    __syncwarp();
+}
+
+// One sample: RTRRT.cpp:263-298 (R1 choose-parent)
+__device__ void expand_one(const EngView &ev, Inst &in, const MarchThresholds &mt, float2 p) {
+    const int lane = threadIdx.x & 31;
+    in.s.iters++;
+    KnnEntry e;
+    const int found = knn_warp(inst_grid(ev, in), (double)p.x, (double)p.y, 25, e);
+    const bool have = lane < found;
+    float2 q = make_float2(0.f, 0.f);
+    uint32_t hs = 0;
+    bool blk = false;
+    if (have) {
+        q = in.xy[e.id];
+        hs = cp_hi(in.cp[e.id]);
+        blk = rt_edge_blocked(in.pl, p.x, p.y, q.x, q.y, mt); // CrashDetection(randpoint, x_near)
+    }
+    const bool blocked0 = __shfl_sync(FULL, blk, 0);
+    if (blocked0) return;
+    const int closest = __shfl_sync(FULL, e.id, 0);
+    const double d2_0 = __shfl_sync(FULL, e.d2, 0);
+    if (__fsqrt_rn(__double2float_rn(d2_0)) > 8.0f) { // RnearR, RTRRT.cpp:270
+        // c_new = cost(x_near) + {E, |rand - x_near|}; strict <, first neighbour wins ties
+        unsigned long long key = ~0ull;
+        if (have) key = ((unsigned long long)cost_add(hs, cost_pack(blk, rt_dist(p.x, p.y, q.x, q.y))) << 32) | (unsigned)lane;
+        for (int off = 16; off; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(FULL, key, off);
+            key = o < key ? o : key;
+        }
+        const int jmin = (int)(key & 31u);
+        const int x_min = __shfl_sync(FULL, e.id, jmin);
+        if (in.s.n >= ev.cap) {
+            in.s.status = 1;
+            return;
+        }
+        const int id = in.s.n;
+        if (lane == 0) {
+            in.xy[id] = p;
+            in.cp[id] = cp_make((uint32_t)(key >> 32), x_min);
+        }
+        in.s.n = id + 1;
+        __syncwarp();
+        qr_push(ev, in, lane == 0, id);
+        maybe_rebuild(ev, in);
+    } else
+        qr_push(ev, in, lane == 0, closest);
+}
+
+// relax the <=25 neighbours of x (RTRRT.cpp:304-319 / 333-346); returns per-lane "improved"
+__device__ __forceinline__ bool relax_neighbours(const EngView &ev, Inst &in, const MarchThresholds &mt, int x, KnnEntry &e,
+                                                 int &found) {
+    const int lane = threadIdx.x & 31;
+    const float2 px = in.xy[x];
+    found = knn_warp(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e);
+    bool improved = false;
+    if (lane < found) {
+        const float2 q = in.xy[e.id];
+        const uint32_t w = cost_pack(rt_edge_blocked(in.pl, px.x, px.y, q.x, q.y, mt), rt_dist(px.x, px.y, q.x, q.y));
+        const uint32_t c_new = cost_add(cp_hi(in.cp[x]), w);
+        if (c_new < cp_hi(in.cp[e.id])) {
+            in.cp[e.id] = cp_make(c_new, x);
+            improved = true;
+        }
+    }
+    __syncwarp();
+    return improved;
+}
+
+__device__ void expand_rewiring(const EngView &ev, Inst &in, const MarchThresholds &mt, long long run_ns, long long dt) {
+    const int lane = threadIdx.x & 31;
+    const long long t0 = clk_now(in, dt);
+    while (clk_now(in, dt) - t0 < run_ns) {
+        if (in.s.samp_pos >= in.s.samp_n || in.s.status) break;
+        const float2 p = in.samples[in.s.samp_pos++];
+        expand_one(ev, in, mt, p);
+        // rewire from the random queue
+        while (in.s.qr_tail != in.s.qr_head && (clk_now(in, dt) - t0 < run_ns)) {
+            const int xr = in.qr[(unsigned)in.s.qr_head % (unsigned)ev.qr_cap];
+            in.s.qr_head++;
+            in.s.pops_r++;
+            KnnEntry e;
+            int found;
+            const bool imp = relax_neighbours(ev, in, mt, xr, e, found);
+            qr_push(ev, in, imp, e.id);
+        }
+        // rewire from the root
+        if (in.s.qs_tail == in.s.qs_head) {
+            in.s.qs_epoch++;
+            in.s.qs_head = in.s.qs_tail = 0;
+            if (lane == 0) {
+                in.qs[0] = in.s.root;
+                in.qs_mark[in.s.root] = in.s.qs_epoch;
+            }
+            in.s.qs_tail = 1;
+            __syncwarp();
+        }
+        while (in.s.qs_tail != in.s.qs_head && (clk_now(in, dt) - t0 < run_ns)) {
+            const int xs = in.qs[in.s.qs_head];
+            in.s.qs_head++;
+            in.s.pops_s++;
+            KnnEntry e;
+            int found;
+            relax_neighbours(ev, in, mt, xs, e, found);
+            const bool fresh = lane < found && in.qs_mark[e.id] != in.s.qs_epoch;
+            const unsigned m = __ballot_sync(FULL, fresh);
+            if (fresh) {
+                in.qs[in.s.qs_tail + __popc(m & ((1u << lane) - 1))] = e.id;
+                in.qs_mark[e.id] = in.s.qs_epoch;
+            }
+            in.s.qs_tail += __popc(m);
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GetPath (RTRRT.cpp:356-400): direct goal-root shortcut, else best entry among the 25-NN of the
+// goal, then the parent walk accumulating the binary32 length c_base.  The depth-5 fallback of
+// :401-437 (no collision-free entry) reports path_len = 0 with the reference's {1, 3.4e38} cost.
+// ---------------------------------------------------------------------------------------------
+__device__ void get_path(const EngView &ev, Inst &in, const MarchThresholds &mt) {
+    const int lane = threadIdx.x & 31;
+    in.s.c_base = -1.0f;
+    in.s.path_len = 0, in.s.path_col = 1, in.s.path_cost = 3.4e38f;
+    if (!(in.s.goal.x > 0.0f)) return; // "goal.x <= 0"
+    const float2 g = in.s.goal, r = in.xy[in.s.root];
+    if (!rt_edge_blocked_warp(in.pl, g.x, g.y, r.x, r.y, mt)) { // CrashDetection(goal, root)
+        if (lane == 0) in.path[0] = in.s.root, in.path[1] = -2; // -2 = the goal point itself
+        in.s.path_len = 2, in.s.path_col = 0, in.s.path_cost = rt_dist(r.x, r.y, g.x, g.y);
+        return;
+    }
+    KnnEntry e;
+    const int found = knn_warp(inst_grid(ev, in), (double)g.x, (double)g.y, 25, e);
+    unsigned long long key = ((unsigned long long)cost_pack(true, FLT_MAX) << 32) | 63u; // c_min = {1, FLT_MAX}
+    if (lane < found) {
+        const float2 q = in.xy[e.id];
+        const uint32_t w = cost_pack(rt_edge_blocked(in.pl, g.x, g.y, q.x, q.y, mt), rt_dist(g.x, g.y, q.x, q.y));
+        const uint32_t c = cost_add(cp_hi(in.cp[e.id]), w);
+        if (c < cost_pack(true, FLT_MAX)) key = ((unsigned long long)c << 32) | (unsigned)lane;
+    }
+    for (int off = 16; off; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, key, off);
+        key = o < key ? o : key;
+    }
+    const uint32_t cmin = (uint32_t)(key >> 32);
+    if (cmin < cost_pack(true, 0.0f)) { // c_min < {1, 0}: a collision-free entry exists
+        const int x_min = __shfl_sync(FULL, e.id, (int)(key & 31u));
+        int len = 0, bad = 0;
+        float cb = 0.0f;
+        if (lane == 0) {
+            // path.push_front(goal); walk parents, c_base += |x_i - path.front()|
+            float2 front = g;
+            int x = x_min;
+            in.path[len++] = -2;
+            while (x >= 0) {
+                const float2 px = in.xy[x];
+                cb = __fadd_rn(cb, rt_dist(px.x, px.y, front.x, front.y));
+                if (len < ev.path_cap) in.path[len] = x;
+                len++;
+                front = px;
+                x = cp_parent(in.cp[x]);
+                if (len > 2000) {
+                    bad = 1;
+                    break;
+                }
+            }
+        }
+        len = __shfl_sync(FULL, len, 0), bad = __shfl_sync(FULL, bad, 0), cb = __shfl_sync(FULL, cb, 0);
+        if (bad) {
+            in.s.path_len = 0, in.s.path_col = 1, in.s.path_cost = 2.4e38f;
+            in.s.c_base = cb; // the reference leaves the partial sum in c_base (RTRRT.cpp:389-396)
+        } else {
+            in.s.path_len = len, in.s.path_col = 0, in.s.path_cost = cb, in.s.c_base = cb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels: one warp per instance
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
+    if (w >= ev.n_inst) return false;
+    in.s = ev.inst[w];
+    const size_t c = (size_t)w * ev.cap, g = (size_t)w * (ev.ncells + 1);
+    in.xy = ev.xy + c, in.sxy = ev.sxy + c, in.cp = ev.cp + c, in.sid = ev.sid + c, in.cell_of = ev.cell_of + c;
+    in.cell_start = ev.cell_start + g, in.cursor = ev.cursor + g;
+    in.qr = ev.qr + (size_t)w * ev.qr_cap, in.qs = ev.qs + c, in.qs_mark = ev.qs_mark + c;
+    in.child_start = ev.child_start + (size_t)w * (ev.cap + 1), in.children = ev.children + c;
+    in.frontier = ev.frontier + 2 * c;
+    in.samples = ev.samples + (size_t)w * ev.max_samples;
+    in.path = ev.path + (size_t)w * ev.path_cap;
+    in.pl = ev.planes[in.s.map_slot & 15];
+    return true;
+}
+
+__global__ void __launch_bounds__(128) engine_tick_kernel(EngView ev, MarchThresholds mt, int do_update, long long run_ns,
+                                                         long long dt, int do_path) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    Inst in;
+    if (!load_inst(ev, w, in)) return;
+    if (in.s.n > 0) {
+        if (do_update) update_tree(ev, in, mt);
+        if (run_ns > 0) expand_rewiring(ev, in, mt, run_ns, dt);
+        if (do_path) get_path(ev, in, mt);
+    }
+    if ((threadIdx.x & 31) == 0) ev.inst[w] = in.s;
+}
+
+// SetAgent for fresh instances (RTRRT.cpp:23-31): the first agent position becomes the root node
+__global__ void engine_init_kernel(EngView ev, const int *__restrict__ slots, const float2 *__restrict__ agent,
+                                   const float2 *__restrict__ goal) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= ev.n_inst) return;
+    EngInst s;
+    memset(&s, 0, sizeof(s));
+    s.map_slot = slots[w];
+    s.agent = agent[w], s.goal = goal[w];
+    s.c_base = -1.0f;
+    s.n = 1, s.n_sorted = 0, s.root = 0;
+    s.path_col = 1, s.path_cost = 3.4e38f;
+    ev.xy[(size_t)w * ev.cap] = agent[w];
+    ev.cp[(size_t)w * ev.cap] = cp_make(cost_pack(false, 0.0f), -1);
+    ev.inst[w] = s;
+}
+
+__global__ void engine_set_agents_kernel(EngView ev, const float2 *__restrict__ agent, const float2 *__restrict__ goal,
+                                         const int *__restrict__ samp_n) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= ev.n_inst) return;
+    if (agent) ev.inst[w].agent = agent[w];
+    if (goal) ev.inst[w].goal = goal[w];
+    if (samp_n) ev.inst[w].samp_n = samp_n[w], ev.inst[w].samp_pos = 0;
+}
+
+__global__ void __launch_bounds__(256) engine_pack_plane_kernel(const uint8_t *__restrict__ src, int W, int H, int tilesX,
+                                                               size_t n_words, uint32_t *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t wi = warp; wi < n_words; wi += nwarps) {
+        size_t tile = wi >> 5;
+        int r = (int)(wi & 31);
+        int ty = (int)(tile / tilesX), tx = (int)(tile - (size_t)ty * tilesX);
+        int y = (ty << 5) + r, x = (tx << 5) + lane;
+        bool on = (y < H && x < W) ? (src[(size_t)y * W + x] != 0) : false;
+        uint32_t word = __ballot_sync(FULL, on);
+        if (lane == 0) dst[wi] = word;
+    }
+}
+__global__ void __launch_bounds__(256) engine_merge_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                                          uint32_t *__restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = a[i] | (b ? b[i] : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+#define ENG_CK(e, call) RTPP_CK((e)->ctx, call)
+
+template <class T> static int eng_alloc(rtpp_engine *e, T **p, size_t count) {
+    ENG_CK(e, cudaMalloc((void **)p, count * sizeof(T)));
+    ENG_CK(e, cudaMemsetAsync(*p, 0, count * sizeof(T), e->ctx->stream));
+    return RTPP_OK;
+}
+
+extern "C" {
+
+int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int node_capacity, int cell_log2, int domain_w,
+                       int domain_h, int max_samples, rtpp_engine **out) {
+    if (!ctx || !out) return RTPP_ERR_INVALID;
+    *out = nullptr;
+    if (planner_kind != 1) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "planner_kind: 1 = RT-RRT*");
+    if (n_instances < 1 || node_capacity < 32 || cell_log2 < 2 || cell_log2 > 10 || domain_w < 1 || domain_h < 1 || max_samples < 1)
+        RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad engine geometry");
+    RTPP_CK(ctx, cudaSetDevice(ctx->device));
+    rtpp_engine *e = new (std::nothrow) rtpp_engine();
+    if (!e) return RTPP_ERR_NOMEM;
+    memset(&e->v, 0, sizeof(e->v));
+    for (int i = 0; i < 16; i++) e->plane_s[i] = e->plane_d[i] = e->plane_sd[i] = nullptr, e->W[i] = e->H[i] = 0, e->plane_words[i] = 0;
+    e->ctx = ctx;
+    EngView &v = e->v;
+    v.n_inst = n_instances, v.cap = node_capacity, v.qr_cap = 8 * node_capacity, v.max_samples = max_samples, v.path_cap = 2048;
+    v.shift = cell_log2;
+    v.gw = ((domain_w - 1) >> cell_log2) + 1, v.gh = ((domain_h - 1) >> cell_log2) + 1, v.ncells = v.gw * v.gh;
+    v.divisor = 5;
+    rtpp_march_thresholds(5, &e->mt);
+    const size_t N = (size_t)n_instances, C = N * node_capacity, G = N * (v.ncells + 1);
+    int rc = 0;
+    rc |= eng_alloc(e, &v.inst, N);
+    rc |= eng_alloc(e, &v.xy, C);
+    rc |= eng_alloc(e, &v.sxy, C);
+    rc |= eng_alloc(e, &v.cp, C);
+    rc |= eng_alloc(e, &v.sid, C);
+    rc |= eng_alloc(e, &v.cell_of, C);
+    rc |= eng_alloc(e, &v.cell_start, G);
+    rc |= eng_alloc(e, &v.cursor, G);
+    rc |= eng_alloc(e, &v.qr, N * v.qr_cap);
+    rc |= eng_alloc(e, &v.qs, C);
+    rc |= eng_alloc(e, &v.qs_mark, C);
+    rc |= eng_alloc(e, &v.child_start, N * (node_capacity + 1));
+    rc |= eng_alloc(e, &v.children, C);
+    rc |= eng_alloc(e, &v.frontier, 2 * C);
+    rc |= eng_alloc(e, &v.samples, N * max_samples);
+    rc |= eng_alloc(e, &v.path, N * v.path_cap);
+    if (rc) return RTPP_ERR_NOMEM;
+    *out = e;
+    return RTPP_OK;
+}
+
+int rtpp_engine_destroy(rtpp_engine *e) {
+    if (!e) return RTPP_ERR_INVALID;
+    cudaStreamSynchronize(e->ctx->stream);
+    EngView &v = e->v;
+    cudaFree(v.inst), cudaFree(v.xy), cudaFree(v.sxy), cudaFree(v.cp), cudaFree(v.sid), cudaFree(v.cell_of);
+    cudaFree(v.cell_start), cudaFree(v.cursor), cudaFree(v.qr), cudaFree(v.qs), cudaFree(v.qs_mark);
+    cudaFree(v.child_start), cudaFree(v.children), cudaFree(v.frontier), cudaFree(v.samples), cudaFree(v.path);
+    for (int i = 0; i < 16; i++) cudaFree(e->plane_s[i]), cudaFree(e->plane_d[i]), cudaFree(e->plane_sd[i]);
+    delete e;
+    return RTPP_OK;
+}
+
+// static (plane = 1) or dynamic (plane = 2; src NULL clears it) byte plane of a map slot
+int rtpp_engine_set_map(rtpp_engine *e, int slot, int plane, const uint8_t *src, int W, int H) {
+    if (!e || slot < 0 || slot >= 16 || (plane != 1 && plane != 2)) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    if (plane == 1 && !src) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "static plane needs data");
+    if (plane == 2 && !e->plane_s[slot]) RTPP_FAIL(ctx, RTPP_ERR_STATE, "set the static plane of the slot first");
+    if (plane == 2) W = e->W[slot], H = e->H[slot];
+    const int tilesX = (W + 31) >> 5, tilesY = (H + 31) >> 5;
+    const size_t words = (size_t)tilesX * tilesY * 32;
+    if (plane == 1) {
+        cudaFree(e->plane_s[slot]), cudaFree(e->plane_d[slot]), cudaFree(e->plane_sd[slot]);
+        e->plane_s[slot] = e->plane_d[slot] = e->plane_sd[slot] = nullptr;
+        ENG_CK(e, cudaMalloc(&e->plane_s[slot], words * 4));
+        ENG_CK(e, cudaMalloc(&e->plane_d[slot], words * 4));
+        ENG_CK(e, cudaMalloc(&e->plane_sd[slot], words * 4));
+        ENG_CK(e, cudaMemsetAsync(e->plane_d[slot], 0, words * 4, ctx->stream));
+        e->W[slot] = W, e->H[slot] = H, e->plane_words[slot] = words;
+    }
+    uint32_t *dst = plane == 1 ? e->plane_s[slot] : e->plane_d[slot];
+    if (src) {
+        void *d = nullptr;
+        int rc = rtpp_scratch(ctx, 0, (size_t)W * H, &d);
+        if (rc) return rc;
+        ENG_CK(e, cudaMemcpyAsync(d, src, (size_t)W * H, cudaMemcpyHostToDevice, ctx->stream));
+        engine_pack_plane_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint8_t *)d, W, H, tilesX, words, dst);
+        RTPP_LAUNCHED(ctx);
+    } else
+        ENG_CK(e, cudaMemsetAsync(dst, 0, words * 4, ctx->stream));
+    engine_merge_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
+    RTPP_LAUNCHED(ctx);
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    e->v.planes[slot].w = e->plane_sd[slot];
+    e->v.planes[slot].W = W, e->v.planes[slot].H = H, e->v.planes[slot].tilesX = tilesX;
+    return RTPP_OK;
+}
+
+static int upload(rtpp_engine *e, int slot, const void *src, size_t bytes, void **d) {
+    *d = nullptr;
+    if (!src) return RTPP_OK;
+    int rc = rtpp_scratch(e->ctx, slot, bytes, d);
+    if (rc) return rc;
+    ENG_CK(e, cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, e->ctx->stream));
+    return RTPP_OK;
+}
+
+// SetAgent on empty planners (creates the root, RTRRT.cpp:23-31) + SetGoal; goal (-1,-1) = none
+int rtpp_engine_init_instances(rtpp_engine *e, const int32_t *map_slot, const float *agent_xy, const float *goal_xy) {
+    if (!e || !map_slot || !agent_xy || !goal_xy) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    const int n = e->v.n_inst;
+    void *ds, *da, *dg;
+    int rc = upload(e, 0, map_slot, (size_t)n * 4, &ds);
+    rc |= upload(e, 1, agent_xy, (size_t)n * 8, &da);
+    rc |= upload(e, 2, goal_xy, (size_t)n * 8, &dg);
+    if (rc) return rc;
+    engine_init_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(e->v, (const int *)ds, (const float2 *)da, (const float2 *)dg);
+    RTPP_LAUNCHED(ctx);
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+// per-tick inputs: agent positions (SetAgent on a non-empty planner just moves the agent,
+// RTRRT.cpp:32-35), goals, and the pre-drawn sample points for the coming ExpandRewiring call
+// (samples_xy: n_inst rows of max_samples points; n_samples: points valid per row).  Any pointer
+// may be NULL = unchanged.
+int rtpp_engine_set_inputs(rtpp_engine *e, const float *agent_xy, const float *goal_xy, const float *samples_xy,
+                           const int32_t *n_samples) {
+    if (!e) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    const int n = e->v.n_inst;
+    void *da, *dg, *dn;
+    int rc = upload(e, 0, agent_xy, (size_t)n * 8, &da);
+    rc |= upload(e, 1, goal_xy, (size_t)n * 8, &dg);
+    rc |= upload(e, 2, n_samples, (size_t)n * 4, &dn);
+    if (rc) return rc;
+    if (samples_xy)
+        ENG_CK(e, cudaMemcpyAsync(e->v.samples, samples_xy, (size_t)n * e->v.max_samples * 8, cudaMemcpyHostToDevice, ctx->stream));
+    engine_set_agents_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(e->v, (const float2 *)da, (const float2 *)dg, (const int *)dn);
+    RTPP_LAUNCHED(ctx);
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+// One MainTask minus DrawDObsmap for every instance (RTRRT.cpp:483-493): optional UpdateTree,
+// ExpandRewiring(run_ms) under the virtual clock (k-th read = k*dt_ns), optional GetPath.
+// Stream-ordered; no synchronisation.
+int rtpp_engine_tick(rtpp_engine *e, int do_update_tree, long run_ms, long long dt_ns, int do_get_path) {
+    if (!e || run_ms < 0 || dt_ns < 1) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    const int warps_per_block = e->v.n_inst >= 4 * ctx->sm_count ? 4 : 1;
+    const int blocks = (e->v.n_inst + warps_per_block - 1) / warps_per_block;
+    engine_tick_kernel<<<blocks, 32 * warps_per_block, 0, ctx->stream>>>(e->v, e->mt, do_update_tree, (long long)run_ms * 1000000LL,
+                                                                         dt_ns, do_get_path);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+// per-instance statistics, 16 int64 each: n_nodes, root, samples_used, clock_reads, iters, pops_r,
+// pops_s, qr_size, qs_size, status, path_len, path_collision, path_cost bits, c_base bits, 0, 0
+int rtpp_engine_read_stats(rtpp_engine *e, long long *out16) {
+    if (!e || !out16) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    const int n = e->v.n_inst;
+    std::string buf((size_t)n * sizeof(EngInst), '\0');
+    ENG_CK(e, cudaMemcpyAsync(&buf[0], e->v.inst, buf.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    const EngInst *s = (const EngInst *)buf.data();
+    for (int i = 0; i < n; i++) {
+        long long *o = out16 + (size_t)i * 16;
+        uint32_t pc, cb;
+        memcpy(&pc, &s[i].path_cost, 4), memcpy(&cb, &s[i].c_base, 4);
+        o[0] = s[i].n, o[1] = s[i].root, o[2] = s[i].samp_pos, o[3] = s[i].clk_n, o[4] = s[i].iters, o[5] = s[i].pops_r;
+        o[6] = s[i].pops_s, o[7] = s[i].qr_tail - s[i].qr_head, o[8] = s[i].qs_tail - s[i].qs_head, o[9] = s[i].status;
+        o[10] = s[i].path_len, o[11] = s[i].path_col, o[12] = pc, o[13] = cb, o[14] = 0, o[15] = 0;
+    }
+    return RTPP_OK;
+}
+
+// nodes of one instance in insertion order (xy, parent, cost, collision): Node_Map read-out
+int rtpp_engine_read_tree(rtpp_engine *e, int inst, int max_nodes, float *xy, int32_t *parent, float *cost, uint8_t *collision,
+                          int *n_out) {
+    if (!e || inst < 0 || inst >= e->v.n_inst || !n_out) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    EngInst s;
+    ENG_CK(e, cudaMemcpyAsync(&s, e->v.inst + inst, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    const int n = s.n < max_nodes ? s.n : max_nodes;
+    *n_out = s.n;
+    if (n <= 0 || !xy) return RTPP_OK;
+    std::string words((size_t)n * 8, '\0');
+    ENG_CK(e, cudaMemcpyAsync(xy, e->v.xy + (size_t)inst * e->v.cap, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ENG_CK(e, cudaMemcpyAsync(&words[0], e->v.cp + (size_t)inst * e->v.cap, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    const cpword *w = (const cpword *)words.data();
+    for (int i = 0; i < n; i++) {
+        const uint32_t hi = cp_hi(w[i]), cb = hi & 0x7fffffffu;
+        if (parent) parent[i] = cp_parent(w[i]);
+        if (cost) memcpy(&cost[i], &cb, 4);
+        if (collision) collision[i] = hi >> 31;
+    }
+    return RTPP_OK;
+}
+
+// path of one instance after a tick with do_get_path: node ids root..entry, then -2 = the goal
+int rtpp_engine_read_path(rtpp_engine *e, int inst, int max_len, int32_t *ids, int *len_out) {
+    if (!e || inst < 0 || inst >= e->v.n_inst || !ids || !len_out) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    EngInst s;
+    ENG_CK(e, cudaMemcpyAsync(&s, e->v.inst + inst, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    int n = s.path_len < e->v.path_cap ? s.path_len : e->v.path_cap;
+    *len_out = s.path_len;
+    if (n > max_len) n = max_len;
+    if (n <= 0) return RTPP_OK;
+    std::string buf((size_t)n * 4, '\0');
+    ENG_CK(e, cudaMemcpyAsync(&buf[0], e->v.path + (size_t)inst * e->v.path_cap, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    const int *p = (const int *)buf.data();
+    // the device stores goal-first (push_front order reversed): emit root..goal like the std::list
+    if (n >= 2 && p[0] == -2) for (int i = 0; i < n; i++) ids[i] = p[n - 1 - i];
+    else memcpy(ids, p, (size_t)n * 4);
+    return RTPP_OK;
+}
+
+} // extern "C"

@@ -16,13 +16,17 @@
 // proves that no unscanned point can enter or tie into the result.  Points appended since the
 // last re-sort (the "tail") are scanned linearly by every query.
 #pragma once
+#include <math_constants.h>
+
 #include "common.cuh"
 
+// (no __restrict__/read-only qualifiers: the planner engines append nodes and re-sort the hash
+// inside the same kernel that queries it, so these loads must stay coherent)
 struct GridView {
-    const float2 *__restrict__ sxy;       // cell-sorted coordinates            [n_sorted]
-    const int *__restrict__ sid;          // cell-sorted position -> node id    [n_sorted]
-    const int *__restrict__ cell_start;   // first sorted position of each cell [gw*gh + 1]
-    const float2 *__restrict__ xy;        // coordinates by node id             [n]
+    const float2 *sxy;                    // cell-sorted coordinates            [n_sorted]
+    const int *sid;                       // cell-sorted position -> node id    [n_sorted]
+    const int *cell_start;                // first sorted position of each cell [gw*gh + 1]
+    const float2 *xy;                     // coordinates by node id             [n]
     int gw, gh, shift;                    // grid of (1<<shift)-pixel cells
     int n_sorted, n;                      // ids >= n_sorted are the unsorted tail
 };

@@ -1,0 +1,99 @@
+"""Planner-engine parity: the GPU RT-RRT* engine (one warp = one planner instance) must reproduce
+the oracle's sequential run bit for bit — node set, parents, costs, collision flags, queue sizes,
+clock reads, path — under the same virtual clock and the same injected samples."""
+import numpy as np
+import pytest
+
+from helpers import dyn_plane
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=True):
+    import rtpp_b200
+
+    S = oracle.load_map(name)
+    H, W = S.shape
+    max_samples = 4096
+    eng = rtpp_b200.Engine(ctx, n_inst, 8192, 5, W, H, max_samples)
+    eng.set_map(0, 1, S)
+    orcs = []
+    for i in range(n_inst):
+        o = oracle.OrcRTRRT(S)
+        o.set_clock(dt)
+        assert o.set_agent(*agent) and o.set_goal(*goal)
+        orcs.append(o)
+    eng.init_instances(np.zeros(n_inst, np.int32), np.tile(np.array(agent, np.float32), (n_inst, 1)),
+                       np.tile(np.array(goal, np.float32), (n_inst, 1)))
+    streams = [oracle.rand31(seed + i, 3_000_000) for i in range(n_inst)]
+    pos = [0] * n_inst
+    rng = np.random.default_rng(seed)
+    for tick in range(ticks):
+        if tick in (2, 5):
+            D = dyn_plane(S.shape, rng, n_blobs=6)
+            eng.set_map(0, 2, D)
+            for o in orcs:
+                o.set_dobs(D)
+        samples = np.zeros((n_inst, max_samples, 2), np.float32)
+        ns = np.zeros(n_inst, np.int32)
+        offs_all = []
+        for i, o in enumerate(orcs):
+            o.update_tree()
+            pts, offs = o.presample(streams[i][pos[i]:], max_samples)
+            samples[i, : len(pts)] = pts
+            ns[i] = len(pts)
+            offs_all.append(offs)
+        eng.set_inputs(samples=samples, n_samples=ns)
+        eng.tick(update_tree=True, run_ms=50, dt_ns=dt, get_path=True)
+        st = eng.stats()
+        for i, o in enumerate(orcs):
+            used = o.expand_rewiring(50, samples[i, : ns[i]])
+            pos[i] += int(offs_all[i][used])
+            opath, ocol, ocost, ocb = o.get_path()
+            a = o.dump()
+            b = eng.read_tree(i)
+            d = dict(zip(eng.STAT, st[i].tolist()))
+            assert d["status"] == 0
+            assert d["samples_used"] == used
+            assert d["n_nodes"] == o.num_nodes()
+            for x, y in zip(a, b):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"tick {tick} inst {i}"
+            assert (d["qr_size"], d["qs_size"]) == o.queue_sizes()
+            assert d["clock_reads"] == o.L.orc_rtrrt_clock_reads(o.h) - (0)  # GetPath reads no clock
+            assert np.array_equal(b[0][d["root"]], o.root())
+            # path (goal-entry branches; the depth-5 fallback is host-side)
+            gcost = np.array([d["path_cost_bits"]], np.uint32).view(np.float32)[0]
+            if not ocol:
+                ids = eng.read_path(i)
+                gp = np.array([goal if j == -2 else b[0][j] for j in ids], np.float32)
+                assert d["path_col"] == 0 and np.array_equal(gp, opath)
+                assert np.array_equal(np.float32(gcost).view(np.uint32), np.float32(ocost).view(np.uint32))
+            else:
+                assert d["path_col"] == 1
+        if moves and tick in (3, 6):
+            # the agent walks to some tree node: next UpdateTree re-roots there
+            new_agents = np.zeros((n_inst, 2), np.float32)
+            for i, o in enumerate(orcs):
+                xy = o.dump()[0]
+                t = xy[(len(xy) * 2) // 3]
+                o.set_agent(float(t[0]), float(t[1]))
+                new_agents[i] = t
+            eng.set_inputs(agent_xy=new_agents)
+    sizes = [o.num_nodes() for o in orcs]
+    eng.close()
+    return sizes
+
+
+def test_rtrrt_engine_single_instance_mess6(ctx, oracle):
+    sizes = _run_pair(ctx, oracle, "MESS6", (720.0, 720.0), (70.0, 70.0), dt=5000, ticks=8, seed=11)
+    assert sizes[0] > 200
+
+
+def test_rtrrt_engine_game0_reaches_goal(ctx, oracle):
+    sizes = _run_pair(ctx, oracle, "GAME0", (350.0, 2350.0), (1400.0, 2050.0), dt=2000, ticks=8, seed=3)
+    assert sizes[0] > 300
+
+
+def test_rtrrt_engine_many_instances(ctx, oracle):
+    sizes = _run_pair(ctx, oracle, "Trap", (660.0, 660.0), (1160.0, 1160.0), dt=20000, ticks=5, seed=100, n_inst=12)
+    assert len(set(sizes)) > 1  # different seeds -> different trees
