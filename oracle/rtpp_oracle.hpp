@@ -445,8 +445,12 @@ struct RTRRT {
         } else {
             float c_min = dist(goal, root);
             float a = c_base / 2.0f;
-            float b = (float)(std::sqrt((double)(c_base * c_base - c_min * c_min)) / 2.0f);
-            float angle = (float)std::atan2((double)(goal.y - root.y), (double)(goal.x - root.x));
+            // unqualified sqrt()/atan2() on float arguments: the planner header pulls in <math.h>
+            // (RTRRT.h:17 -> CGAL/Exact_predicates_inexact_constructions_kernel.h:24 ->
+            // CGAL/double.h:26), whose libstdc++ wrapper makes the float overloads visible at global
+            // scope, so these are sqrtf / atan2f (confirmed by the oracle/_ref build).
+            float b = sqrtf(c_base * c_base - c_min * c_min) / 2.0f;
+            float angle = atan2f(goal.y - root.y, goal.x - root.x);
             int guard = 0;
             while (true) {
                 float th = rs.u() * 2 * 3.141592954f;
@@ -1140,8 +1144,8 @@ struct AMRRT {
             } else if (goal.x >= 0) {
                 float c_min = dist(goal, root);
                 float a = c_base / 2.0f;
-                float b = (float)(std::sqrt((double)(c_base * c_base - c_min * c_min)) / 2.0f);
-                float angle = (float)std::atan2((double)(goal.y - root.y), (double)(goal.x - root.x));
+                float b = sqrtf(c_base * c_base - c_min * c_min) / 2.0f; // float overloads, see RTRRT::sample
+                float angle = atan2f(goal.y - root.y, goal.x - root.x);
                 float th = rs.u() * 2 * 3.141592954f;
                 float rr = sqrtf(rs.u());
                 float x = a * cosf(th) * rr;

@@ -31,3 +31,33 @@ def dyn_plane(shape, rng, n_blobs=6, value=127):
             sub = (yy[y0:y1] - cy) ** 2 + (xx[:, x0:x1] - cx) ** 2 <= r * r
             D[y0:y1, x0:x1][sub] = value
     return D
+
+
+def synthetic_diffusion(W, G=100, dim=10, seed=5):
+    """A synthetic diffusion-map table like AMRRT/diffusion/*: G x G grid cells (some missing),
+    `dim` floats per cell; ratio = G / shapeX narrowed to float (AMRRT/test/test.cpp:56)."""
+    rng = np.random.default_rng(seed)
+    cells = np.array([(i, j) for i in range(G) for j in range(G) if (i * 7 + j * 3) % 11 != 0], np.int32)
+    mat = rng.standard_normal((len(cells), dim)).astype(np.float32)
+    return cells, mat, np.float32(G / W)
+
+
+def golden_cases():
+    """The scenario definitions shared by tools/make_golden.py (reference run) and the tests.
+    Start / goal points come from the reference's scripted scenarios (RTRRT/test/testD.cpp:36-47)."""
+    return {
+        "rtrrt": [
+            dict(name="mess6", map="MESS6", agent=(720.0, 720.0), goal=(70.0, 70.0), seed=11, n_rand=3_000_000, dt=5000, ticks=8,
+                 dobs_ticks=(2, 5), move_ticks=(3,)),
+            dict(name="game0", map="GAME0", agent=(350.0, 2350.0), goal=(1400.0, 2050.0), seed=3, n_rand=3_000_000, dt=2000, ticks=6,
+                 dobs_ticks=(2,), move_ticks=()),
+        ],
+        "rtfmt": [
+            dict(name="mess6", map="MESS6", agent=(720.0, 720.0), goal=(70.0, 70.0), seed=7, n_rand=100_000, samples=2000, rounds=8,
+                 dobs_rounds=(0, 4), move_rounds=(5,)),
+        ],
+        "amrrt": [
+            dict(name="mess6", map="MESS6", agent=(720.0, 720.0), goal=(1240.0, 1240.0), seed=9, n_rand=3_000_000, dt=500000, ticks=25,
+                 dobs_ticks=(0, 12), diffusion=synthetic_diffusion),
+        ],
+    }
