@@ -430,6 +430,43 @@ def measure_extras(wl, torch):
     torch.cuda.synchronize()
     out["rewire_to_quiescence_ms"] = (time.perf_counter() - t0) * 1e3
     out["rewire_sweeps"] = sweeps
+    out.update(measure_replanning(ctx))
+    return out
+
+
+def measure_replanning(ctx, n_inst=4096, ticks=3, dt=5000):
+    """Replan iterations/s and tick latency: RT-RRT* engine (one warp per planner instance) over the
+    reference's scripted scenarios (8 bundled maps x 4 goals x seeds), against the CPU oracle port of
+    the same loops on all host threads.  One tick = UpdateTree + ExpandRewiring(50 ms) + GetPath under
+    the virtual clock (dt ns per clock read => 50e6/dt = 10^4 queue pops per tick)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sweep_bench as sb
+    from oracle import loader as orc
+
+    maps = {name: orc.load_map(name) for name in sb.SCEN}
+    inst = sb.make_instances(n_inst, maps)
+    lat, st, samples = sb.run_gpu(ctx, orc, inst, maps, 2000, ticks, dt)
+    tot = sum(lat)
+    out = {"replan": {"planner": "RT-RRT*", "instances": n_inst, "ticks": ticks, "virtual_dt_ns": dt,
+                      "gpu_iters_per_s": float(st[:, 4].sum() / tot), "gpu_queue_pops_per_s": float((st[:, 5] + st[:, 6]).sum() / tot),
+                      "gpu_sweep_tick_ms_p50": float(np.median(lat) * 1e3)}}
+    threads = os.cpu_count() or 1
+    m = min(n_inst, 2 * threads)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(lambda k: sb.run_cpu_instance(orc, maps[inst[k][1]], inst[k][2], inst[k][3], samples[k], ticks, dt), range(m)))
+    wall = time.perf_counter() - t0
+    out["replan"].update({
+        "cpu_iters_per_s": sum(r[1]["iters"] for r in res) / wall,
+        "cpu_queue_pops_per_s": sum(r[1]["pops_r"] + r[1]["pops_s"] for r in res) / wall,
+        "cpu_threads": threads, "cpu_kind": "port (oracle loops, grid k-NN; the reference rebuilds a kd-tree per insert)",
+        "cpu_sample": f"{m} of the {n_inst} instances",
+        "cpu_single_thread_tick_ms_p50": float(np.median([x for r in res for x in r[0]]) * 1e3),
+        "trees_match_gpu": bool(all(res[k][1]["n_nodes"] == int(st[k, 0]) and res[k][1]["samples_used"] == int(st[k, 2]) for k in range(m)))})
+    lat1, st1, _ = sb.run_gpu(ctx, orc, inst[:1], maps, 2000, 9, dt)
+    out["replan"]["gpu_single_instance_tick_ms_p50"] = float(np.median(lat1) * 1e3)
     return out
 
 

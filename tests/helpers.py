@@ -61,3 +61,35 @@ def golden_cases():
                  dobs_ticks=(0, 12), diffusion=synthetic_diffusion),
         ],
     }
+
+
+# outlines of the reference's scripted dynamic obstacles (RTRRT/test/testD.cpp:57-69)
+TESTD_OUTLINES = [
+    [(-65, 65), (65, 65), (65, -65), (-65, -65)],
+    [(-54, -28), (-28, -28), (-28, -54), (28, -54), (28, -28), (54, -28), (54, 28), (28, 28), (28, 54), (-28, 54), (-28, 28), (-54, 28)],
+    [(0, -81), (-81, 81), (81, 81)],
+    [(0, -57), (57, 0), (57, 57), (-57, 57), (-57, 0)],
+    [(-57, -57), (57, -57), (57, 57), (-57, 57)],
+    [(-52, 0), (-31, -49), (31, -49), (52, 0), (31, 49), (-31, 49)],
+]
+
+
+def raster_cases(seed=3):
+    """(kind, H, W, arg): filled circles (also clipped by the border) and in-image polygons."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(40):
+        H, W = int(rng.integers(60, 300)), int(rng.integers(60, 300))
+        cases.append(("circle", H, W, (int(rng.integers(-30, W + 30)), int(rng.integers(-30, H + 30)), int(rng.integers(0, 120)))))
+    for _ in range(40):
+        H, W = int(rng.integers(60, 300)), int(rng.integers(60, 300))
+        n = int(rng.integers(3, 13))
+        cases.append(("poly", H, W, np.stack([rng.integers(2, W - 2, n), rng.integers(2, H - 2, n)], 1).astype(np.int32).tolist()))
+    for k, outline in enumerate(TESTD_OUTLINES):
+        sh = np.array(outline, np.float32)
+        for a in (0.0, 0.78539816, 1.1, 2.5, 4.0):
+            c, s = np.float32(np.cos(a)), np.float32(np.sin(a))
+            pts = np.stack([(c * sh[:, 0] - s * sh[:, 1] + np.float32(150)).astype(np.int32),
+                            (s * sh[:, 0] + c * sh[:, 1] + np.float32(150)).astype(np.int32)], 1)
+            cases.append(("poly", 300, 300, pts.tolist()))
+    return cases
