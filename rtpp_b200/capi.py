@@ -300,3 +300,121 @@ class Engine:
         n = C.c_int()
         self._ck(self.L.rtpp_engine_read_path(self.h, inst, cap, _p(ids), C.byref(n)))
         return ids[: min(n.value, cap)]
+
+
+# ---------------------------------------------------------------------------------------------
+# C++ drop-in planner classes (rtpp_b200/planners, librtpp_planners.so) through their C harness
+# ---------------------------------------------------------------------------------------------
+_plib = None
+
+
+def planners_lib():
+    global _plib
+    if _plib is None:
+        path = os.path.join(HERE, "librtpp_planners.so")
+        if not os.path.exists(path):
+            raise RtppError(f"{path} is missing: run __graft_entry__.build()")
+        lib()  # librtpp_gpu.so first (same directory, rpath $ORIGIN)
+        _plib = C.CDLL(path)
+        _plib.pl_rtrrt_create.restype = C.c_void_p
+        _plib.pl_rtrrt_rand_pos.restype = C.c_longlong
+        _plib.pl_rtrrt_clock_reads.restype = C.c_longlong
+    return _plib
+
+
+class PlannerRTRRT:
+    """The C++ RTRRTplanner drop-in (same methods as the reference class) driven from Python."""
+
+    def __init__(self, obstacle_plane, device=0):
+        self.L = planners_lib()
+        S = _c(obstacle_plane, np.uint8)
+        self.shape = S.shape
+        h = self.L.pl_rtrrt_create(_p(S), S.shape[0], S.shape[1], device)
+        if not h:
+            raise RtppError("RTRRTplanner could not be created (no CUDA device; there is no CPU fallback)")
+        self.h = C.c_void_p(h)
+        self._rand = None
+
+    def close(self):
+        if self.h:
+            self.L.pl_rtrrt_destroy(self.h)
+            self.h = None
+
+    def set_clock(self, dt_ns):
+        self.L.pl_rtrrt_set_clock(self.h, C.c_longlong(dt_ns))
+
+    def set_rand(self, r):
+        self._rand = _c(r, np.int32)
+        self.L.pl_rtrrt_set_rand(self.h, _p(self._rand), C.c_longlong(len(self._rand)))
+
+    def rand_pos(self):
+        return int(self.L.pl_rtrrt_rand_pos(self.h))
+
+    def set_agent(self, x, y):
+        self.L.pl_rtrrt_set_agent(self.h, C.c_float(x), C.c_float(y))
+
+    def set_goal(self, x, y):
+        self.L.pl_rtrrt_set_goal(self.h, C.c_float(x), C.c_float(y))
+
+    def set_dobs(self, plane):
+        plane = None if plane is None else _c(plane, np.uint8)
+        self.L.pl_rtrrt_set_dobs(self.h, _p(plane))
+
+    def add_obstacle(self, num, typ, x, y, angle, radius, outline):
+        o = _c(outline, np.float32).reshape(-1, 2)
+        self.L.pl_rtrrt_add_obstacle(self.h, num, typ, C.c_float(x), C.c_float(y), C.c_float(angle), C.c_float(radius), _p(o), len(o))
+
+    def draw_dobs(self):
+        self.L.pl_rtrrt_draw_dobs(self.h)
+
+    def get_dobs(self):
+        out = np.zeros(self.shape, np.uint8)
+        self.L.pl_rtrrt_get_dobs(self.h, _p(out))
+        return out
+
+    def update_tree(self):
+        self.L.pl_rtrrt_update_tree(self.h)
+
+    def expand_rewiring(self, ms):
+        self.L.pl_rtrrt_expand_rewiring(self.h, C.c_long(ms))
+
+    def main_task(self):
+        self.L.pl_rtrrt_main_task(self.h)
+
+    def crash(self, a, b):
+        return bool(self.L.pl_rtrrt_crash(self.h, C.c_float(a[0]), C.c_float(a[1]), C.c_float(b[0]), C.c_float(b[1])))
+
+    def num_nodes(self):
+        return self.L.pl_rtrrt_num_nodes(self.h)
+
+    def dump(self):
+        n = self.num_nodes()
+        xy, par = np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+        cost, col = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self.L.pl_rtrrt_dump(self.h, _p(xy), _p(par), _p(cost), _p(col))
+        return xy, par, cost, col
+
+    def root(self):
+        xy = np.zeros(2, np.float32)
+        self.L.pl_rtrrt_root(self.h, _p(xy))
+        return xy
+
+    def queue_sizes(self):
+        a, b = C.c_int(), C.c_int()
+        self.L.pl_rtrrt_queue_sizes(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def get_path(self, cap=2048):
+        xy = np.zeros((cap, 2), np.float32)
+        col, cost = C.c_int(), C.c_float()
+        n = self.L.pl_rtrrt_get_path(self.h, _p(xy), cap, C.byref(col), C.byref(cost))
+        return xy[: min(n, cap)], bool(col.value), cost.value
+
+
+def host_raster_circle(img, cx, cy, r, v=127):
+    planners_lib().pl_raster_circle(_p(img), img.shape[0], img.shape[1], int(cx), int(cy), int(r), int(v))
+
+
+def host_raster_fillpoly(img, pts, v=127):
+    pts = _c(pts, np.int32).reshape(-1, 2)
+    planners_lib().pl_raster_fillpoly(_p(img), img.shape[0], img.shape[1], _p(pts), len(pts), int(v))

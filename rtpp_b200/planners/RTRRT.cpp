@@ -1,0 +1,361 @@
+// RTRRT.cpp — see RTRRT.h.  Every public method names the reference lines whose behaviour it keeps.
+#include "RTRRT.h"
+
+#include <cfloat>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+
+bool RTRRTplanner::Fail(const char *what, int rc) {
+    fprintf(stderr, "RTRRTplanner: %s failed: %s (%s)\n", what, rtpp_status_string(rc), ctx_ ? rtpp_last_error(ctx_) : "no ctx");
+    return false;
+}
+
+RTRRTplanner::RTRRTplanner(int device) {
+    agent = {-1, -1};
+    int rc = rtpp_create(device, &ctx_);
+    if (rc) {
+        ctx_ = nullptr;
+        fprintf(stderr, "RTRRTplanner: no CUDA device / rtpp_create failed (%s); there is no CPU fallback\n", rtpp_status_string(rc));
+    }
+}
+
+RTRRTplanner::~RTRRTplanner() {
+    if (eng_) rtpp_engine_destroy(eng_);
+    if (ctx_) rtpp_destroy(ctx_);
+}
+
+// reference RTRRT.cpp:57-80: grey image -> threshold(th, 255, BINARY) -> bitwise_not = Obsmap
+void RTRRTplanner::InitializeInvironment(const uint8_t *gray, int rows, int cols, int th) {
+    if (!gray || rows <= 0 || cols <= 0) {
+        fprintf(stderr, "Failed to load input image.\n");
+        return;
+    }
+    Freemap.create(rows, cols), Obsmap.create(rows, cols), DObsmap.create(rows, cols);
+    for (size_t i = 0; i < (size_t)rows * cols; i++) {
+        const uint8_t f = gray[i] > th ? 255 : 0;
+        Freemap.data[i] = f;
+        Obsmap.data[i] = (uint8_t)~f;
+    }
+    shapeX = cols, shapeY = rows;
+    if (!ctx_) return;
+    int rc = rtpp_map_set_plane(ctx_, RTPP_PLANE_STATIC, Obsmap.data.data(), cols, rows);
+    if (rc) {
+        Fail("rtpp_map_set_plane", rc);
+        return;
+    }
+    if (eng_) {
+        rtpp_engine_destroy(eng_);
+        eng_ = nullptr, started_ = false;
+    }
+}
+
+void RTRRTplanner::InitializeInvironment(const char *IMGmap, int th) {
+    std::ifstream f(IMGmap, std::ios::binary);
+    std::string magic;
+    int w = 0, h = 0, maxv = 0;
+    if (f) {
+        f >> magic;
+        auto skip = [&] {
+            f >> std::ws;
+            while (f.peek() == '#') f.ignore(1 << 20, '\n'), f >> std::ws;
+        };
+        skip(), f >> w, skip(), f >> h, skip(), f >> maxv;
+        f.get();
+    }
+    if (!f || magic != "P5" || w <= 0 || h <= 0 || maxv != 255) {
+        fprintf(stderr, "Failed to load input image.\n");
+        return;
+    }
+    std::vector<uint8_t> g((size_t)w * h);
+    f.read((char *)g.data(), g.size());
+    if (!f) {
+        fprintf(stderr, "Failed to load input image.\n");
+        return;
+    }
+    InitializeInvironment(g.data(), h, w, th);
+}
+
+bool RTRRTplanner::EnsureEngine() {
+    if (eng_) return true;
+    if (!ctx_ || shapeX <= 0) return false;
+    int rc = rtpp_engine_create(ctx_, 1, 1, node_capacity_, 5, shapeX, shapeY, max_samples_, &eng_);
+    if (rc) return Fail("rtpp_engine_create", rc);
+    rc = rtpp_engine_set_map(eng_, 0, 1, Obsmap.data.data(), shapeX, shapeY);
+    if (rc) return Fail("rtpp_engine_set_map", rc);
+    return true;
+}
+
+// reference RTRRT.cpp:11-36
+void RTRRTplanner::SetAgent(RTpoint &point) {
+    if (point.x >= shapeX || point.y >= shapeY) {
+        printf("SetAgent error: Init point is too large!!\r\n");
+        return;
+    }
+    if (Obsmap.at<uint8_t>((int)point.y, (int)point.x)) {
+        printf("SetAgent error: robot can't be here!!\r\n");
+        return;
+    }
+    if (!started_) {
+        if (!EnsureEngine()) return;
+        root = point, agent = root;
+        const int32_t slot = 0;
+        const float a[2] = {point.x, point.y}, g[2] = {goal.x, goal.y};
+        int rc = rtpp_engine_init_instances(eng_, &slot, a, g);
+        if (rc) {
+            Fail("rtpp_engine_init_instances", rc);
+            return;
+        }
+        started_ = true;
+    } else
+        agent = point;
+}
+
+// reference RTRRT.cpp:38-55
+void RTRRTplanner::SetGoal(RTpoint &point) {
+    if (point.x >= shapeX || point.y >= shapeY) {
+        printf("SetGoal error: Init point is too large!!\r\n");
+        return;
+    }
+    if (Obsmap.at<uint8_t>((int)point.y, (int)point.x)) {
+        printf("SetAgent error: robot can't be here!!\r\n");
+        return;
+    }
+    if (goal != point) goal = point;
+}
+
+void RTRRTplanner::AddDynamicObstacle(int num, RTrrt_DynamicObstacle &obs) { DObstacles[num] = obs; }
+void RTRRTplanner::DelDynamicObstacle(int num) { DObstacles.erase(num); }
+
+void RTRRTplanner::SetDObsmap(const uint8_t *plane) {
+    if (DObsmap.empty()) return;
+    if (plane) memcpy(DObsmap.data.data(), plane, DObsmap.data.size());
+    else DObsmap.zero();
+    if (!ctx_) return;
+    rtpp_map_set_plane(ctx_, RTPP_PLANE_DYNAMIC, DObsmap.data.data(), shapeX, shapeY);
+    if (EnsureEngine()) rtpp_engine_set_map(eng_, 0, 2, DObsmap.data.data(), shapeX, shapeY);
+}
+
+// reference RTRRT.cpp:138-169: fresh zero plane, circles / polygon of value 127 at the rotated outline
+void RTRRTplanner::DrawDObsmap(void) {
+    if (DObsmap.empty()) return;
+    DObsmap.zero();
+    for (const auto &kv : DObstacles) {
+        const RTrrt_DynamicObstacle &obs = kv.second;
+        const float sinangle = sinf(obs.angle), cosangle = cosf(obs.angle);
+        std::vector<std::pair<int, int>> pts;
+        for (const RTpoint &p : obs.OutLine) {
+            const float a = cosangle * p.x, b = sinangle * p.y, c = sinangle * p.x, d = cosangle * p.y;
+            pts.push_back({(int)((a - b) + obs.x), (int)((c + d) + obs.y)});
+        }
+        if (obs.DObsType == 0)
+            for (const auto &q : pts) rtpp::fill_circle(DObsmap, q.first, q.second, (int)obs.radius, 127);
+        else if (obs.DObsType == 1)
+            rtpp::fill_polygon(DObsmap, pts, 127);
+    }
+    SetDObsmap(DObsmap.data.data());
+}
+
+void RTRRTplanner::UploadAgentGoal() {
+    const float a[2] = {agent.x, agent.y}, g[2] = {goal.x, goal.y};
+    rtpp_engine_set_inputs(eng_, a, g, nullptr, nullptr);
+}
+
+// reference RTRRT.cpp:92-136
+void RTRRTplanner::UpdateTree(void) {
+    if (!started_) return;
+    UploadAgentGoal();
+    int rc = rtpp_engine_tick(eng_, 1, 0, dt_ns_, 0);
+    if (rc) Fail("rtpp_engine_tick", rc);
+    long long st[16];
+    if (rtpp_engine_read_stats(eng_, st) == 0) {
+        float xy[2];
+        int n = 0;
+        // the root id may have moved: fetch its coordinates
+        std::vector<float> all((size_t)st[0] * 2);
+        if (rtpp_engine_read_tree(eng_, 0, (int)st[0], all.data(), nullptr, nullptr, nullptr, &n) == 0 && st[1] < n) {
+            xy[0] = all[2 * st[1]], xy[1] = all[2 * st[1] + 1];
+            root = {xy[0], xy[1]};
+        }
+    }
+}
+
+int RTRRTplanner::NextRand() {
+    if (rand_stream_) return rand_pos_ < rand_n_ ? rand_stream_[rand_pos_++] : 0;
+    return rand();
+}
+
+// reference RTRRT.cpp:234-262 (host-only: glibc sinf/cosf/atan2f/sqrtf).  The float overloads of
+// sqrt/atan2 are what the reference's translation unit resolves to (CGAL/double.h:26 pulls <math.h>).
+// Guard: a degenerate ellipse (c_base < |goal-root|, reference loops forever) samples uniformly.
+RTpoint RTRRTplanner::SamplePoint() {
+    const float p0 = NextRand() / (float(RAND_MAX));
+    float rx, ry;
+    const bool degenerate = c_base >= 0 && c_base < (goal % root);
+    if (p0 < 0.1f || c_base < 0 || degenerate) {
+        rx = NextRand() / (float(RAND_MAX)) * shapeX;
+        ry = NextRand() / (float(RAND_MAX)) * shapeY;
+    } else {
+        const float c_min = goal % root;
+        const float a = c_base / 2.0f;
+        const float b = sqrtf(c_base * c_base - c_min * c_min) / 2.0f;
+        const float angle = atan2f(goal.y - root.y, goal.x - root.x);
+        for (int guard = 0;; guard++) {
+            const float th = NextRand() / (float(RAND_MAX)) * 2 * 3.141592954f;
+            const float rr = sqrtf(NextRand() / (float(RAND_MAX)));
+            const float x = a * cosf(th) * rr, y = b * sinf(th) * rr;
+            rx = cosf(angle) * x - sinf(angle) * y;
+            ry = sinf(angle) * x + cosf(angle) * y;
+            rx = rx + (goal.x + root.x) / 2;
+            ry = ry + (goal.y + root.y) / 2;
+            if (rx >= 0 && rx < shapeX && ry >= 0 && ry < shapeY) break;
+            if (guard > 100000 || (rand_stream_ && rand_pos_ >= rand_n_)) break;
+        }
+    }
+    return {rx, ry};
+}
+
+// reference RTRRT.cpp:226-355.  The samples of one call depend only on (c_base, root, goal, shape),
+// all fixed during the call, so they are drawn up front on the host and the engine consumes as
+// many as the (virtual) time budget allows; unused draws are returned to the stream.
+void RTRRTplanner::ExpandRewiring(long RunTime) {
+    if (!started_) return;
+    const long long reads = (long long)RunTime * 1000000LL / dt_ns_;
+    const int n = (int)std::min<long long>(max_samples_, reads + 1);
+    std::vector<float> pts((size_t)max_samples_ * 2, 0.f);
+    std::vector<long long> offs(n + 1);
+    const long long pos0 = rand_pos_;
+    for (int i = 0; i < n; i++) {
+        offs[i] = rand_pos_;
+        const RTpoint p = SamplePoint();
+        pts[2 * i] = p.x, pts[2 * i + 1] = p.y;
+    }
+    offs[n] = rand_pos_;
+    const int32_t ns = n;
+    int rc = rtpp_engine_set_inputs(eng_, nullptr, nullptr, pts.data(), &ns);
+    if (!rc) rc = rtpp_engine_tick(eng_, 0, RunTime, dt_ns_, 0);
+    long long st[16] = {0};
+    if (!rc) rc = rtpp_engine_read_stats(eng_, st);
+    if (rc) {
+        Fail("ExpandRewiring", rc);
+        return;
+    }
+    if (st[9]) fprintf(stderr, "RTRRTplanner: engine capacity exceeded (status %lld)\n", st[9]);
+    if (rand_stream_) rand_pos_ = offs[st[2] < n ? st[2] : n]; // give back the draws of unused samples
+    (void)pos0;
+}
+
+void RTRRTplanner::Start(void) {}
+
+// reference RTRRT.cpp:483-493
+void RTRRTplanner::MainTask(void) {
+    DrawDObsmap();
+    UpdateTree();
+    ExpandRewiring(50);
+}
+
+// reference RTRRT.cpp:202-222 — a single edge through the batched kernel (callers with many edges
+// should use rtpp_edges_check directly).
+bool RTRRTplanner::CrashDetection(const RTpoint &ps, const RTpoint &pe) {
+    if (!ctx_) return true;
+    const float e[4] = {ps.x, ps.y, pe.x, pe.y};
+    uint32_t bits = 1;
+    int rc = rtpp_edges_check(ctx_, e, 1, 5, RTPP_PLANE_STATIC | RTPP_PLANE_DYNAMIC, &bits);
+    if (rc) Fail("rtpp_edges_check", rc);
+    return bits & 1u;
+}
+
+int RTRRTplanner::NodeCount() {
+    long long st[16];
+    if (!started_ || rtpp_engine_read_stats(eng_, st)) return 0;
+    return (int)st[0];
+}
+int RTRRTplanner::ReadTree(float *xy, int32_t *parent, float *cost, uint8_t *col, int max_nodes) {
+    int n = 0;
+    if (!started_ || rtpp_engine_read_tree(eng_, 0, max_nodes, xy, parent, cost, col, &n)) return 0;
+    return n;
+}
+void RTRRTplanner::QueueSizes(int *qr, int *qs) {
+    long long st[16] = {0};
+    if (started_) rtpp_engine_read_stats(eng_, st);
+    *qr = (int)st[7], *qs = (int)st[8];
+}
+long long RTRRTplanner::ClockReads() {
+    long long st[16] = {0};
+    if (started_) rtpp_engine_read_stats(eng_, st);
+    return st[3];
+}
+
+void RTRRTplanner::SyncNodeMap() {
+    Node_Map.clear();
+    const int n = NodeCount();
+    if (n <= 0) return;
+    std::vector<float> xy((size_t)n * 2), cost(n);
+    std::vector<int32_t> par(n);
+    std::vector<uint8_t> col(n);
+    ReadTree(xy.data(), par.data(), cost.data(), col.data(), n);
+    for (int i = 0; i < n; i++) {
+        RTrrt_NodeAttribute &a = Node_Map[{xy[2 * i], xy[2 * i + 1]}];
+        a.cost = {col[i] != 0, cost[i]};
+        a.par = par[i] >= 0 ? RTpoint{xy[2 * par[i]], xy[2 * par[i] + 1]} : RTpoint{-1, -1};
+    }
+    for (int i = 0; i < n; i++)
+        if (par[i] >= 0) Node_Map[{xy[2 * par[i]], xy[2 * par[i] + 1]}].subs.insert({xy[2 * i], xy[2 * i + 1]});
+}
+
+// reference RTRRT.cpp:356-478.  The goal-entry branches run on the device; the depth-<=5 fallback
+// (no collision-free entry among the 25-NN of the goal, :401-437) walks the materialised Node_Map.
+RTrrt_Cost RTRRTplanner::GetPath(std::list<RTpoint> &path) {
+    c_base = -1;
+    path.clear();
+    if (goal.x <= 0 || !started_) return {1, 3.4e38f};
+    UploadAgentGoal();
+    int rc = rtpp_engine_tick(eng_, 0, 0, dt_ns_, 1);
+    long long st[16] = {0};
+    if (!rc) rc = rtpp_engine_read_stats(eng_, st);
+    if (rc) {
+        Fail("GetPath", rc);
+        return {1, 3.4e38f};
+    }
+    float pcost, cb;
+    const uint32_t pc = (uint32_t)st[12], cbb = (uint32_t)st[13];
+    memcpy(&pcost, &pc, 4), memcpy(&cb, &cbb, 4);
+    c_base = cb;
+    if (st[11] == 0 && st[10] > 0) { // collision-free path found on the device
+        std::vector<int32_t> ids(st[10]);
+        int len = 0;
+        rtpp_engine_read_path(eng_, 0, (int)ids.size(), ids.data(), &len);
+        const int n = NodeCount();
+        std::vector<float> xy((size_t)n * 2);
+        ReadTree(xy.data(), nullptr, nullptr, nullptr, n);
+        for (int id : ids) path.push_back(id == -2 ? goal : RTpoint{xy[2 * id], xy[2 * id + 1]});
+        return {0, pcost};
+    }
+    if (pcost == 2.4e38f) return {1, 2.4e38f}; // >2000 hops (reference :392-396)
+    SyncNodeMap();
+    RTpoint x_min = {-1, -1};
+    RTrrt_Cost c_min = {1, 3.3e38f};
+    std::queue<std::pair<int, RTpoint>> Q;
+    Q.push({0, root});
+    while (!Q.empty()) {
+        auto cur = Q.front();
+        Q.pop();
+        RTrrt_NodeAttribute &nc = Node_Map[cur.second];
+        if (cur.first < 5 && nc.subs.size())
+            for (const RTpoint &s : nc.subs)
+                if (!Node_Map[s].cost.collision) Q.push({cur.first + 1, s});
+        RTrrt_Cost c_now = {nc.cost.collision, cur.second % goal};
+        if (c_now < c_min) c_min = c_now, x_min = cur.second;
+    }
+    RTpoint x_i = x_min;
+    while (x_i.x >= 0) {
+        path.push_front(x_i);
+        x_i = Node_Map[x_i].par;
+        if (path.size() > 2000) {
+            path.clear();
+            return {1, 2.4e38f};
+        }
+    }
+    return {1, 3.4e38f};
+}

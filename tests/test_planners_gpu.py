@@ -1,0 +1,82 @@
+"""Drop-in parity: the C++ RTRRTplanner class (rtpp_b200/planners, GPU engine underneath) driven
+through the reference's own method sequence must reproduce the golden vectors that the REFERENCE
+produced (tests/golden/rtrrt_*.npz, from oracle/_ref): node set, parents, cost bits, collision flags,
+queue lengths, rand() consumption and the returned path, tick after tick."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import TESTD_OUTLINES, dyn_plane, golden_cases
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("case", golden_cases()["rtrrt"], ids=lambda c: c["name"])
+def test_cpp_planner_reproduces_reference_golden(oracle, case):
+    from rtpp_b200 import capi
+
+    g = np.load(os.path.join(GOLD, f"rtrrt_{case['name']}.npz"))
+    S = oracle.load_map(case["map"])
+    pl = capi.PlannerRTRRT(S)
+    pl.set_clock(case["dt"])
+    pl.set_rand(oracle.rand31(case["seed"], case["n_rand"]))
+    pl.set_agent(*case["agent"])
+    pl.set_goal(*case["goal"])
+    rng = np.random.default_rng(case["seed"])
+    for tick in range(case["ticks"]):
+        if tick in case["dobs_ticks"]:
+            pl.set_dobs(dyn_plane(S.shape, rng, n_blobs=6))
+        pl.update_tree()
+        pl.expand_rewiring(50)
+        path, col, cost = pl.get_path()
+        xy, par, c, cl = pl.dump()
+        k = f"t{tick}_"
+        assert pl.rand_pos() == int(g[k + "rand_pos"])
+        assert np.array_equal(xy, g[k + "xy"]) and np.array_equal(par, g[k + "par"])
+        assert np.array_equal(c.view(np.uint32), g[k + "cost"].view(np.uint32)) and np.array_equal(cl, g[k + "col"])
+        assert tuple(g[k + "queues"]) == pl.queue_sizes()
+        assert bool(g[k + "path_col"]) == col and np.array_equal(path, g[k + "path"])
+        assert np.float32(cost).view(np.uint32) == g[k + "path_cost"].view(np.uint32)
+        if tick in case["move_ticks"]:
+            t = xy[(len(xy) * 2) // 3]
+            pl.set_agent(float(t[0]), float(t[1]))
+    pl.close()
+
+
+def test_cpp_planner_main_task_with_obstacles(oracle):
+    """MainTask() = DrawDObsmap + UpdateTree + ExpandRewiring(50) with the scripted GAME0 obstacle
+    set; the drawn plane equals the oracle rasteriser's and single-edge CrashDetection agrees."""
+    from rtpp_b200 import capi
+
+    S = oracle.load_map("GAME0")
+    pl = capi.PlannerRTRRT(S)
+    pl.set_clock(20000)
+    pl.set_rand(oracle.rand31(5, 1_000_000))
+    pl.set_agent(350.0, 2350.0)
+    pl.set_goal(1400.0, 2050.0)
+    obs = [(0, 370, 388, 0.0, 57, [(0, 0)]), (0, 2370, 630, 0.0, 114, [(0, 0)]),
+           (1, 1364, 1364, 0.78539816, 0, TESTD_OUTLINES[3]), (1, 1340, 2520, 0.0, 0, TESTD_OUTLINES[4])]
+    want = np.zeros(S.shape, np.uint8)
+    for num, (typ, x, y, ang, rad, outline) in enumerate(obs):
+        pl.add_obstacle(num, typ, x, y, ang, rad, outline)
+        c, s = np.float32(np.cos(np.float32(ang))), np.float32(np.sin(np.float32(ang)))
+        o = np.array(outline, np.float32)
+        px = (c * o[:, 0] - s * o[:, 1] + np.float32(x)).astype(np.int32)
+        py = (s * o[:, 0] + c * o[:, 1] + np.float32(y)).astype(np.int32)
+        if typ == 0:
+            for qx, qy in zip(px, py):
+                oracle.raster_circle(want, int(qx), int(qy), int(rad))
+        else:
+            oracle.raster_fillpoly(want, np.stack([px, py], 1))
+    for _ in range(3):
+        pl.main_task()
+    assert np.array_equal(pl.get_dobs(), want)
+    assert pl.num_nodes() > 20
+    xy = pl.dump()[0]
+    e = np.concatenate([xy[:-1], xy[1:]], 1)[:200]
+    want_v = oracle.edges_check(S, want, e, 5, 3)
+    got_v = np.array([pl.crash(r[:2], r[2:]) for r in e], np.uint8)
+    assert np.array_equal(got_v, want_v)
+    pl.close()
