@@ -12,6 +12,7 @@
 
 #include "knn.cuh"
 #include "nodes.cuh"
+#include "scan.cuh"
 
 static constexpr int kTailMax = 512;
 
@@ -24,32 +25,6 @@ __global__ void __launch_bounds__(256) grid_count_kernel(const float2 *__restric
         cell_of[i] = c;
         atomicAdd(&count[c], 1);
     }
-}
-
-// exclusive scan of count[0..m) into start[0..m]; one block, each thread owns a contiguous slice
-// (count and cursor may alias: every thread reads count[i] before it overwrites cursor[i])
-__global__ void __launch_bounds__(1024) grid_scan_kernel(const int *count, int m, int *__restrict__ start, int *cursor) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x, per = (m + 1023) / 1024;
-    const int a = min(m, t * per), b = min(m, a + per);
-    int s = 0;
-    for (int i = a; i < b; i++) s += count[i];
-    part[t] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) { // Hillis-Steele inclusive scan of the 1024 partials
-        int v = (t >= off) ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    int run = part[t] - s;
-    for (int i = a; i < b; i++) {
-        const int c = count[i];
-        start[i] = run;
-        cursor[i] = run;
-        run += c;
-    }
-    if (t == 1023) start[m] = part[1023];
 }
 
 __global__ void __launch_bounds__(256) grid_scatter_kernel(const float2 *__restrict__ xy, const int *__restrict__ cell_of,
@@ -111,7 +86,7 @@ void rtpp_nodes_destroy(rtpp_ctx *ctx) {
     NodeStore *s = ctx->nodes;
     if (!s) return;
     cudaFree(s->xy), cudaFree(s->sxy), cudaFree(s->sid), cudaFree(s->cell_of), cudaFree(s->cell_start), cudaFree(s->cursor);
-    cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
+    cudaFree(s->scan_totals), cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
     delete s;
     ctx->nodes = nullptr;
 }
@@ -133,8 +108,10 @@ int rtpp_nodes_build_internal(rtpp_ctx *ctx) {
     grid_count_kernel<<<grid_for(ctx, s->n), 256, 0, ctx->stream>>>(s->xy, s->n, s->shift, s->gw, s->gh, s->cell_of, s->cursor);
     RTPP_LAUNCHED(ctx);
     // cursor currently holds the counts; scan them into cell_start and reset cursor to the starts
-    grid_scan_kernel<<<1, 1024, 0, ctx->stream>>>(s->cursor, m, s->cell_start, s->cursor);
-    RTPP_LAUNCHED(ctx);
+    {
+        int rc = rtpp_exclusive_scan(ctx, s->cursor, m, s->cell_start, s->cursor, s->scan_totals);
+        if (rc) return rc;
+    }
     grid_scatter_kernel<<<grid_for(ctx, s->n), 256, 0, ctx->stream>>>(s->xy, s->cell_of, s->n, s->cursor, s->sxy, s->sid);
     RTPP_LAUNCHED(ctx);
     s->n_sorted = s->n;
@@ -176,6 +153,7 @@ int rtpp_nodes_reset(rtpp_ctx *ctx, int cell_log2, size_t capacity, int domain_w
     RTPP_CK(ctx, cudaMalloc(&s->cell_of, capacity * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cell_start, m * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cursor, m * sizeof(int)));
+    RTPP_CK(ctx, cudaMalloc(&s->scan_totals, ((m > capacity ? m : capacity) / 2048 + 4) * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cp, capacity * sizeof(unsigned long long)));
     RTPP_CK(ctx, cudaMemsetAsync(s->cp, 0xff, capacity * sizeof(unsigned long long), ctx->stream));
     RTPP_CK(ctx, cudaMemsetAsync(s->cell_start, 0, m * sizeof(int), ctx->stream));

@@ -33,6 +33,7 @@ struct NodeStore {
     int *cell_of = nullptr;     // [capacity] scratch
     int *cell_start = nullptr;  // [gw*gh + 1]
     int *cursor = nullptr;      // [gw*gh + 1]
+    int *scan_totals = nullptr; // scratch of the prefix sums
     cpword *cp = nullptr;       // [capacity] cost|parent words
     // tree.cu scratch (allocated on first use)
     uint32_t *edge_w = nullptr; // per node: weight of the edge (parent -> node)

@@ -18,6 +18,7 @@
 #include <math_constants.h>
 
 #include "nodes.cuh"
+#include "scan.cuh"
 namespace cg = cooperative_groups;
 
 static int grid_for(rtpp_ctx *ctx, size_t n, int per_block = 256) {
@@ -58,30 +59,6 @@ tree_edge_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const cpwo
     }
 }
 
-__global__ void __launch_bounds__(1024) tree_scan_kernel(const int *count, int m, int *start, int *cursor) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x, per = (m + 1023) / 1024;
-    const int a = min(m, t * per), b = min(m, a + per);
-    int s = 0;
-    for (int i = a; i < b; i++) s += count[i];
-    part[t] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        int v = (t >= off) ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    int run = part[t] - s;
-    for (int i = a; i < b; i++) {
-        const int c = count[i];
-        start[i] = run;
-        cursor[i] = run;
-        run += c;
-    }
-    if (t == 1023) start[m] = part[1023];
-}
-
 __global__ void __launch_bounds__(256) tree_children_kernel(const cpword *__restrict__ cp, int n, int root,
                                                            int *__restrict__ cursor, int *__restrict__ children) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -112,21 +89,37 @@ tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int 
         const int *cur = frontier + (size_t)(level & 1) * capacity;
         int *nxt = frontier + (size_t)((level + 1) & 1) * capacity;
         if (tid == 0) counters[(level + 2) % 3] = 0;
-        for (int f = tid; f < cur_n; f += nth) {
-            const int p = cur[f];
-            const uint32_t hp = cp_hi(cp[p]);
-            const int s = child_start[p], e = child_start[p + 1];
-            for (int j = s; j < e; j++) {
-                const int c = children[j];
+        // one frontier node per thread; the warp reserves its children's slots with ONE atomicAdd
+        for (int f0 = (tid & ~31); f0 < cur_n; f0 += nth) {
+            const int f = f0 + (tid & 31);
+            int p = -1, s = 0, e = 0;
+            uint32_t hp = 0;
+            if (f < cur_n) {
+                p = cur[f];
+                hp = cp_hi(cp[p]);
+                s = child_start[p], e = child_start[p + 1];
+            }
+            const int cnt = e - s;
+            int x = cnt;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, off);
+                if ((tid & 31) >= off) x += y;
+            }
+            const int total = __shfl_sync(0xffffffffu, x, 31);
+            int base = 0;
+            if ((tid & 31) == 31 && total) base = atomicAdd(cnt_next, total);
+            base = __shfl_sync(0xffffffffu, base, 31) + x - cnt;
+            for (int j = 0; j < cnt; j++) {
+                const int c = children[s + j];
                 const uint32_t hn = cost_add(hp, w[c]);
                 if (flags) {
                     const uint32_t ho = cp_hi(cp[c]);
                     flags[c] = (uint8_t)(((hn >> 31) & ~(ho >> 31) & 1u) | ((hn > ho) ? 2u : 0u) | ((hn < ho) ? 4u : 0u));
                 }
                 cp[c] = cp_make(hn, p);
-                nxt[atomicAdd(cnt_next, 1)] = c;
+                nxt[base + j] = c;
             }
-            if (e > s) atomicAdd(&counters[3], e - s);
+            if ((tid & 31) == 31 && total) atomicAdd(&counters[3], total);
         }
         grid.sync();
     }
@@ -283,8 +276,8 @@ int rtpp_tree_propagate_dev(rtpp_ctx *ctx, int root, int divisor, int plane_mask
     if (d_flags) RTPP_CK(ctx, cudaMemsetAsync(d_flags, 0, n, ctx->stream));
     tree_edge_weights_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(pv, s->xy, s->cp, n, root, mt, s->edge_w, s->child_start);
     RTPP_LAUNCHED(ctx);
-    tree_scan_kernel<<<1, 1024, 0, ctx->stream>>>(s->child_start, n, s->child_start, cursor);
-    RTPP_LAUNCHED(ctx);
+    rc = rtpp_exclusive_scan(ctx, s->child_start, n, s->child_start, cursor, s->scan_totals);
+    if (rc) return rc;
     tree_children_kernel<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(s->cp, n, root, cursor, s->children);
     RTPP_LAUNCHED(ctx);
     // persistent cooperative walk: one block for small trees (cheap syncs), else all SMs
