@@ -302,6 +302,73 @@ class Engine:
         return ids[: min(n.value, cap)]
 
 
+class FmtEngine:
+    """ctypes mirror of the rtpp_fmt_* entry points (RT-FMT engine)."""
+
+    STAT = ["n_nodes", "root", "z", "n_unv", "n_open", "n_opennew", "n_toopen", "x_near", "n_b", "qo_size", "qr_size",
+            "expand_calls", "status", "path_len", "path_ok"]
+
+    def __init__(self, ctx, n_instances, node_capacity, cell_log2, domain_w, domain_h):
+        self.ctx, self.L, self.n, self.cap = ctx, ctx.L, n_instances, node_capacity
+        h = C.c_void_p()
+        ctx._ck(self.L.rtpp_fmt_create(ctx.h, n_instances, node_capacity, cell_log2, domain_w, domain_h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.rtpp_fmt_destroy(self.h)
+            self.h = None
+
+    def set_map(self, slot, plane, rowmajor):
+        if rowmajor is None:
+            self.ctx._ck(self.L.rtpp_fmt_set_map(self.h, slot, plane, None, 0, 0))
+        else:
+            a = _c(rowmajor, np.uint8)
+            self.ctx._ck(self.L.rtpp_fmt_set_map(self.h, slot, plane, _p(a), a.shape[1], a.shape[0]))
+
+    def start(self, map_slot, nodes_list, goal_xy):
+        """nodes_list: per instance an (n_i, 2) float32 array, row 0 = the agent."""
+        xy = np.zeros((self.n, self.cap, 2), np.float32)
+        nn = np.zeros(self.n, np.int32)
+        for i, a in enumerate(nodes_list):
+            a = _c(a, np.float32).reshape(-1, 2)
+            xy[i, : len(a)] = a
+            nn[i] = len(a)
+        s, g = _c(map_slot, np.int32), _c(goal_xy, np.float32).reshape(self.n, 2)
+        self.ctx._ck(self.L.rtpp_fmt_start(self.h, _p(s), _p(nn), _p(xy), _p(g)))
+
+    def set_inputs(self, agent_xy=None, goal_xy=None):
+        a = None if agent_xy is None else _c(agent_xy, np.float32).reshape(self.n, 2)
+        g = None if goal_xy is None else _c(goal_xy, np.float32).reshape(self.n, 2)
+        self.ctx._ck(self.L.rtpp_fmt_set_inputs(self.h, _p(a), _p(g)))
+
+    def tick(self, update_tree=True, iters=500, with_rewire=True, get_path=False):
+        self.ctx._ck(self.L.rtpp_fmt_tick(self.h, int(update_tree), int(iters), int(with_rewire), int(get_path)))
+
+    def stats(self):
+        out = np.zeros((self.n, 16), np.int64)
+        self.ctx._ck(self.L.rtpp_fmt_read_stats(self.h, _p(out)))
+        return out
+
+    def stats_dict(self, inst=0):
+        return dict(zip(self.STAT, self.stats()[inst].tolist()))
+
+    def read_tree(self, inst=0):
+        n = C.c_int()
+        self.ctx._ck(self.L.rtpp_fmt_read_tree(self.h, inst, 0, None, None, None, None, C.byref(n)))
+        n = n.value
+        par, cost = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        col, st = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self.ctx._ck(self.L.rtpp_fmt_read_tree(self.h, inst, n, _p(par), _p(cost), _p(col), _p(st), C.byref(C.c_int())))
+        return par, cost, col, st
+
+    def read_path(self, inst=0, cap=2048):
+        ids = np.zeros(cap, np.int32)
+        n = C.c_int()
+        self.ctx._ck(self.L.rtpp_fmt_read_path(self.h, inst, cap, _p(ids), C.byref(n)))
+        return ids[: min(n.value, cap)]
+
+
 # ---------------------------------------------------------------------------------------------
 # C++ drop-in planner classes (rtpp_b200/planners, librtpp_planners.so) through their C harness
 # ---------------------------------------------------------------------------------------------
