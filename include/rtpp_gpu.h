@@ -185,9 +185,23 @@ RTPP_API int rtpp_engine_init_instances(rtpp_engine *e, const int32_t *map_slot,
 RTPP_API int rtpp_engine_set_inputs(rtpp_engine *e, const float *agent_xy, const float *goal_xy, const float *samples_xy,
                                     const int32_t *n_samples);
 RTPP_API int rtpp_engine_tick(rtpp_engine *e, int do_update_tree, long run_ms, long long dt_ns, int do_get_path);
+/* planner_kind 2 = AM-RRT* (divisor 2): the tick runs UpdateTree AMRRT.cpp:156-200, then the MainTask loop
+ * AMRRT.cpp:598-613 = { Expand :395-481 (sampler, Steer :354-390 with CrashDetectionStart :287-308 and
+ * DiffusivityMetric :94-116, choose-parent), RewireRoot :483-519 } under the virtual clock (run_ms > 0
+ * enables the loop; its budgets are the reference's 80 / 20 / 5 ms), and GetPath :310-351.  rand() is
+ * consumed on the device from an injected stream (`max_samples` of rtpp_engine_create = draws per
+ * instance and call).  RewireGoal (:521-585) is only reachable when the goal point itself becomes a
+ * tree node; that is reported as status 3 and not run. */
+RTPP_API int rtpp_engine_set_diffusion(rtpp_engine *e, const int32_t *cells_ij, int ncells, const float *matrix, int dim,
+                                       float ratio);
+/* rand: n_inst rows of `max_samples` raw rand() values, n_rand[i] valid; ellipse: 6 floats per instance
+ * {c_base/2, sqrtf(c_base^2-c_min^2)/2, cosf(angle), sinf(angle), (goal.x+root.x)/2, (goal.y+root.y)/2}
+ * (AMRRT.cpp:418-432; host glibc); outpath_nonempty: OutPath.size() != 0.  NULL = unchanged. */
+RTPP_API int rtpp_engine_set_am_inputs(rtpp_engine *e, const int32_t *rand, const int32_t *n_rand, const float *ellipse,
+                                       const int32_t *outpath_nonempty);
 /* 16 int64 per instance: n_nodes, root, samples_used, clock_reads, iterations, pops_r, pops_s,
- * qr_size, qs_size, status (0 ok, 1 node store full, 2 queue overflow), path_len, path_collision,
- * path_cost (float bits), c_base (float bits), 0, 0 */
+ * qr_size, qs_size, status (0 ok, 1 node store full, 2 queue overflow, 3 RewireGoal needed),
+ * path_len, path_collision, path_cost (float bits), c_base (float bits), rand_pos, rand_exhausted */
 RTPP_API int rtpp_engine_read_stats(rtpp_engine *e, long long *out16);
 RTPP_API int rtpp_engine_read_tree(rtpp_engine *e, int inst, int max_nodes, float *xy, int32_t *parent, float *cost,
                                    uint8_t *collision, int *n_out);

@@ -271,7 +271,20 @@ class Engine:
         self._ck(self.L.rtpp_engine_tick(self.h, int(update_tree), C.c_long(run_ms), C.c_longlong(dt_ns), int(get_path)))
 
     STAT = ["n_nodes", "root", "samples_used", "clock_reads", "iters", "pops_r", "pops_s", "qr_size", "qs_size", "status",
-            "path_len", "path_col", "path_cost_bits", "c_base_bits"]
+            "path_len", "path_col", "path_cost_bits", "c_base_bits", "rand_pos", "rand_exhausted"]
+
+    # ---- AM-RRT* (kind 2)
+    def set_diffusion(self, cells_ij, matrix, ratio):
+        cells = _c(cells_ij, np.int32).reshape(-1, 2)
+        m = _c(matrix, np.float32).reshape(len(cells), -1)
+        self._ck(self.L.rtpp_engine_set_diffusion(self.h, _p(cells), len(cells), _p(m), m.shape[1], C.c_float(ratio)))
+
+    def set_am_inputs(self, rand=None, n_rand=None, ellipse=None, outpath_nonempty=None):
+        r = None if rand is None else _c(rand, np.int32).reshape(self.n, self.max_samples)
+        nr = None if n_rand is None else _c(n_rand, np.int32)
+        el = None if ellipse is None else _c(ellipse, np.float32).reshape(self.n, 6)
+        op = None if outpath_nonempty is None else _c(outpath_nonempty, np.int32)
+        self._ck(self.L.rtpp_engine_set_am_inputs(self.h, _p(r), _p(nr), _p(el), _p(op)))
 
     def stats(self):
         out = np.zeros((self.n, 16), np.int64)

@@ -18,6 +18,9 @@
 #include <float.h>
 #include <math_constants.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "nodes.cuh"
 
 #define FULL 0xffffffffu
@@ -32,9 +35,12 @@ struct EngInst {
     long long clk_n;
     int samp_pos, samp_n;
     long long iters, pops_r, pops_s;
-    int status; // 0 ok; 1 node store full; 2 queue overflow
+    int status; // 0 ok; 1 node store full; 2 queue overflow; 3 RewireGoal needed (goal is a tree node)
     int path_len, path_col;
     float path_cost;
+    // AM-RRT* (planner_kind 2): injected rand() stream position and the informed-sampler ellipse
+    int rand_pos, rand_n, rand_exhausted, outpath_nonempty;
+    float ell_a, ell_b, ell_cos, ell_sin, ell_mx, ell_my;
 };
 
 struct EngView {
@@ -50,6 +56,16 @@ struct EngView {
     int *path;
     PlaneView planes[16]; // merged S|D plane per map slot
     int divisor;
+    int kind; // 1 RT-RRT*, 2 AM-RRT*
+    // AM-RRT*: rand stream with host-tabulated cosf/sinf of the angle each draw would produce, and
+    // the diffusion-map table (AMRRT.cpp:58-116)
+    const int *rand_stream;
+    const float2 *rand_cs;
+    int rand_cap;
+    const int *diff_cell; // [diff_gw * diff_gh] row index or -1
+    const float *diff_rows;
+    int diff_gw, diff_gh, diff_dim;
+    float diff_ratio;
 };
 
 struct rtpp_engine {
@@ -59,6 +75,9 @@ struct rtpp_engine {
     int W[16], H[16];
     size_t plane_words[16];
     MarchThresholds mt;
+    int *d_rand = nullptr, *d_diff_cell = nullptr;
+    float2 *d_rand_cs = nullptr;
+    float *d_diff_rows = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -72,6 +91,8 @@ struct Inst {
     const float2 *samples;
     int *path;
     PlaneView pl;
+    const int *rand_stream; // AM-RRT*
+    const float2 *rand_cs;
 };
 
 __device__ __forceinline__ GridView inst_grid(const EngView &ev, const Inst &in) {
@@ -414,6 +435,307 @@ __device__ void get_path(const EngView &ev, Inst &in, const MarchThresholds &mt)
     }
 }
 
+
+// =============================================================================================
+// AM-RRT* (planner_kind 2): AMRRT/lib/AMrrt/AMRRT.cpp
+//   Expand :395-481 (sampler, Steer :354-390, choose-parent), RewireRoot :483-519, MainTask loop
+//   :598-613, DiffusivityMetric :94-116, CrashDetectionStart :287-308, GetPath :310-351.
+// rand() is consumed on the device from the injected stream (its consumption depends on the tree);
+// cosf32/sinf32 of the drawn angles are host-tabulated per stream position so that the glibc
+// results are used bit for bit.  RewireGoal (:521-585) runs only when the goal point itself is a
+// tree node — unreachable through Expand (the goal-bias branch :402-403 never breaks) — and is
+// reported as status 3 instead of being run.
+// =============================================================================================
+__device__ __forceinline__ int am_rand(Inst &in) { // orc::RandStream::next
+    if (in.s.rand_pos >= in.s.rand_n) {
+        in.s.rand_exhausted = 1;
+        return 0;
+    }
+    return in.rand_stream[in.s.rand_pos++];
+}
+__device__ __forceinline__ float am_u(Inst &in) { return __fdiv_rn((float)am_rand(in), 2147483648.0f); }
+// u and the tabulated (cosf, sinf) of theta = u*2*3.141592954f for the same draw
+__device__ __forceinline__ float am_u_cs(Inst &in, float2 &cs) {
+    const int pos = in.s.rand_pos;
+    cs = pos < in.s.rand_n ? in.rand_cs[pos] : make_float2(1.0f, 0.0f);
+    return am_u(in);
+}
+
+// DiffusivityMetric (AMRRT.cpp:94-116)
+__device__ float am_diffusivity(const EngView &ev, float ax, float ay, float bx, float by) {
+    const int is = __float2int_rz(__fmul_rn(ax, ev.diff_ratio)), js = __float2int_rz(__fmul_rn(ay, ev.diff_ratio));
+    if ((unsigned)is >= (unsigned)ev.diff_gw || (unsigned)js >= (unsigned)ev.diff_gh) return 3.4e38f;
+    const int ra = ev.diff_cell[js * ev.diff_gw + is];
+    if (ra < 0) return 3.4e38f;
+    const int ie = __float2int_rz(__fmul_rn(bx, ev.diff_ratio)), je = __float2int_rz(__fmul_rn(by, ev.diff_ratio));
+    if ((unsigned)ie >= (unsigned)ev.diff_gw || (unsigned)je >= (unsigned)ev.diff_gh) return 3.4e38f;
+    const int rb = ev.diff_cell[je * ev.diff_gw + ie];
+    if (rb < 0) return 3.4e38f;
+    const float *pa = ev.diff_rows + (size_t)ra * ev.diff_dim, *pb = ev.diff_rows + (size_t)rb * ev.diff_dim;
+    float len = 0.0f;
+    for (int i = 0; i < ev.diff_dim; i++) {
+        const float d = __fsub_rn(pa[i], pb[i]);
+        len = __fadd_rn(len, __fmul_rn(d, d));
+    }
+    return __fdiv_rn(__fsqrt_rn(len), ev.diff_ratio);
+}
+
+// CrashDetectionStart (AMRRT.cpp:287-308) for one edge by the whole warp
+__device__ bool am_first_hit_warp(const PlaneView &pl, float2 ps, float2 pe, float2 &pstart) {
+    const int lane = threadIdx.x & 31;
+    pstart = ps;
+    if (rt_probe(pl, __float2int_rz(ps.y), __float2int_rz(ps.x)) | rt_probe(pl, __float2int_rz(pe.y), __float2int_rz(pe.x))) return true;
+    const int M = rt_march_M(rt_dist(ps.x, ps.y, pe.x, pe.y), 2.0f);
+    const float Mf = (float)M;
+    auto point = [&](int i) {
+        const float t = __fdiv_rn((float)i, Mf), omt = __fsub_rn(1.0f, t);
+        return make_float2(__fadd_rn(__fmul_rn(pe.x, t), __fmul_rn(omt, ps.x)), __fadd_rn(__fmul_rn(pe.y, t), __fmul_rn(omt, ps.y)));
+    };
+    for (int i0 = 1; i0 < M; i0 += 32) {
+        const int i = i0 + lane;
+        bool hit = false;
+        if (i < M) {
+            const float2 q = point(i);
+            hit = rt_probe(pl, __float2int_rz(q.y), __float2int_rz(q.x));
+        }
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if (hm) {
+            const int f = i0 + __ffs(hm) - 1;
+            if (f > 1) pstart = point(f - 1);
+            return true;
+        }
+    }
+    pstart = pe;
+    return false;
+}
+
+// Steer (AMRRT.cpp:354-390)
+__device__ float2 am_steer(const EngView &ev, Inst &in, const MarchThresholds &mt, float2 xi, float2 xe, long long dt) {
+    const int lane = threadIdx.x & 31;
+    float2 x_start;
+    if (!am_first_hit_warp(in.pl, xi, xe, x_start)) {
+        const float len = rt_dist(xi.x, xi.y, xe.x, xe.y);
+        const float p = __fdiv_rn(100.0f, len);
+        if (p < 1.0f) {
+            const float omp = __fsub_rn(1.0f, p);
+            return make_float2(__fadd_rn(__fmul_rn(omp, xi.x), __fmul_rn(p, xe.x)), __fadd_rn(__fmul_rn(omp, xi.y), __fmul_rn(p, xe.y)));
+        }
+        return xe;
+    }
+    float2 x_min = x_start;
+    float c_min = am_diffusivity(ev, x_start.x, x_start.y, xe.x, xe.y);
+    const float r_sam = fminf(100.0f, rt_dist(xi.x, xi.y, xe.x, xe.y));
+    // the random local search runs while (now() - t0 < 5 ms): count the iterations first, then
+    // evaluate the candidates 32 at a time (they are independent; only the running minimum is
+    // sequential, and "strictly smaller, not blocked" = first minimum among the unblocked ones)
+    const long long t0 = clk_now(in, dt);
+    int K = 0;
+    while (clk_now(in, dt) - t0 < 5000000LL) K++;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        float2 cand = make_float2(0.f, 0.f);
+        float c_new = CUDART_INF_F;
+        if (k < K) {
+            const int pos = in.s.rand_pos + 2 * k;
+            float2 cs = make_float2(1.0f, 0.0f);
+            float rr = 0.0f;
+            if (pos < in.s.rand_n) cs = in.rand_cs[pos];
+            if (pos + 1 < in.s.rand_n) rr = __fdiv_rn((float)in.rand_stream[pos + 1], 2147483648.0f);
+            rr = __fmul_rn(__fsqrt_rn(rr), r_sam);
+            cand = make_float2(__fadd_rn(__fmul_rn(cs.x, rr), xi.x), __fadd_rn(__fmul_rn(cs.y, rr), xi.y));
+            c_new = am_diffusivity(ev, cand.x, cand.y, xe.x, xe.y);
+        }
+        bool ok = k < K && c_new < c_min;
+        if (ok) ok = !rt_edge_blocked(in.pl, xi.x, xi.y, cand.x, cand.y, mt);
+        unsigned long long key = ok ? (((unsigned long long)__float_as_uint(c_new) << 32) | (unsigned)lane) : ~0ull;
+        for (int off = 16; off; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(FULL, key, off);
+            key = o < key ? o : key;
+        }
+        if (key != ~0ull) {
+            const int j = (int)(key & 31u);
+            c_min = __uint_as_float((uint32_t)(key >> 32));
+            x_min = make_float2(__shfl_sync(FULL, cand.x, j), __shfl_sync(FULL, cand.y, j));
+        }
+    }
+    const int used = 2 * K;
+    if (in.s.rand_pos + used > in.s.rand_n) {
+        in.s.rand_exhausted = 1;
+        in.s.rand_pos = in.s.rand_n;
+    } else
+        in.s.rand_pos += used;
+    return x_min;
+}
+
+// Expand (AMRRT.cpp:395-481)
+__device__ void am_expand(const EngView &ev, Inst &in, const MarchThresholds &mt, long long dt) {
+    const int lane = threadIdx.x & 31;
+    in.s.iters++;
+    float2 x_rand = make_float2(0.f, 0.f);
+    const float W = (float)in.pl.W, H = (float)in.pl.H;
+    while (!in.s.rand_exhausted) { // SampleState
+        const float p = am_u(in);
+        if (p > 0.9f && !in.s.outpath_nonempty && in.s.goal.x >= 0.0f) {
+            x_rand = in.s.goal; // no break in the reference: draws again
+        } else if (p < (0.9f / 4.0f) || !in.s.outpath_nonempty) {
+            const float rx = __fmul_rn(am_u(in), W), ry = __fmul_rn(am_u(in), H);
+            if (!rt_probe(in.pl, __float2int_rz(ry), __float2int_rz(rx))) {
+                x_rand = make_float2(rx, ry);
+                break;
+            }
+        } else if (in.s.goal.x >= 0.0f) {
+            float2 cs;
+            am_u_cs(in, cs); // theta draw: only its cosf/sinf are needed
+            const float rr = __fsqrt_rn(am_u(in));
+            const float x = __fmul_rn(__fmul_rn(in.s.ell_a, cs.x), rr), y = __fmul_rn(__fmul_rn(in.s.ell_b, cs.y), rr);
+            float rx = __fsub_rn(__fmul_rn(in.s.ell_cos, x), __fmul_rn(in.s.ell_sin, y));
+            float ry = __fadd_rn(__fmul_rn(in.s.ell_sin, x), __fmul_rn(in.s.ell_cos, y));
+            rx = __fadd_rn(rx, in.s.ell_mx), ry = __fadd_rn(ry, in.s.ell_my);
+            if (rx >= 0.0f && rx < W && ry >= 0.0f && ry < H && !rt_probe(in.pl, __float2int_rz(ry), __float2int_rz(rx))) {
+                x_rand = make_float2(rx, ry);
+                break;
+            }
+        }
+    }
+    if (in.s.rand_exhausted) return;
+    KnnEntry e;
+    knn_warp(inst_grid(ev, in), (double)x_rand.x, (double)x_rand.y, 25, e);
+    const int x_nrst = __shfl_sync(FULL, e.id, 0);
+    const float2 p_nrst = in.xy[x_nrst];
+    const float2 x_new = am_steer(ev, in, mt, p_nrst, x_rand, dt);
+    const int found = knn_warp(inst_grid(ev, in), (double)x_new.x, (double)x_new.y, 25, e);
+    const int nearest = __shfl_sync(FULL, e.id, 0);
+    const float2 p_near = in.xy[nearest];
+    if (!(rt_dist(p_near.x, p_near.y, x_new.x, x_new.y) > 4.0f)) return; // k_max
+    // c_min starts at x_nrst WITHOUT an edge check (:455-456); neighbours must be strictly better and free
+    const uint32_t c0 = cost_add(cp_hi(in.cp[x_nrst]), cost_pack(false, rt_dist(p_nrst.x, p_nrst.y, x_new.x, x_new.y)));
+    unsigned long long key = ((unsigned long long)c0 << 32) | 63u;
+    if (lane < found) {
+        const float2 q = in.xy[e.id];
+        const uint32_t w = cost_pack(rt_edge_blocked(in.pl, q.x, q.y, x_new.x, x_new.y, mt), rt_dist(q.x, q.y, x_new.x, x_new.y));
+        const uint32_t c = cost_add(cp_hi(in.cp[e.id]), w);
+        if (c < c0 && !cost_col(c)) key = ((unsigned long long)c << 32) | (unsigned)lane;
+    }
+    for (int off = 16; off; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, key, off);
+        key = o < key ? o : key;
+    }
+    const uint32_t c_min = (uint32_t)(key >> 32);
+    if (cost_col(c_min)) return;
+    const int x_min = (key & 63u) == 63u ? x_nrst : __shfl_sync(FULL, e.id, (int)(key & 31u));
+    if (in.s.n >= ev.cap) {
+        in.s.status = 1;
+        return;
+    }
+    const int id = in.s.n;
+    if (lane == 0) {
+        in.xy[id] = x_new;
+        in.cp[id] = cp_make(c_min, x_min);
+    }
+    in.s.n = id + 1;
+    __syncwarp();
+    maybe_rebuild(ev, in);
+    // MainTask would now call RewireGoal (AMRRT.cpp:604-612: the goal point is a collision-free node)
+    if (x_new.x == in.s.goal.x && x_new.y == in.s.goal.y) in.s.status = 3;
+}
+
+// RewireRoot (AMRRT.cpp:483-519): Qroot / rewired_root reuse the Qs arrays and epoch marks
+__device__ void am_rewire_root(const EngView &ev, Inst &in, const MarchThresholds &mt, long long dt) {
+    const int lane = threadIdx.x & 31;
+    if (in.s.qs_tail == in.s.qs_head) {
+        in.s.qs_epoch++;
+        in.s.qs_head = 0, in.s.qs_tail = 1;
+        if (lane == 0) {
+            in.qs[0] = in.s.root;
+            in.qs_mark[in.s.root] = in.s.qs_epoch;
+        }
+        __syncwarp();
+    }
+    const long long t0 = clk_now(in, dt);
+    while (clk_now(in, dt) - t0 < 20000000LL && in.s.qs_tail != in.s.qs_head) {
+        const int xr = in.qs[in.s.qs_head];
+        in.s.qs_head++;
+        in.s.pops_s++;
+        const float2 pr = in.xy[xr];
+        KnnEntry e;
+        const int found = knn_warp(inst_grid(ev, in), (double)pr.x, (double)pr.y, 25, e);
+        bool free_edge = false;
+        if (lane < found) {
+            const float2 q = in.xy[e.id];
+            free_edge = !rt_edge_blocked(in.pl, q.x, q.y, pr.x, pr.y, mt); // CrashDetection(x_near, x_r)
+            if (free_edge) {
+                const uint32_t c_new = cost_add(cp_hi(in.cp[xr]), cost_pack(false, rt_dist(q.x, q.y, pr.x, pr.y)));
+                if (c_new < cp_hi(in.cp[e.id]) && !cost_col(c_new)) in.cp[e.id] = cp_make(c_new, xr);
+            }
+        }
+        __syncwarp();
+        const bool fresh = free_edge && in.qs_mark[e.id] != in.s.qs_epoch;
+        const unsigned m = __ballot_sync(FULL, fresh);
+        if (fresh) {
+            in.qs[in.s.qs_tail + __popc(m & ((1u << lane) - 1))] = e.id;
+            in.qs_mark[e.id] = in.s.qs_epoch;
+        }
+        in.s.qs_tail += __popc(m);
+        __syncwarp();
+    }
+}
+
+// MainTask loop (AMRRT.cpp:598-613) after UpdateTree
+__device__ void am_main_loop(const EngView &ev, Inst &in, const MarchThresholds &mt, long long dt) {
+    const long long t0 = clk_now(in, dt);
+    while (clk_now(in, dt) - t0 < 80000000LL && !in.s.rand_exhausted && !in.s.status) {
+        am_expand(ev, in, mt, dt);
+        am_rewire_root(ev, in, mt, dt);
+    }
+}
+
+// GetPath (AMRRT.cpp:310-351): like RT-RRT*'s goal-entry branch, without the direct shortcut
+__device__ void am_get_path(const EngView &ev, Inst &in, const MarchThresholds &mt) {
+    const int lane = threadIdx.x & 31;
+    in.s.c_base = -1.0f;
+    in.s.path_len = 0, in.s.path_col = 1, in.s.path_cost = 3.4e38f;
+    if (!(in.s.goal.x > 0.0f)) return;
+    const float2 g = in.s.goal;
+    KnnEntry e;
+    const int found = knn_warp(inst_grid(ev, in), (double)g.x, (double)g.y, 25, e);
+    unsigned long long key = ((unsigned long long)cost_pack(true, FLT_MAX) << 32) | 63u;
+    if (lane < found) {
+        const float2 q = in.xy[e.id];
+        const uint32_t w = cost_pack(rt_edge_blocked(in.pl, g.x, g.y, q.x, q.y, mt), rt_dist(g.x, g.y, q.x, q.y));
+        const uint32_t c = cost_add(cp_hi(in.cp[e.id]), w);
+        if (c < cost_pack(true, FLT_MAX)) key = ((unsigned long long)c << 32) | (unsigned)lane;
+    }
+    for (int off = 16; off; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, key, off);
+        key = o < key ? o : key;
+    }
+    if ((uint32_t)(key >> 32) < cost_pack(true, 0.0f)) {
+        const int x_min = __shfl_sync(FULL, e.id, (int)(key & 31u));
+        int len = 0, bad = 0;
+        float cb = 0.0f;
+        if (lane == 0) {
+            float2 front = g;
+            int x = x_min;
+            in.path[len++] = -2;
+            while (x >= 0) {
+                const float2 px = in.xy[x];
+                cb = __fadd_rn(cb, rt_dist(px.x, px.y, front.x, front.y));
+                if (len < ev.path_cap) in.path[len] = x;
+                len++;
+                front = px;
+                x = cp_parent(in.cp[x]);
+                if (len > 2000) {
+                    bad = 1;
+                    break;
+                }
+            }
+        }
+        len = __shfl_sync(FULL, len, 0), bad = __shfl_sync(FULL, bad, 0), cb = __shfl_sync(FULL, cb, 0);
+        if (bad) in.s.path_len = 0, in.s.path_col = 1, in.s.path_cost = 2.4e38f, in.s.c_base = -1.0f;
+        else in.s.path_len = len, in.s.path_col = 0, in.s.path_cost = cb, in.s.c_base = cb;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernels: one warp per instance
 // ---------------------------------------------------------------------------------------------
@@ -429,6 +751,8 @@ __device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
     in.samples = ev.samples + (size_t)w * ev.max_samples;
     in.path = ev.path + (size_t)w * ev.path_cap;
     in.pl = ev.planes[in.s.map_slot & 15];
+    in.rand_stream = ev.rand_stream ? ev.rand_stream + (size_t)w * ev.rand_cap : nullptr;
+    in.rand_cs = ev.rand_cs ? ev.rand_cs + (size_t)w * ev.rand_cap : nullptr;
     return true;
 }
 
@@ -439,8 +763,13 @@ __global__ void __launch_bounds__(128) engine_tick_kernel(EngView ev, MarchThres
     if (!load_inst(ev, w, in)) return;
     if (in.s.n > 0) {
         if (do_update) update_tree(ev, in, mt);
-        if (run_ns > 0) expand_rewiring(ev, in, mt, run_ns, dt);
-        if (do_path) get_path(ev, in, mt);
+        if (ev.kind == 2) {
+            if (run_ns > 0) am_main_loop(ev, in, mt, dt);
+            if (do_path) am_get_path(ev, in, mt);
+        } else {
+            if (run_ns > 0) expand_rewiring(ev, in, mt, run_ns, dt);
+            if (do_path) get_path(ev, in, mt);
+        }
     }
     if ((threadIdx.x & 31) == 0) ev.inst[w] = in.s;
 }
@@ -509,7 +838,7 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
                        int domain_h, int max_samples, rtpp_engine **out) {
     if (!ctx || !out) return RTPP_ERR_INVALID;
     *out = nullptr;
-    if (planner_kind != 1) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "planner_kind: 1 = RT-RRT*");
+    if (planner_kind != 1 && planner_kind != 2) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "planner_kind: 1 = RT-RRT*, 2 = AM-RRT*");
     if (n_instances < 1 || node_capacity < 32 || cell_log2 < 2 || cell_log2 > 10 || domain_w < 1 || domain_h < 1 || max_samples < 1)
         RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad engine geometry");
     RTPP_CK(ctx, cudaSetDevice(ctx->device));
@@ -522,8 +851,9 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
     v.n_inst = n_instances, v.cap = node_capacity, v.qr_cap = 8 * node_capacity, v.max_samples = max_samples, v.path_cap = 2048;
     v.shift = cell_log2;
     v.gw = ((domain_w - 1) >> cell_log2) + 1, v.gh = ((domain_h - 1) >> cell_log2) + 1, v.ncells = v.gw * v.gh;
-    v.divisor = 5;
-    rtpp_march_thresholds(5, &e->mt);
+    v.kind = planner_kind;
+    v.divisor = planner_kind == 2 ? 2 : 5; // AMRRT.cpp:273 vs RTRRT.cpp:209
+    rtpp_march_thresholds(v.divisor, &e->mt);
     const size_t N = (size_t)n_instances, C = N * node_capacity, G = N * (v.ncells + 1);
     int rc = 0;
     rc |= eng_alloc(e, &v.inst, N);
@@ -540,7 +870,13 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
     rc |= eng_alloc(e, &v.child_start, N * (node_capacity + 1));
     rc |= eng_alloc(e, &v.children, C);
     rc |= eng_alloc(e, &v.frontier, 2 * C);
-    rc |= eng_alloc(e, &v.samples, N * max_samples);
+    rc |= eng_alloc(e, &v.samples, planner_kind == 1 ? N * max_samples : 1);
+    if (planner_kind == 2) { // max_samples = rand() draws available per instance and call
+        v.rand_cap = max_samples;
+        rc |= eng_alloc(e, &e->d_rand, N * max_samples);
+        rc |= eng_alloc(e, &e->d_rand_cs, N * max_samples);
+        v.rand_stream = e->d_rand, v.rand_cs = e->d_rand_cs;
+    }
     rc |= eng_alloc(e, &v.path, N * v.path_cap);
     if (rc) return RTPP_ERR_NOMEM;
     *out = e;
@@ -555,6 +891,7 @@ int rtpp_engine_destroy(rtpp_engine *e) {
     cudaFree(v.cell_start), cudaFree(v.cursor), cudaFree(v.qr), cudaFree(v.qs), cudaFree(v.qs_mark);
     cudaFree(v.child_start), cudaFree(v.children), cudaFree(v.frontier), cudaFree(v.samples), cudaFree(v.path);
     for (int i = 0; i < 16; i++) cudaFree(e->plane_s[i]), cudaFree(e->plane_d[i]), cudaFree(e->plane_sd[i]);
+    cudaFree(e->d_rand), cudaFree(e->d_rand_cs), cudaFree(e->d_diff_cell), cudaFree(e->d_diff_rows);
     delete e;
     return RTPP_OK;
 }
@@ -642,6 +979,77 @@ int rtpp_engine_set_inputs(rtpp_engine *e, const float *agent_xy, const float *g
     return RTPP_OK;
 }
 
+// AM-RRT*: InitializeDiffusion (AMRRT.cpp:58-93): cells (i,j) -> row of `matrix` (ncells x dim floats)
+int rtpp_engine_set_diffusion(rtpp_engine *e, const int32_t *cells_ij, int ncells, const float *matrix, int dim, float ratio) {
+    if (!e || !cells_ij || !matrix || ncells < 1 || dim < 1) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    int gw = 1, gh = 1;
+    for (int i = 0; i < ncells; i++) {
+        if (cells_ij[2 * i] < 0 || cells_ij[2 * i + 1] < 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "negative diffusion cell");
+        gw = std::max(gw, cells_ij[2 * i] + 1), gh = std::max(gh, cells_ij[2 * i + 1] + 1);
+    }
+    std::vector<int> grid((size_t)gw * gh, -1);
+    for (int i = 0; i < ncells; i++) grid[(size_t)cells_ij[2 * i + 1] * gw + cells_ij[2 * i]] = i; // later rows win, like std::map[]=
+    cudaFree(e->d_diff_cell), cudaFree(e->d_diff_rows);
+    ENG_CK(e, cudaMalloc(&e->d_diff_cell, grid.size() * 4));
+    ENG_CK(e, cudaMalloc(&e->d_diff_rows, (size_t)ncells * dim * 4));
+    ENG_CK(e, cudaMemcpyAsync(e->d_diff_cell, grid.data(), grid.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ENG_CK(e, cudaMemcpyAsync(e->d_diff_rows, matrix, (size_t)ncells * dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    e->v.diff_cell = e->d_diff_cell, e->v.diff_rows = e->d_diff_rows;
+    e->v.diff_gw = gw, e->v.diff_gh = gh, e->v.diff_dim = dim, e->v.diff_ratio = ratio;
+    return RTPP_OK;
+}
+
+__global__ void engine_set_am_kernel(EngView ev, const int *__restrict__ n_rand, const float *__restrict__ ell, const int *__restrict__ outpath) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= ev.n_inst) return;
+    EngInst &s = ev.inst[w];
+    if (n_rand) s.rand_n = n_rand[w], s.rand_pos = 0, s.rand_exhausted = 0;
+    if (ell) {
+        const float *p = ell + 6 * w;
+        s.ell_a = p[0], s.ell_b = p[1], s.ell_cos = p[2], s.ell_sin = p[3], s.ell_mx = p[4], s.ell_my = p[5];
+    }
+    if (outpath) s.outpath_nonempty = outpath[w];
+}
+
+// AM-RRT* per-call inputs.  rand: n_inst rows of rand capacity raw rand() values (n_rand[i] valid);
+// the (cosf, sinf) table of theta = u*2*3.141592954f is computed here on the host with glibc.
+// ellipse: 6 floats per instance {a, b, cos(angle), sin(angle), (goal.x+root.x)/2, (goal.y+root.y)/2}
+// of the informed sampler (AMRRT.cpp:418-432), computed by the caller after UpdateTree;
+// outpath_nonempty: OutPath.size() != 0 (AMRRT.cpp:402,404).  Any pointer may be NULL = unchanged.
+int rtpp_engine_set_am_inputs(rtpp_engine *e, const int32_t *rand, const int32_t *n_rand, const float *ellipse,
+                              const int32_t *outpath_nonempty) {
+    if (!e || e->v.kind != 2) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    const int n = e->v.n_inst, cap = e->v.rand_cap;
+    if (rand) {
+        if (!n_rand) return RTPP_ERR_INVALID;
+        std::vector<float2> cs((size_t)n * cap);
+        for (int w = 0; w < n; w++) {
+            if (n_rand[w] < 0 || n_rand[w] > cap) RTPP_FAIL(ctx, RTPP_ERR_CAPACITY, "more rand draws than the engine's capacity");
+            for (int i = 0; i < n_rand[w]; i++) {
+                volatile float u = (float)rand[(size_t)w * cap + i] / 2147483648.0f;
+                volatile float t2 = u * 2;
+                const float th = t2 * 3.141592954f;
+                cs[(size_t)w * cap + i] = make_float2(cosf(th), sinf(th));
+            }
+        }
+        ENG_CK(e, cudaMemcpyAsync(e->d_rand, rand, (size_t)n * cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ENG_CK(e, cudaMemcpyAsync(e->d_rand_cs, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    }
+    void *dn, *de, *dout;
+    int rc = upload(e, 0, n_rand, (size_t)n * 4, &dn);
+    rc |= upload(e, 1, ellipse, (size_t)n * 24, &de);
+    rc |= upload(e, 2, outpath_nonempty, (size_t)n * 4, &dout);
+    if (rc) return rc;
+    engine_set_am_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(e->v, (const int *)dn, (const float *)de, (const int *)dout);
+    RTPP_LAUNCHED(ctx);
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
 // One MainTask minus DrawDObsmap for every instance (RTRRT.cpp:483-493): optional UpdateTree,
 // ExpandRewiring(run_ms) under the virtual clock (k-th read = k*dt_ns), optional GetPath.
 // Stream-ordered; no synchronisation.
@@ -672,7 +1080,7 @@ int rtpp_engine_read_stats(rtpp_engine *e, long long *out16) {
         memcpy(&pc, &s[i].path_cost, 4), memcpy(&cb, &s[i].c_base, 4);
         o[0] = s[i].n, o[1] = s[i].root, o[2] = s[i].samp_pos, o[3] = s[i].clk_n, o[4] = s[i].iters, o[5] = s[i].pops_r;
         o[6] = s[i].pops_s, o[7] = s[i].qr_tail - s[i].qr_head, o[8] = s[i].qs_tail - s[i].qs_head, o[9] = s[i].status;
-        o[10] = s[i].path_len, o[11] = s[i].path_col, o[12] = pc, o[13] = cb, o[14] = 0, o[15] = 0;
+        o[10] = s[i].path_len, o[11] = s[i].path_col, o[12] = pc, o[13] = cb, o[14] = s[i].rand_pos, o[15] = s[i].rand_exhausted;
     }
     return RTPP_OK;
 }
