@@ -441,6 +441,19 @@ class OrcAMRRT(_TreePlanner):
     def expand(self):
         self._f("expand")(self.h)
 
+    def set_outpath(self, nonempty):
+        self._f("set_outpath")(self.h, int(bool(nonempty)))
+
+    def c_base(self):
+        f = self._f("c_base")
+        f.restype = C.c_float
+        return float(f(self.h))
+
+    def root(self):
+        xy = np.zeros(2, np.float32)
+        self._f("root")(self.h, _ptr(xy))
+        return xy
+
     def rewire_root(self):
         self._f("rewire_root")(self.h)
 

@@ -53,6 +53,13 @@ REF_EXPORT float ref_amrrt_diffusivity(void *h, float ax, float ay, float bx, fl
     RTpoint a{ax, ay}, b{bx, by};
     return ((RefAMRRT *)h)->p.DiffusivityMetric(a, b);
 }
+REF_EXPORT void ref_amrrt_set_outpath(void *h, int nonempty) {
+    AMRRTplanner &p = ((RefAMRRT *)h)->p;
+    p.OutPath.clear();
+    if (nonempty) p.OutPath.push_back({0, 0});
+}
+REF_EXPORT float ref_amrrt_c_base(void *h) { return ((RefAMRRT *)h)->p.c_base; }
+REF_EXPORT void ref_amrrt_root(void *h, float *xy) { xy[0] = ((RefAMRRT *)h)->p.root.x, xy[1] = ((RefAMRRT *)h)->p.root.y; }
 REF_EXPORT void ref_amrrt_update_tree(void *h) { ((RefAMRRT *)h)->p.UpdateTree(); }
 REF_EXPORT void ref_amrrt_expand(void *h) { ((RefAMRRT *)h)->p.Expand(); }
 REF_EXPORT void ref_amrrt_rewire_root(void *h) { ((RefAMRRT *)h)->p.RewireRoot(); }

@@ -380,6 +380,15 @@ ORC_EXPORT void orc_amrrt_set_diffusion(void *h, const int32_t *cells_ij, int nc
 ORC_EXPORT float orc_amrrt_diffusivity(void *h, float ax, float ay, float bx, float by) {
     return ((HAMRRT *)h)->p.DiffusivityMetric({ax, ay}, {bx, by});
 }
+// OutPath is only ever filled by the caller (AMRRT/test/testD.cpp passes planner.OutPath to GetPath);
+// non-empty switches the sampler to the informed ellipse (AMRRT.cpp:402-404)
+ORC_EXPORT void orc_amrrt_set_outpath(void *h, int nonempty) {
+    AMRRT &p = ((HAMRRT *)h)->p;
+    p.OutPath.clear();
+    if (nonempty) p.OutPath.push_back({0, 0});
+}
+ORC_EXPORT float orc_amrrt_c_base(void *h) { return ((HAMRRT *)h)->p.c_base; }
+ORC_EXPORT void orc_amrrt_root(void *h, float *xy) { xy[0] = ((HAMRRT *)h)->p.root.x, xy[1] = ((HAMRRT *)h)->p.root.y; }
 ORC_EXPORT void orc_amrrt_update_tree(void *h) { ((HAMRRT *)h)->p.UpdateTree(); }
 ORC_EXPORT void orc_amrrt_expand(void *h) { ((HAMRRT *)h)->p.Expand(((HAMRRT *)h)->rs); }
 ORC_EXPORT void orc_amrrt_rewire_root(void *h) { ((HAMRRT *)h)->p.RewireRoot(); }

@@ -52,3 +52,69 @@ def test_am_engine_reproduces_reference_golden(ctx, oracle, case):
             assert np.uint32(d["path_cost_bits"]) == g[k + "path_cost"].view(np.uint32)
     assert len(xy) > 80
     eng.close()
+
+
+def _ellipse(c_base, goal, root):
+    """Host side of the informed sampler (AMRRT.cpp:418-432) with glibc float functions."""
+    import ctypes as C
+
+    m = C.CDLL("libm.so.6")
+    for f in (m.cosf, m.sinf, m.sqrtf):
+        f.restype, f.argtypes = C.c_float, [C.c_float]
+    m.atan2f.restype, m.atan2f.argtypes = C.c_float, [C.c_float, C.c_float]
+    f32 = np.float32
+    dx, dy = f32(goal[0]) - f32(root[0]), f32(goal[1]) - f32(root[1])
+    c_min = f32(m.sqrtf(f32(f32(dx * dx) + f32(dy * dy))))
+    a = f32(f32(c_base) / f32(2.0))
+    with np.errstate(invalid="ignore"):
+        b = f32(f32(m.sqrtf(f32(f32(f32(c_base) * f32(c_base)) - f32(c_min * c_min)))) / f32(2.0))
+    ang = f32(m.atan2f(dy, dx))
+    return [a, b, f32(m.cosf(ang)), f32(m.sinf(ang)), f32(f32(f32(goal[0]) + f32(root[0])) / f32(2)), f32(f32(f32(goal[1]) + f32(root[1])) / f32(2))]
+
+
+def test_am_engine_informed_sampling_against_oracle(ctx, oracle):
+    """OutPath filled by the caller (AMRRT/test/testD.cpp) switches the sampler to the informed ellipse:
+    the engine with host-computed ellipse parameters and host-tabulated cos/sin against the oracle."""
+    import rtpp_b200
+    from helpers import synthetic_diffusion
+
+    S = oracle.load_map("MESS6")
+    H, W = S.shape
+    cap_rand = 200_000
+    agent, goal = (720.0, 720.0), (1240.0, 1240.0)
+    eng = rtpp_b200.Engine(ctx, 1, 8192, 5, W, H, cap_rand, kind=2)
+    eng.set_map(0, 1, S)
+    cells, mat, ratio = synthetic_diffusion(W)
+    eng.set_diffusion(cells, mat, ratio)
+    eng.init_instances(np.zeros(1, np.int32), np.array([agent], np.float32), np.array([goal], np.float32))
+    orc = oracle.OrcAMRRT(S)
+    orc.set_diffusion(cells, mat, ratio)
+    r = oracle.rand31(33, 3_000_000)
+    orc.set_rand(r)
+    orc.set_clock(500000, 0)
+    orc.set_agent(*agent)
+    orc.set_goal(*goal)
+    pos, informed, found, c_base = 0, 0, False, -1.0
+    for tick in range(30):
+        chunk = np.zeros((1, cap_rand), np.int32)
+        chunk[0] = r[pos: pos + cap_rand]
+        eng.set_am_inputs(rand=chunk, n_rand=np.array([cap_rand], np.int32), outpath_nonempty=np.array([int(found)], np.int32))
+        eng.tick(update_tree=True, run_ms=0, dt_ns=500000, get_path=False)  # UpdateTree first: the ellipse needs the root
+        root = eng.read_tree(0)[0][eng.stats()[0][1]]
+        eng.set_am_inputs(ellipse=np.array([_ellipse(c_base, goal, root)], np.float32))
+        eng.tick(update_tree=False, run_ms=80, dt_ns=500000, get_path=True)
+        orc.main_task()
+        d = dict(zip(eng.STAT, eng.stats()[0].tolist()))
+        pos += d["rand_pos"]
+        assert d["status"] == 0 and pos == orc.rand_pos(), f"tick {tick}"
+        for x, y in zip(orc.dump(), eng.read_tree(0)):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"tick {tick}"
+        opath, ocol, ocost = orc.get_path()
+        assert bool(d["path_col"]) == ocol
+        c_base = orc.c_base()
+        assert np.float32(c_base).view(np.uint32) == np.uint32(d["c_base_bits"])
+        found = not ocol
+        orc.set_outpath(found)
+        informed += int(found)
+    assert informed >= 5
+    eng.close()

@@ -62,3 +62,34 @@ def test_rtrrt_live_with_informed_sampling(oracle):
         for x, y in zip(ref.dump(), orc.dump()):
             assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
     assert informed >= 2, "the scenario must reach the informed-sampling branch"
+
+
+def test_amrrt_live_with_informed_sampling(oracle):
+    """AM-RRT* with OutPath filled by the caller (as AMRRT/test/testD.cpp does): the informed-ellipse
+    sampler branch (AMRRT.cpp:415-441) of the oracle against the compiled reference."""
+    from helpers import synthetic_diffusion
+
+    S = oracle.load_map("MESS6")
+    ref, orc = oracle.RefAMRRT(S), oracle.OrcAMRRT(S)
+    cells, mat, ratio = synthetic_diffusion(S.shape[1])
+    r = oracle.rand31(33, 3_000_000)
+    for p in (ref, orc):
+        p.set_diffusion(cells, mat, ratio)
+        p.set_rand(r)
+        p.set_clock(500000, 0)
+        p.set_agent(720.0, 720.0)
+        p.set_goal(1240.0, 1240.0)
+    informed = 0
+    for tick in range(30):
+        for p in (ref, orc):
+            p.main_task()
+        rp, op = ref.get_path(), orc.get_path()
+        assert np.array_equal(rp[0], op[0]) and rp[1:] == op[1:]
+        found = not op[1]
+        for p in (ref, orc):
+            p.set_outpath(found)
+        informed += int(found)
+        assert ref.rand_pos() == orc.rand_pos()
+        for x, y in zip(ref.dump(), orc.dump()):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    assert informed >= 5
