@@ -212,9 +212,10 @@ RTPP_API int rtpp_engine_read_path(rtpp_engine *e, int inst, int max_len, int32_
  *   rtpp_fmt_start      = SetAgent on an empty planner + Start     RTFMT.cpp:11-36, 393-422
  *                         (the free-space samples are drawn by the host-side sampler; node 0 = agent)
  *   rtpp_fmt_set_inputs = SetAgent / SetGoal on a live planner      RTFMT.cpp:32-35, 38-55
- *   rtpp_fmt_tick       = UpdateTree RTFMT.cpp:92-176 (with N_b capture), then `iters` rounds of
- *                         ExpandFMT :423-529 [+ RewireFromObstacles :531-595 + RewireFromRoot :665-703],
- *                         GetPath :285-320 (each optional): MainTask :704-728 is tick(1, 500, 1, x).
+ *   rtpp_fmt_tick       = UpdateTree RTFMT.cpp:92-176 (with N_b capture), then `iters` rounds of the
+ *                         phases in phase_mask (1 ExpandFMT :423-529, 2 RewireFromObstacles :531-595,
+ *                         4 RewireFromRoot :665-703), GetPath :285-320 (each optional): MainTask :704-728
+ *                         is tick(1, 500, 7, x).
  * nodes_xy: per instance node_capacity (x,y) slots, n_nodes[i] used. */
 typedef struct rtpp_fmt_engine rtpp_fmt_engine;
 RTPP_API int rtpp_fmt_create(rtpp_ctx *ctx, int n_instances, int node_capacity, int cell_log2, int domain_w, int domain_h,
@@ -224,7 +225,7 @@ RTPP_API int rtpp_fmt_set_map(rtpp_fmt_engine *e, int slot, int plane, const uin
 RTPP_API int rtpp_fmt_start(rtpp_fmt_engine *e, const int32_t *map_slot, const int32_t *n_nodes, const float *nodes_xy,
                             const float *goal_xy);
 RTPP_API int rtpp_fmt_set_inputs(rtpp_fmt_engine *e, const float *agent_xy, const float *goal_xy);
-RTPP_API int rtpp_fmt_tick(rtpp_fmt_engine *e, int do_update_tree, int iters, int with_rewire, int do_get_path);
+RTPP_API int rtpp_fmt_tick(rtpp_fmt_engine *e, int do_update_tree, int iters, int phase_mask, int do_get_path);
 /* 16 int64 per instance: n_nodes, root, z, |V_unv|, |V_open|, |V_opennew|, |V_toopen|, |X_near|, |N_b|,
  * |Qo|, |Qr|, ExpandFMT calls, status, path_len, path_ok, 0 */
 RTPP_API int rtpp_fmt_read_stats(rtpp_fmt_engine *e, long long *out16);

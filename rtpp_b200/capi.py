@@ -356,7 +356,7 @@ class FmtEngine:
         self.ctx._ck(self.L.rtpp_fmt_set_inputs(self.h, _p(a), _p(g)))
 
     def tick(self, update_tree=True, iters=500, with_rewire=True, get_path=False):
-        self.ctx._ck(self.L.rtpp_fmt_tick(self.h, int(update_tree), int(iters), int(with_rewire), int(get_path)))
+        self.ctx._ck(self.L.rtpp_fmt_tick(self.h, int(update_tree), int(iters), 7 if with_rewire is True else (1 if with_rewire is False else int(with_rewire)), int(get_path)))
 
     def stats(self):
         out = np.zeros((self.n, 16), np.int64)
@@ -498,3 +498,143 @@ def host_raster_circle(img, cx, cy, r, v=127):
 def host_raster_fillpoly(img, pts, v=127):
     pts = _c(pts, np.int32).reshape(-1, 2)
     planners_lib().pl_raster_fillpoly(_p(img), img.shape[0], img.shape[1], _p(pts), len(pts), int(v))
+
+
+class PlannerRTFMT:
+    """The C++ RTFMTplanner drop-in driven from Python (same call sequence as the reference class)."""
+
+    def __init__(self, obstacle_plane, device=0):
+        self.L = planners_lib()
+        self.L.pl_rtfmt_create.restype = C.c_void_p
+        self.L.pl_rtfmt_rand_pos.restype = C.c_longlong
+        S = _c(obstacle_plane, np.uint8)
+        h = self.L.pl_rtfmt_create(_p(S), S.shape[0], S.shape[1], device)
+        if not h:
+            raise RtppError("RTFMTplanner could not be created (no CUDA device; there is no CPU fallback)")
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if self.h:
+            self.L.pl_rtfmt_destroy(self.h)
+            self.h = None
+
+    def set_rand(self, r):
+        self._rand = _c(r, np.int32)
+        self.L.pl_rtfmt_set_rand(self.h, _p(self._rand), C.c_longlong(len(self._rand)))
+
+    def rand_pos(self):
+        return int(self.L.pl_rtfmt_rand_pos(self.h))
+
+    def set_agent(self, x, y):
+        self.L.pl_rtfmt_set_agent(self.h, C.c_float(x), C.c_float(y))
+
+    def set_goal(self, x, y):
+        self.L.pl_rtfmt_set_goal(self.h, C.c_float(x), C.c_float(y))
+
+    def set_dobs(self, plane):
+        plane = None if plane is None else _c(plane, np.uint8)
+        self.L.pl_rtfmt_set_dobs(self.h, _p(plane))
+
+    def start(self, sample_n=2000):
+        self.L.pl_rtfmt_start(self.h, int(sample_n))
+
+    def update_tree(self):
+        self.L.pl_rtfmt_update_tree(self.h)
+
+    def expand(self, iters, with_rewire=True):
+        self.L.pl_rtfmt_expand(self.h, int(iters), int(with_rewire))
+
+    def num_nodes(self):
+        return self.L.pl_rtfmt_num_nodes(self.h)
+
+    def dump(self):
+        n = self.num_nodes()
+        xy, par = np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+        cost, col, st = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self.L.pl_rtfmt_dump(self.h, _p(xy), _p(par), _p(cost), _p(col), _p(st))
+        return xy, par, cost, col, st
+
+    def z(self):
+        xy = np.zeros(2, np.float32)
+        self.L.pl_rtfmt_z(self.h, _p(xy))
+        return xy
+
+    def get_path(self, cap=2048):
+        xy = np.zeros((cap, 2), np.float32)
+        n = self.L.pl_rtfmt_get_path(self.h, _p(xy), cap)
+        return xy[: min(n, cap)]
+
+    def set_sizes(self):
+        out = np.zeros(6, np.int32)
+        self.L.pl_rtfmt_set_sizes(self.h, _p(out))
+        return dict(zip(["unv", "open", "opennew", "closed", "toopen", "node_map"], out.tolist()))
+
+
+class PlannerAMRRT:
+    """The C++ AMRRTplanner drop-in driven from Python."""
+
+    def __init__(self, obstacle_plane, device=0):
+        self.L = planners_lib()
+        self.L.pl_amrrt_create.restype = C.c_void_p
+        self.L.pl_amrrt_rand_pos.restype = C.c_longlong
+        self.L.pl_amrrt_diffusivity.restype = C.c_float
+        S = _c(obstacle_plane, np.uint8)
+        h = self.L.pl_amrrt_create(_p(S), S.shape[0], S.shape[1], device)
+        if not h:
+            raise RtppError("AMRRTplanner could not be created (no CUDA device; there is no CPU fallback)")
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if self.h:
+            self.L.pl_amrrt_destroy(self.h)
+            self.h = None
+
+    def set_clock(self, dt_ns):
+        self.L.pl_amrrt_set_clock(self.h, C.c_longlong(dt_ns))
+
+    def set_rand(self, r):
+        self._rand = _c(r, np.int32)
+        self.L.pl_amrrt_set_rand(self.h, _p(self._rand), C.c_longlong(len(self._rand)))
+
+    def rand_pos(self):
+        return int(self.L.pl_amrrt_rand_pos(self.h))
+
+    def set_agent(self, x, y):
+        self.L.pl_amrrt_set_agent(self.h, C.c_float(x), C.c_float(y))
+
+    def set_goal(self, x, y):
+        self.L.pl_amrrt_set_goal(self.h, C.c_float(x), C.c_float(y))
+
+    def set_dobs(self, plane):
+        plane = None if plane is None else _c(plane, np.uint8)
+        self.L.pl_amrrt_set_dobs(self.h, _p(plane))
+
+    def set_diffusion(self, cells_ij, matrix, ratio):
+        cells = _c(cells_ij, np.int32).reshape(-1, 2)
+        m = _c(matrix, np.float32).reshape(len(cells), -1)
+        self.L.pl_amrrt_set_diffusion(self.h, _p(cells), len(cells), _p(m), m.shape[1], C.c_float(ratio))
+
+    def diffusivity(self, a, b):
+        return float(self.L.pl_amrrt_diffusivity(self.h, C.c_float(a[0]), C.c_float(a[1]), C.c_float(b[0]), C.c_float(b[1])))
+
+    def set_outpath(self, nonempty):
+        self.L.pl_amrrt_set_outpath(self.h, int(bool(nonempty)))
+
+    def main_task(self):
+        self.L.pl_amrrt_main_task(self.h)
+
+    def num_nodes(self):
+        return self.L.pl_amrrt_num_nodes(self.h)
+
+    def dump(self):
+        n = self.num_nodes()
+        xy, par = np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+        cost, col = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self.L.pl_amrrt_dump(self.h, _p(xy), _p(par), _p(cost), _p(col))
+        return xy, par, cost, col
+
+    def get_path(self, cap=2048):
+        xy = np.zeros((cap, 2), np.float32)
+        col, cost = C.c_int(), C.c_float()
+        n = self.L.pl_amrrt_get_path(self.h, _p(xy), cap, C.byref(col), C.byref(cost))
+        return xy[: min(n, cap)], bool(col.value), cost.value

@@ -491,7 +491,7 @@ __device__ void fmt_get_path(const FmtView &ev, FI &in, const MarchThresholds &m
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) fmt_tick_kernel(FmtView ev, MarchThresholds mt, int do_update, int iters, int with_rewire,
+__global__ void __launch_bounds__(128) fmt_tick_kernel(FmtView ev, MarchThresholds mt, int do_update, int iters, int phases,
                                                       int do_path) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     FI in;
@@ -499,11 +499,9 @@ __global__ void __launch_bounds__(128) fmt_tick_kernel(FmtView ev, MarchThreshol
     if (in.s.n > 0) {
         if (do_update) fmt_update_tree(ev, in, mt);
         for (int i = 0; i < iters && !in.s.status; i++) { // RTFMT.cpp:714-719
-            expand_fmt(in, mt);
-            if (with_rewire) {
-                rewire_from_obstacles(ev, in, mt);
-                rewire_from_root(in, mt);
-            }
+            if (phases & 1) expand_fmt(in, mt);
+            if (phases & 2) rewire_from_obstacles(ev, in, mt);
+            if (phases & 4) rewire_from_root(in, mt);
         }
         if (do_path) fmt_get_path(ev, in, mt);
     }
@@ -762,13 +760,14 @@ int rtpp_fmt_set_inputs(rtpp_fmt_engine *e, const float *agent_xy, const float *
     return RTPP_OK;
 }
 
-// MainTask minus DrawDObsmap (RTFMT.cpp:704-728): optional UpdateTree, `iters` rounds of
-// ExpandFMT (+ RewireFromObstacles + RewireFromRoot when with_rewire), optional GetPath.
-int rtpp_fmt_tick(rtpp_fmt_engine *e, int do_update_tree, int iters, int with_rewire, int do_get_path) {
-    if (!e || iters < 0) return RTPP_ERR_INVALID;
+// MainTask minus DrawDObsmap (RTFMT.cpp:704-728): optional UpdateTree, `iters` rounds of the phases
+// selected by phase_mask (1 ExpandFMT, 2 RewireFromObstacles, 4 RewireFromRoot; MainTask = 7),
+// optional GetPath.
+int rtpp_fmt_tick(rtpp_fmt_engine *e, int do_update_tree, int iters, int phase_mask, int do_get_path) {
+    if (!e || iters < 0 || phase_mask < 0 || phase_mask > 7) return RTPP_ERR_INVALID;
     rtpp_ctx *ctx = e->ctx;
     const int wpb = e->v.n_inst >= 4 * ctx->sm_count ? 4 : 1;
-    fmt_tick_kernel<<<(e->v.n_inst + wpb - 1) / wpb, 32 * wpb, 0, ctx->stream>>>(e->v, e->mt, do_update_tree, iters, with_rewire, do_get_path);
+    fmt_tick_kernel<<<(e->v.n_inst + wpb - 1) / wpb, 32 * wpb, 0, ctx->stream>>>(e->v, e->mt, do_update_tree, iters, phase_mask, do_get_path);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }

@@ -15,55 +15,7 @@
 // No CPU fallback: construction fails loudly (ok() == false, message on stderr) without a CUDA device.
 #ifndef RTPP_B200_RTRRT_H
 #define RTPP_B200_RTRRT_H
-#include <cmath>
-#include <cstdint>
-#include <cstdio>
-#include <list>
-#include <map>
-#include <queue>
-#include <set>
-#include <vector>
-
-#include "../../include/rtpp_gpu.h"
-#include "raster.hpp"
-
-struct RTpoint {
-    float x;
-    float y;
-    bool operator!=(const RTpoint &o) const { return x != o.x || y != o.y; }
-    bool operator<(const RTpoint &o) const { return x != o.x ? x < o.x : y < o.y; }
-    RTpoint operator+(const RTpoint &o) const { return {x + o.x, y + o.y}; }
-    float operator%(const RTpoint &o) const { // Euclidean distance, binary32, unfused
-        float dx = x - o.x, dy = y - o.y;
-        float xx = dx * dx, yy = dy * dy;
-        return sqrtf(xx + yy);
-    }
-};
-
-struct RTrrt_Cost {
-    bool collision;
-    float cost;
-    RTrrt_Cost operator+(const RTrrt_Cost &o) const { return {collision || o.collision, cost + o.cost}; }
-    bool operator==(const RTrrt_Cost &o) const { return collision == o.collision && cost == o.cost; }
-    bool operator<(const RTrrt_Cost &o) const { return collision == o.collision ? cost < o.cost : collision < o.collision; }
-    bool operator>(const RTrrt_Cost &o) const { return o < *this; }
-    bool operator<=(const RTrrt_Cost &o) const { return !(o < *this); }
-    bool operator>=(const RTrrt_Cost &o) const { return !(*this < o); }
-};
-
-typedef struct {
-    int DObsType; // -1 off, 0 circles at the outline points, 1 polygon
-    float x, y, angle, radius, sampleRadius;
-    std::vector<RTpoint> OutLine;
-    std::vector<RTpoint> CheckPoints;
-    std::set<int> ObsIslands;
-} RTrrt_DynamicObstacle;
-
-struct RTrrt_NodeAttribute {
-    RTrrt_Cost cost;
-    RTpoint par;
-    std::set<RTpoint> subs;
-};
+#include "rtpp_types.h"
 
 class RTRRTplanner {
   private:

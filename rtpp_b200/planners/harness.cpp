@@ -93,3 +93,127 @@ PL_EXPORT void pl_raster_fillpoly(uint8_t *img, int rows, int cols, const int *x
     rtpp::fill_polygon(p, pts, (uint8_t)v);
     memcpy(img, p.data.data(), p.data.size());
 }
+
+// ------------------------------------------------------------------------------------- RT-FMT
+#include "RTFMT.h"
+PL_EXPORT void *pl_rtfmt_create(const uint8_t *obs, int rows, int cols, int device) {
+    RTFMTplanner *p = new RTFMTplanner(device);
+    if (!p->ok()) {
+        delete p;
+        return nullptr;
+    }
+    std::vector<uint8_t> gray((size_t)rows * cols);
+    for (size_t i = 0; i < gray.size(); i++) gray[i] = obs[i] ? 0 : 255;
+    p->InitializeInvironment(gray.data(), rows, cols, 128);
+    return p;
+}
+PL_EXPORT void pl_rtfmt_destroy(void *h) { delete (RTFMTplanner *)h; }
+PL_EXPORT void pl_rtfmt_set_rand(void *h, const int32_t *r, long long n) { ((RTFMTplanner *)h)->SetRandStream(r, n); }
+PL_EXPORT long long pl_rtfmt_rand_pos(void *h) { return ((RTFMTplanner *)h)->RandPos(); }
+PL_EXPORT void pl_rtfmt_set_agent(void *h, float x, float y) {
+    RTpoint p{x, y};
+    ((RTFMTplanner *)h)->SetAgent(p);
+}
+PL_EXPORT void pl_rtfmt_set_goal(void *h, float x, float y) {
+    RTpoint p{x, y};
+    ((RTFMTplanner *)h)->SetGoal(p);
+}
+PL_EXPORT void pl_rtfmt_set_dobs(void *h, const uint8_t *plane) { ((RTFMTplanner *)h)->SetDObsmap(plane); }
+PL_EXPORT void pl_rtfmt_start(void *h, int sample_n) {
+    ((RTFMTplanner *)h)->SetSampleN(sample_n);
+    ((RTFMTplanner *)h)->Start();
+}
+PL_EXPORT void pl_rtfmt_update_tree(void *h) { ((RTFMTplanner *)h)->UpdateTree(); }
+PL_EXPORT void pl_rtfmt_expand(void *h, int iters, int with_rewire) {
+    RTFMTplanner *p = (RTFMTplanner *)h;
+    if (iters <= 3) { // the reference's own call sequence, one method at a time
+        for (int i = 0; i < iters; i++) {
+            p->ExpandFMT();
+            if (with_rewire) p->RewireFromObstacles(), p->RewireFromRoot();
+        }
+    } else
+        p->RunRounds(iters, with_rewire != 0);
+}
+PL_EXPORT int pl_rtfmt_num_nodes(void *h) { return ((RTFMTplanner *)h)->NodeCount(); }
+PL_EXPORT int pl_rtfmt_dump(void *h, float *xy, int32_t *parent, float *cost, uint8_t *col, uint8_t *state) {
+    RTFMTplanner *p = (RTFMTplanner *)h;
+    memcpy(xy, p->NodesXY().data(), p->NodesXY().size() * 4);
+    return p->ReadTree(parent, cost, col, state);
+}
+PL_EXPORT void pl_rtfmt_z(void *h, float *xy) {
+    RTpoint z = ((RTFMTplanner *)h)->Z();
+    xy[0] = z.x, xy[1] = z.y;
+}
+PL_EXPORT int pl_rtfmt_get_path(void *h, float *out_xy, int cap) {
+    std::list<RTpoint> path;
+    ((RTFMTplanner *)h)->GetPath(path);
+    int n = 0;
+    for (const RTpoint &q : path) {
+        if (n < cap) out_xy[2 * n] = q.x, out_xy[2 * n + 1] = q.y;
+        n++;
+    }
+    return n;
+}
+PL_EXPORT int pl_rtfmt_set_sizes(void *h, int *sizes6) {
+    RTFMTplanner *p = (RTFMTplanner *)h;
+    p->SyncSets();
+    sizes6[0] = (int)p->V_unv.size(), sizes6[1] = (int)p->V_open.size(), sizes6[2] = (int)p->V_opennew.size();
+    sizes6[3] = (int)p->V_closed.size(), sizes6[4] = (int)p->V_toopen.size(), sizes6[5] = (int)p->Node_Map.size();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- AM-RRT*
+#include "AMRRT.h"
+PL_EXPORT void *pl_amrrt_create(const uint8_t *obs, int rows, int cols, int device) {
+    AMRRTplanner *p = new AMRRTplanner(device);
+    if (!p->ok()) {
+        delete p;
+        return nullptr;
+    }
+    std::vector<uint8_t> gray((size_t)rows * cols);
+    for (size_t i = 0; i < gray.size(); i++) gray[i] = obs[i] ? 0 : 255;
+    p->InitializeInvironment(gray.data(), rows, cols, 128);
+    return p;
+}
+PL_EXPORT void pl_amrrt_destroy(void *h) { delete (AMRRTplanner *)h; }
+PL_EXPORT void pl_amrrt_set_clock(void *h, long long dt) { ((AMRRTplanner *)h)->SetVirtualClock(dt); }
+PL_EXPORT void pl_amrrt_set_rand(void *h, const int32_t *r, long long n) { ((AMRRTplanner *)h)->SetRandStream(r, n); }
+PL_EXPORT long long pl_amrrt_rand_pos(void *h) { return ((AMRRTplanner *)h)->RandPos(); }
+PL_EXPORT void pl_amrrt_set_agent(void *h, float x, float y) {
+    RTpoint p{x, y};
+    ((AMRRTplanner *)h)->SetAgent(p);
+}
+PL_EXPORT void pl_amrrt_set_goal(void *h, float x, float y) {
+    RTpoint p{x, y};
+    ((AMRRTplanner *)h)->SetGoal(p);
+}
+PL_EXPORT void pl_amrrt_set_dobs(void *h, const uint8_t *plane) { ((AMRRTplanner *)h)->SetDObsmap(plane); }
+PL_EXPORT void pl_amrrt_set_diffusion(void *h, const int32_t *cells, int n, const float *m, int dim, float ratio) {
+    ((AMRRTplanner *)h)->InitializeDiffusion(cells, n, m, dim, ratio);
+}
+PL_EXPORT float pl_amrrt_diffusivity(void *h, float ax, float ay, float bx, float by) {
+    RTpoint a{ax, ay}, b{bx, by};
+    return ((AMRRTplanner *)h)->DiffusivityMetric(a, b);
+}
+PL_EXPORT void pl_amrrt_set_outpath(void *h, int nonempty) {
+    AMRRTplanner *p = (AMRRTplanner *)h;
+    p->OutPath.clear();
+    if (nonempty) p->OutPath.push_back({0, 0});
+}
+PL_EXPORT void pl_amrrt_main_task(void *h) { ((AMRRTplanner *)h)->MainTask(); }
+PL_EXPORT int pl_amrrt_num_nodes(void *h) { return ((AMRRTplanner *)h)->NodeCount(); }
+PL_EXPORT int pl_amrrt_dump(void *h, float *xy, int32_t *parent, float *cost, uint8_t *col) {
+    AMRRTplanner *p = (AMRRTplanner *)h;
+    return p->ReadTree(xy, parent, cost, col, p->NodeCount());
+}
+PL_EXPORT int pl_amrrt_get_path(void *h, float *out_xy, int cap, int *collision, float *cost) {
+    std::list<RTpoint> path;
+    RTrrt_Cost c = ((AMRRTplanner *)h)->GetPath(path);
+    *collision = c.collision, *cost = c.cost;
+    int n = 0;
+    for (const RTpoint &q : path) {
+        if (n < cap) out_xy[2 * n] = q.x, out_xy[2 * n + 1] = q.y;
+        n++;
+    }
+    return n;
+}

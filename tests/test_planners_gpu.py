@@ -80,3 +80,76 @@ def test_cpp_planner_main_task_with_obstacles(oracle):
     got_v = np.array([pl.crash(r[:2], r[2:]) for r in e], np.uint8)
     assert np.array_equal(got_v, want_v)
     pl.close()
+
+
+@pytest.mark.parametrize("case", golden_cases()["rtfmt"], ids=lambda c: c["name"])
+def test_cpp_rtfmt_planner_reproduces_reference_golden(oracle, case):
+    """RTFMTplanner (C++ drop-in): SetAgent/SetGoal/Start with the injected rand stream, then the
+    reference's call sequence UpdateTree + 500 x (ExpandFMT, RewireFromObstacles, RewireFromRoot)."""
+    from rtpp_b200 import capi
+
+    g = np.load(os.path.join(GOLD, f"rtfmt_{case['name']}.npz"))
+    S = oracle.load_map(case["map"])
+    pl = capi.PlannerRTFMT(S)
+    pl.set_rand(oracle.rand31(case["seed"], case["n_rand"]))
+    pl.set_agent(*case["agent"])
+    pl.set_goal(*case["goal"])
+    pl.start(case["samples"])
+    assert pl.rand_pos() == int(g["rand_used"])
+    rng = np.random.default_rng(case["seed"])
+    for rnd in range(case["rounds"]):
+        if rnd in case["dobs_rounds"]:
+            pl.set_dobs(dyn_plane(S.shape, rng, n_blobs=5))
+        pl.update_tree()
+        if rnd == 1:
+            pl.expand(2, True)      # method-by-method calls, as a caller of the reference class would
+            pl.expand(498, True)
+        else:
+            pl.expand(500, True)
+        xy, par, c, cl, st = pl.dump()
+        k = f"r{rnd}_"
+        assert np.array_equal(xy, g["xy"]) and np.array_equal(par, g[k + "par"])
+        assert np.array_equal(c.view(np.uint32), g[k + "cost"].view(np.uint32))
+        assert np.array_equal(cl, g[k + "col"]) and np.array_equal(st, g[k + "state"])
+        assert np.array_equal(pl.z(), g[k + "z"])
+        p = pl.get_path()
+        assert np.array_equal(p, g[k + "path"])
+        if rnd in case["move_rounds"] and len(p) > 2:
+            pl.set_agent(float(p[1][0]), float(p[1][1]))
+    sizes = pl.set_sizes()
+    assert sizes["node_map"] == len(xy) and sizes["unv"] + sizes["open"] + sizes["opennew"] + sizes["closed"] == len(xy)
+    pl.close()
+
+
+@pytest.mark.parametrize("case", golden_cases()["amrrt"], ids=lambda c: c["name"])
+def test_cpp_amrrt_planner_reproduces_reference_golden(oracle, case):
+    """AMRRTplanner (C++ drop-in): MainTask + GetPath, 25 ticks, against the reference's golden."""
+    from rtpp_b200 import capi
+
+    g = np.load(os.path.join(GOLD, f"amrrt_{case['name']}.npz"))
+    S = oracle.load_map(case["map"])
+    pl = capi.PlannerAMRRT(S)
+    cells, mat, ratio = case["diffusion"](S.shape[1])
+    pl.set_diffusion(cells, mat, ratio)
+    pl.set_rand(oracle.rand31(case["seed"], case["n_rand"]))
+    pl.set_clock(case["dt"])
+    pl.set_agent(*case["agent"])
+    pl.set_goal(*case["goal"])
+    o = oracle.OrcAMRRT(S)
+    o.set_diffusion(cells, mat, ratio)
+    assert pl.diffusivity((100, 200), (700, 900)) == o.diffusivity((100, 200), (700, 900))
+    rng = np.random.default_rng(case["seed"])
+    pl.set_dobs(None)
+    for tick in range(case["ticks"]):
+        if tick in case["dobs_ticks"]:
+            pl.set_dobs(dyn_plane(S.shape, rng, n_blobs=4))
+        pl.main_task()
+        xy, par, c, cl = pl.dump()
+        path, pcol, pcost = pl.get_path()
+        k = f"t{tick}_"
+        assert pl.rand_pos() == int(g[k + "rand_pos"]), f"tick {tick}"
+        assert np.array_equal(xy, g[k + "xy"]) and np.array_equal(par, g[k + "par"])
+        assert np.array_equal(c.view(np.uint32), g[k + "cost"].view(np.uint32)) and np.array_equal(cl, g[k + "col"])
+        assert np.array_equal(path, g[k + "path"]) and pcol == bool(g[k + "path_col"])
+        assert np.float32(pcost).view(np.uint32) == g[k + "path_cost"].view(np.uint32)
+    pl.close()
