@@ -83,6 +83,14 @@ RTPP_API int rtpp_map_clear_plane(rtpp_ctx *ctx, int plane);
 /* Unpack the plane selected by plane_mask (1 = S, 2 = D, 3 = S|D) back to H*W bytes (0/1). */
 RTPP_API int rtpp_map_get_plane(rtpp_ctx *ctx, int plane_mask, uint8_t *out_rowmajor);
 RTPP_API int rtpp_map_shape(rtpp_ctx *ctx, int *W, int *H);
+/* D1 DrawDObsmap (RTRRT.cpp:138-169, RTFMT.cpp:178-209, AMRRT.cpp:202-233, CDRT.cpp:605-636) on the
+ * device: clears the dynamic plane, draws n_circles filled circles — (cx, cy, r) int triples, one per
+ * outline point of a type-0 obstacle, = cv::circle(.., FILLED) — and n_polys filled polygons — poly_xy
+ * concatenated (x, y) int pairs, poly_sizes[p] vertices each (<= 64), = cv::fillPoly — then refreshes
+ * the merged S|D plane.  The outline rotation (sinf/cosf, truncation: RTRRT.cpp:145-152) is done by the
+ * caller on the host, so a tick ships a few hundred bytes instead of an H*W byte plane. */
+RTPP_API int rtpp_map_draw_dynamic(rtpp_ctx *ctx, const int32_t *circles, int n_circles, const int32_t *poly_xy,
+                                   const int32_t *poly_sizes, int n_polys);
 
 /* ---------------------------------------------------------------- edge checks (K1) ----------- */
 /* E1 RTRRTplanner::CrashDetection RTRRT.cpp:202-222, RTFMTplanner::CrashDetection RTFMT.cpp:242-262
@@ -106,6 +114,14 @@ RTPP_API int rtpp_edges_first_hit(rtpp_ctx *ctx, const float *xyxy, size_t n, ui
                                   float *pstart_xy);
 RTPP_API int rtpp_edges_first_hit_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, uint32_t *d_blocked_bits,
                                       float *d_pstart_xy);
+/* One replanning tick's collision pass over the RESIDENT tree (nodes + parents + k-NN table on the
+ * device): edge e < n-1 is the tree edge (parent(e+1) -> e+1) that UpdateTree re-costs (RTRRT.cpp:132,
+ * AMRRT.cpp:196), edge n-1 + i*k + j is the rewire edge (node i -> knn[i][j]) (RTRRT.cpp:310,339,
+ * AMRRT.cpp:500).  What crosses the boundary per tick is what changes per tick: the new dynamic plane
+ * in (H*W bytes as DrawDObsmap produces it; NULL = unchanged), the verdict words out. */
+RTPP_API int rtpp_tick_edges_check(rtpp_ctx *ctx, const uint8_t *dynamic_plane, int divisor, int plane_mask,
+                                   uint32_t *blocked_bits, size_t *n_edges);
+RTPP_API int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_blocked_bits, size_t *n_edges);
 /* C2 RTpoint::operator% RTRRT.h:47-52 on n point pairs (exposed for parity tests). */
 RTPP_API int rtpp_dist(rtpp_ctx *ctx, const float *xyxy, size_t n, float *out);
 
@@ -136,6 +152,10 @@ RTPP_API int rtpp_knn_dev(rtpp_ctx *ctx, const double *d_qxy, size_t nq, int k, 
 /* All-k-NN table of the node set itself, row i = neighbours of node i (includes i at d2 = 0, as
  * the reference's queries at tree nodes do: RTRRT.cpp:304, RTFMT.cpp:440). */
 RTPP_API int rtpp_knn_nodes_dev(rtpp_ctx *ctx, int k, int32_t *d_idx, double *d_d2);
+
+/* Resident all-k-NN table inside the ctx (rows of k ids per node), for the tick-level calls. */
+RTPP_API int rtpp_knn_table_build(rtpp_ctx *ctx, int k);
+RTPP_API int rtpp_knn_table_dev(rtpp_ctx *ctx, const int32_t **d_idx, int *k);
 
 /* ---------------------------------------------------------------- tree costs (K4/K5) --------- */
 /* Per-node cost and parent link: RTrrt_NodeAttribute {cost, par} (RTRRT.h:108-113) with

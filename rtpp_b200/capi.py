@@ -130,6 +130,15 @@ class Ctx:
         self.call("map_get_plane", int(mask), _p(out))
         return out
 
+    def map_draw_dynamic(self, circles=(), polys=()):
+        """circles: iterable of (cx, cy, r); polys: iterable of (n_i, 2) integer vertex arrays."""
+        c = _c(np.asarray(list(circles), np.int32).reshape(-1, 3), np.int32)
+        polys = [np.asarray(p, np.int32).reshape(-1, 2) for p in polys]
+        pxy = _c(np.concatenate(polys) if polys else np.zeros((0, 2), np.int32), np.int32)
+        sizes = _c(np.array([len(p) for p in polys], np.int32), np.int32)
+        self.call("map_draw_dynamic", _p(c) if len(c) else None, len(c), _p(pxy) if len(polys) else None,
+                  _p(sizes) if len(polys) else None, len(polys))
+
     # ---- edges
     @staticmethod
     def unpack_bits(bits, n):
@@ -199,6 +208,18 @@ class Ctx:
 
     def knn_nodes_dev(self, k, d_idx, d_d2=0):
         self.call("knn_nodes_dev", int(k), C.c_void_p(d_idx), C.c_void_p(d_d2))
+
+    def knn_table_build(self, k):
+        self.call("knn_table_build", int(k))
+
+    def tick_edges_check(self, dynamic_plane, divisor, mask):
+        """One tick through host buffers: dynamic byte plane in (None = unchanged), verdict bits out."""
+        n = self.nodes_count()
+        d = None if dynamic_plane is None else _c(dynamic_plane, np.uint8)
+        ne = C.c_size_t()
+        bits = np.zeros(((n - 1) + n * 32 + 31) // 32, np.uint32)
+        self.call("tick_edges_check", _p(d), int(divisor), int(mask), _p(bits), C.byref(ne))
+        return self.unpack_bits(bits, ne.value)
 
     # ---- tree costs
     def tree_set(self, parent, cost, col):

@@ -16,7 +16,7 @@
 //
 // Roofline: algorithmic bytes per edge = 16 + 4*n_probes + 1/8; the edge list streams
 // from HBM, the bit-plane (0.9-2 MB) is L2/L1 resident.
-#include "common.cuh"
+#include "nodes.cuh"
 
 static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 32 -> warp marches
 
@@ -206,6 +206,42 @@ edge_first_hit_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, 
     }
 }
 
+// Tick-level form of K1: the edges are implied by the resident tree — edge e < n-1 is the tree edge
+// (parent(e+1) -> e+1) of UpdateTree (AMRRT.cpp:185-199), edge n-1 + i*k + j is the rewire edge
+// (node i -> knn[i][j]) of RewireRoot (AMRRT.cpp:496-500) — so a tick moves no edge list at all:
+// 4 index bytes + two 8-byte coordinate gathers (L2-resident node table) per edge.
+__global__ void __launch_bounds__(256)
+edge_check_resident_kernel(PlaneView pl, const float2 *__restrict__ xy, const cpword *__restrict__ cp, const int *__restrict__ knn,
+                           int n, int k, MarchThresholds mt, uint32_t *__restrict__ out_bits) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const size_t n_edges = (size_t)(n - 1) + (size_t)n * k;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t nwords = (n_edges + 31) >> 5;
+    for (size_t w = warp0; w < nwords; w += nwarps) {
+        const size_t i = (w << 5) + lane;
+        bool blocked = false;
+        if (i < n_edges) {
+            int a, b;
+            if (i < (size_t)(n - 1)) {
+                b = (int)i + 1;
+                a = cp_parent(cp[b]);
+            } else {
+                const size_t r = i - (size_t)(n - 1);
+                a = (int)(r / k);
+                b = knn[r];
+            }
+            if (a >= 0 && b >= 0) {
+                const float2 pa = xy[a], pb = xy[b];
+                blocked = rt_edge_blocked(pl, pa.x, pa.y, pb.x, pb.y, mt);
+            }
+        }
+        const unsigned bits = __ballot_sync(full, blocked);
+        if (lane == 0) out_bits[w] = bits;
+    }
+}
+
 __global__ void __launch_bounds__(256) dist_kernel(const float4 *__restrict__ e, size_t n, float *__restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float4 v = e[i];
@@ -261,6 +297,50 @@ int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divis
     rtpp_march_thresholds(divisor, &mt);
     edge_check_f32_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits);
     RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_bits, size_t *n_edges) {
+    if (!ctx || !d_bits) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s || !s->knn_table) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_knn_table_build has not been called");
+    if (s->knn_n != s->n) RTPP_FAIL(ctx, RTPP_ERR_STATE, "nodes were appended after rtpp_knn_table_build");
+    if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    PlaneView pv;
+    int rc = rtpp_select_plane(ctx, plane_mask, &pv);
+    if (rc) return rc;
+    const size_t ne = (size_t)(s->n - 1) + (size_t)s->n * s->knn_k;
+    if (n_edges) *n_edges = ne;
+    MarchThresholds mt;
+    rtpp_march_thresholds(divisor, &mt);
+    edge_check_resident_kernel<<<edge_grid(ctx, ne, 256), 256, 0, ctx->stream>>>(pv, s->xy, s->cp, s->knn_table, s->n, s->knn_k, mt, d_bits);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+// One tick through host buffers: new dynamic plane in (NULL = unchanged), verdict words out.
+int rtpp_tick_edges_check(rtpp_ctx *ctx, const uint8_t *dynamic_plane, int divisor, int plane_mask, uint32_t *blocked_bits,
+                          size_t *n_edges) {
+    if (!ctx || !blocked_bits) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s || !s->knn_table) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_knn_table_build has not been called");
+    int rc;
+    if (dynamic_plane) {
+        void *d = nullptr;
+        rc = rtpp_scratch(ctx, 0, (size_t)ctx->W * ctx->H, &d);
+        if (rc) return rc;
+        RTPP_CK(ctx, cudaMemcpyAsync(d, dynamic_plane, (size_t)ctx->W * ctx->H, cudaMemcpyHostToDevice, ctx->stream));
+        rc = rtpp_map_set_plane_dev(ctx, RTPP_PLANE_DYNAMIC, (const uint8_t *)d, ctx->W, ctx->H);
+        if (rc) return rc;
+    }
+    const size_t ne = (size_t)(s->n - 1) + (size_t)s->n * s->knn_k, nwords = (ne + 31) / 32;
+    void *d_b = nullptr;
+    rc = rtpp_scratch(ctx, 1, nwords * 4, &d_b);
+    if (rc) return rc;
+    rc = rtpp_tick_edges_check_dev(ctx, divisor, plane_mask, (uint32_t *)d_b, n_edges);
+    if (rc) return rc;
+    RTPP_CK(ctx, cudaMemcpyAsync(blocked_bits, d_b, nwords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
     return RTPP_OK;
 }
 

@@ -86,7 +86,7 @@ void rtpp_nodes_destroy(rtpp_ctx *ctx) {
     NodeStore *s = ctx->nodes;
     if (!s) return;
     cudaFree(s->xy), cudaFree(s->sxy), cudaFree(s->sid), cudaFree(s->cell_of), cudaFree(s->cell_start), cudaFree(s->cursor);
-    cudaFree(s->scan_totals), cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
+    cudaFree(s->knn_table), cudaFree(s->scan_totals), cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
     delete s;
     ctx->nodes = nullptr;
 }
@@ -131,6 +131,8 @@ int rtpp_grid_view(rtpp_ctx *ctx, GridView *g) {
 }
 
 extern "C" {
+
+int rtpp_knn_nodes_dev(rtpp_ctx *ctx, int k, int32_t *d_idx, double *d_d2);
 
 int rtpp_nodes_reset(rtpp_ctx *ctx, int cell_log2, size_t capacity, int domain_w, int domain_h) {
     if (!ctx) return RTPP_ERR_INVALID;
@@ -237,6 +239,34 @@ int rtpp_knn(rtpp_ctx *ctx, const double *qxy, size_t nq, int k, int32_t *idx, d
     if (d2) RTPP_CK(ctx, cudaMemcpyAsync(d2, d_d, nq * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (count) RTPP_CK(ctx, cudaMemcpyAsync(count, d_c, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+// resident all-k-NN table of the node set, kept inside the ctx for the tick-level calls
+int rtpp_knn_table_build(rtpp_ctx *ctx, int k) {
+    if (!ctx) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
+    if (k < 1 || k > 32) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "k must be in 1..32");
+    if (s->knn_table && (s->knn_k != k || s->knn_n < s->n)) {
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(s->knn_table);
+        s->knn_table = nullptr;
+    }
+    if (!s->knn_table) {
+        RTPP_CK(ctx, cudaMalloc(&s->knn_table, (size_t)s->capacity * k * sizeof(int)));
+        s->knn_k = k;
+    }
+    s->knn_n = s->n;
+    return rtpp_knn_nodes_dev(ctx, k, s->knn_table, nullptr);
+}
+
+int rtpp_knn_table_dev(rtpp_ctx *ctx, const int32_t **d_idx, int *k) {
+    if (!ctx || !d_idx) return RTPP_ERR_INVALID;
+    NodeStore *s = ctx->nodes;
+    if (!s || !s->knn_table) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_knn_table_build has not been called");
+    *d_idx = s->knn_table;
+    if (k) *k = s->knn_k;
     return RTPP_OK;
 }
 

@@ -41,6 +41,8 @@ struct NodeStore {
     int *children = nullptr;    // [capacity]
     int *frontier = nullptr;    // [2 * capacity]
     int *counters = nullptr;    // [8]
+    int *knn_table = nullptr;   // resident all-k-NN table [n * knn_k] (rtpp_knn_table_build)
+    int knn_k = 0, knn_n = 0;
 };
 
 int rtpp_nodes_build_internal(rtpp_ctx *ctx);

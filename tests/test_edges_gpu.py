@@ -92,3 +92,30 @@ def test_edges_other_maps(ctx, oracle, name):
     for divisor in (5, 2):
         got = ctx.edges_check(e, divisor, 3)
         assert np.array_equal(got, oracle.edges_check(S, None, e, divisor, 1, nthreads=8))
+
+
+def test_tick_edges_check_equals_explicit_list(ctx, oracle):
+    """The tick-level call over the resident tree (parents + k-NN table) returns, edge for edge, the
+    verdicts of the explicit end-point list it stands for, and of the oracle."""
+    S = oracle.load_map("MESS6")
+    H, W = S.shape
+    rng = np.random.default_rng(31)
+    D = dyn_plane(S.shape, rng, n_blobs=6)
+    ctx.map_set_plane(1, S)
+    ctx.map_clear_plane(2)
+    n, k = 20_000, 25
+    xy = (rng.random((n, 2), dtype=np.float32) * np.array([W, H], np.float32)).astype(np.float32)
+    ctx.nodes_reset(4, n, W, H)
+    ctx.nodes_append(xy)
+    ctx.knn_table_build(k)
+    idx, _, _ = ctx.knn(xy.astype(np.float64), k)
+    par = rng.integers(0, n, n).astype(np.int32)
+    par[0] = -1
+    ctx.tree_set(par, np.zeros(n, np.float32), np.zeros(n, np.uint8))
+    got = ctx.tick_edges_check(D, 2, 3)  # uploads the dynamic plane, checks (n-1) + n*k edges
+    tree = np.concatenate([xy[par[1:]], xy[1:]], 1)
+    rew = np.concatenate([np.repeat(xy, k, axis=0), xy[idx.reshape(-1)]], 1)
+    e = np.ascontiguousarray(np.concatenate([tree, rew]), np.float32)
+    assert len(got) == len(e)
+    assert np.array_equal(got, ctx.edges_check(e, 2, 3))
+    assert np.array_equal(got, oracle.edges_check(S, D, e, 2, 3, nthreads=8))
