@@ -58,12 +58,13 @@ def c4_map(seed=42):
         r = int(rng.integers(8, 97))
         x, y = (int(v) for v in rng.integers(0, MAP_SIZE, 2))
         disc(S, x, y, r, 255)
-    D = np.zeros_like(S)
-    for _ in range(6):
-        r = int(rng.integers(40, 120))
-        x, y = (int(v) for v in rng.integers(0, MAP_SIZE, 2))
-        disc(D, x, y, r, 127)
-    return S, D
+    # dynamic obstacles as the planners hold them (DObstacles): 4 discs + 2 polygons, integer pixel points
+    circles = [(int(rng.integers(200, MAP_SIZE - 200)), int(rng.integers(200, MAP_SIZE - 200)), int(rng.integers(40, 120))) for _ in range(4)]
+    polys = []
+    for _ in range(2):
+        cx, cy = (int(v) for v in rng.integers(300, MAP_SIZE - 300, 2))
+        polys.append(np.array([(cx - 90, cy - 60), (cx + 90, cy - 60), (cx + 120, cy + 70), (cx, cy + 110), (cx - 120, cy + 70)], np.int32))
+    return S, (circles, polys)
 
 
 def c4_nodes(S, seed, n=N_NODES):
@@ -94,9 +95,10 @@ class Workload:
         torch.cuda.set_stream(self.stream)
         self.ctx = rtpp_b200.Ctx(device)
         self.ctx.set_stream(self.stream.cuda_stream)
-        self.S, self.D = c4_map(42)
+        self.S, self.obstacles = c4_map(42)
         self.ctx.map_set_plane(1, self.S)
-        self.ctx.map_set_plane(2, self.D)
+        self.ctx.map_draw_dynamic(*self.obstacles)          # D1 on the device
+        self.D = self.ctx.map_get_plane(2) * np.uint8(127)   # the byte plane the CPU arm probes
         self.xy = c4_nodes(self.S, 1000 + seed)
         n = len(self.xy)
         self.ctx.nodes_reset(4, n, MAP_SIZE, MAP_SIZE)
@@ -214,13 +216,18 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU CrashDetection over the step's edges (rank 0 only)."""
     if rank != 0:
         return
-    S, D = c4_map(42)
+    S, (circles, polys) = c4_map(42)
+    from oracle import loader as orc
+
+    D = np.zeros_like(S)  # DrawDObsmap with the oracle's OpenCV-pinned rasteriser
+    for cx, cy, r in circles:
+        orc.raster_circle(D, cx, cy, r)
+    for p in polys:
+        orc.raster_fillpoly(D, p)
     xy = c4_nodes(S, 1000)
     threads = os.cpu_count() or 1
     # the same edge population as the GPU arm, rebuilt on the CPU for a bounded sample of nodes:
     # tree edge + 25 rewire edges of the first `m` nodes (neighbours by the oracle's exact k-NN)
-    from oracle import loader as orc
-
     m = 40_000
     idx, _, _ = orc.knn(xy, xy[:m].astype(np.float64), KNN, grid=(MAP_SIZE, MAP_SIZE, 16), nthreads=threads)
     src = np.repeat(xy[:m], KNN, axis=0)
@@ -322,19 +329,23 @@ def main():
     ms_step = ms_total / args.steps
     value = wl.n_edges * world / (ms_step * 1e-3)
 
-    # ---- e2e: one replanning tick through the host-buffer C-ABI call.  What changes per tick crosses
-    # the boundary inside the timed region: the new dynamic-obstacle byte plane (as DrawDObsmap produces
-    # it) goes in from pinned host memory, the verdict words come back; the tree itself (nodes, parents,
-    # k-NN table) is resident, exactly as the planner classes keep it.  Same 26.0 M edges, same verdicts.
+    # ---- e2e: one replanning tick through the host-buffer C-ABI calls.  What changes per tick crosses
+    # the boundary inside the timed region: the obstacle poses go in (DrawDObsmap runs on the device), the
+    # verdict words come back to pinned host memory; the tree itself (nodes, parents, k-NN table) is
+    # resident, exactly as the planner classes keep it.  Same 26.0 M edges, same verdicts as `value`.
     import ctypes as C
 
     e2e_steps = max(3, min(args.steps, 20))
-    h_plane = torch.from_numpy(wl.D.copy()).pin_memory()
     h_bits = torch.empty((wl.n_edges + 31) // 32, dtype=torch.int32, pin_memory=True)
     ne = C.c_size_t()
+    circ = np.ascontiguousarray(np.array(wl.obstacles[0], np.int32))
+    pxy = np.ascontiguousarray(np.concatenate(wl.obstacles[1]).astype(np.int32))
+    psz = np.ascontiguousarray(np.array([len(p) for p in wl.obstacles[1]], np.int32))
 
     def e2e_step():
-        ctx.call("tick_edges_check", C.c_void_p(h_plane.data_ptr()), DIVISOR, 3, C.c_void_p(h_bits.data_ptr()), C.byref(ne))
+        # MainTask's DrawDObsmap (obstacle poses in) + the tick's collision pass (verdict words out)
+        ctx.call("map_draw_dynamic", C.c_void_p(circ.ctypes.data), len(circ), C.c_void_p(pxy.ctypes.data), C.c_void_p(psz.ctypes.data), len(psz))
+        ctx.call("tick_edges_check", None, DIVISOR, 3, C.c_void_p(h_bits.data_ptr()), C.byref(ne))
 
     for _ in range(3):
         e2e_step()
@@ -349,9 +360,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     same = bool(ne.value == wl.n_edges and (h_bits.to(wl.dev) == wl.bits).all().item())
-    e2e = {"value": wl.n_edges * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h_plane.numel()),
+    e2e = {"value": wl.n_edges * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(circ.nbytes + pxy.nbytes + psz.nbytes),
            "d2h_bytes_per_step": int(h_bits.numel() * 4), "steps": e2e_steps, "matches_resident_run": same,
-           "api": "rtpp_tick_edges_check (host buffers, pinned): dynamic plane in, verdict words out, tree resident"}
+           "api": "rtpp_map_draw_dynamic + rtpp_tick_edges_check (host buffers): obstacle poses in, verdict words out (pinned), tree resident"}
     # the same batch as an explicit end-point list from the host (rtpp_edges_check): PCIe-bound by 16 B/edge
     h_edges = torch.empty((wl.n_edges, 4), dtype=torch.float32, pin_memory=True)
     h_edges.copy_(wl.edges)

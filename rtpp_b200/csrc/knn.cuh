@@ -11,7 +11,7 @@
 // The warp walks square rings of cells around the query cell; a row of cells is one contiguous,
 // coalesced range of the cell-sorted point array.  Lane j holds the j-th best (d2,id) so far
 // (sorted across lanes); candidates that beat the current k-th are inserted with one ballot and
-// one shfl_up.  The walk stops when the k-th distance is strictly below the squared gap between
+// one shfl_up (chunks with many winners are merged in with a bitonic sort + merge).  The walk stops when the k-th distance is strictly below the squared gap between
 // the query and every still-open side of the scanned square (computed rounding down), which
 // proves that no unscanned point can enter or tie into the result.  Points appended since the
 // last re-sort (the "tail") are scanned linearly by every query.
@@ -61,8 +61,44 @@ __device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy,
     double kd2 = CUDART_INF; // current k-th entry (broadcast copy)
     int kid = 0x7fffffff;
 
+    // compare-exchange with the lane `stride` away: keep the smaller (keep_min) or larger pair
+    auto cmpx = [&](double &d, int &i, int stride, bool keep_min) {
+        const double od = __shfl_xor_sync(full, d, stride);
+        const int oi = __shfl_xor_sync(full, i, stride);
+        const bool other_less = knn_less(od, oi, d, i);
+        if (other_less == keep_min) d = od, i = oi;
+    };
     auto offer = [&](bool valid, double d2, int id) {
-        unsigned m = __ballot_sync(full, valid && knn_less(d2, id, kd2, kid));
+        const bool acc = valid && knn_less(d2, id, kd2, kid);
+        unsigned m = __ballot_sync(full, acc);
+        const int cnt = __popc(m);
+        if (cnt == 0) return;
+        if (cnt >= 6) {
+            // many candidates beat the k-th (early chunks): sort the chunk across the lanes (bitonic,
+            // 15 compare-exchange stages), keep the 32 smallest of {best list, chunk} and re-sort
+            // them with one bitonic merge (the pointwise minimum of an ascending and a reversed
+            // ascending sequence is bitonic)
+            double cd = acc ? d2 : CUDART_INF;
+            int ci = acc ? id : 0x7fffffff;
+#pragma unroll
+            for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+                for (int stride = size >> 1; stride > 0; stride >>= 1)
+                    cmpx(cd, ci, stride, ((lane & stride) == 0) == ((lane & size) == 0));
+            const double rd = __shfl_sync(full, cd, 31 - lane);
+            const int ri = __shfl_sync(full, ci, 31 - lane);
+            if (knn_less(rd, ri, mine.d2, mine.id)) mine.d2 = rd, mine.id = ri;
+#pragma unroll
+            for (int stride = 16; stride > 0; stride >>= 1) cmpx(mine.d2, mine.id, stride, (lane & stride) == 0);
+            if (lane >= k) {
+                mine.d2 = CUDART_INF;
+                mine.id = 0x7fffffff;
+            }
+            found = min(found + cnt, k);
+            kd2 = __shfl_sync(full, mine.d2, k - 1);
+            kid = __shfl_sync(full, mine.id, k - 1);
+            return;
+        }
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
