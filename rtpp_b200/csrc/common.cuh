@@ -112,6 +112,11 @@ __device__ __forceinline__ bool rt_probe(const PlaneView &p, int row, int col) {
     return (word >> (col & 31)) & 1u;
 }
 
+// Truncation of a non-negative binary32 below 2^23 without the conversion pipe: adding 2^23 with
+// round-toward-zero leaves floor(v) in the low mantissa bits (one FADD.RZ instead of F2I.TRUNC,
+// which issues at a quarter of the FP32 rate).  Only used where 0 <= v < 2^23 is proven (safe edges).
+__device__ __forceinline__ int rt_trunc_pos(float v) { return __float_as_int(__fadd_rz(v, 8388608.0f)) - 0x4B000000; }
+
 // Probe with no bounds test: only for coordinates proven to be inside the plane.
 __device__ __forceinline__ uint32_t rt_probe_word(const PlaneView &p, int row, int col) {
     return __ldg(p.w + ((((unsigned)(row >> 5) * p.tilesX + (col >> 5)) << 5) + (row & 31))) >> (col & 31);
@@ -165,11 +170,13 @@ __device__ __forceinline__ bool rt_edge_blocked(const PlaneView &p, float psx, f
     const float inv = rt_inv_pow2(P);
     if (rt_edge_safe(p, psx, psy, pex, pey)) {
         uint32_t acc = 0;
+        float t = inv; // t_j = j/P accumulated exactly (dyadic)
         for (int j = 1; j < P; j++) {
-            const float t = __fmul_rn((float)j, inv), omt = __fsub_rn(1.0f, t);
-            const int x = __float2int_rz(__fadd_rn(__fmul_rn(psx, t), __fmul_rn(omt, pex)));
-            const int y = __float2int_rz(__fadd_rn(__fmul_rn(psy, t), __fmul_rn(omt, pey)));
+            const float omt = __fsub_rn(1.0f, t);
+            const int x = rt_trunc_pos(__fadd_rn(__fmul_rn(psx, t), __fmul_rn(omt, pex)));
+            const int y = rt_trunc_pos(__fadd_rn(__fmul_rn(psy, t), __fmul_rn(omt, pey)));
             acc |= rt_probe_word(p, y, x);
+            t = __fadd_rn(t, inv);
         }
         return acc & 1u;
     }

@@ -20,67 +20,74 @@
 
 static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 32 -> warp marches
 
+// The warp-level body of K1: every lane brings one edge (e = ps.x, ps.y, pe.x, pe.y; valid = false
+// for padding lanes) and gets the ballot word of the 32 verdicts.
+__device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, const float4 e, const bool valid, const MarchThresholds &mt) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t acc = 0; // bit 0 = blocked
+    int P = 1;
+    bool safe = true;
+    if (valid) {
+        safe = rt_edge_safe(pl, e.x, e.y, e.z, e.w);
+        if (safe)
+            acc = rt_probe_word(pl, rt_trunc_pos(e.y), rt_trunc_pos(e.x)) | rt_probe_word(pl, rt_trunc_pos(e.w), rt_trunc_pos(e.z));
+        else
+            acc = rt_probe(pl, __float2int_rz(e.y), __float2int_rz(e.x)) | rt_probe(pl, __float2int_rz(e.w), __float2int_rz(e.z));
+        P = rt_march_P(mt, rt_sqlen(e.x, e.y, e.z, e.w));
+    }
+    acc &= 1u;
+    if (!acc && P <= kShortMaxP) {
+        const float inv = rt_inv_pow2(P);
+        if (safe) {
+            float t = inv; // t_j = j/P accumulated exactly (dyadic), no int->float conversion
+#pragma unroll 4
+            for (int j = 1; j < P; j++) {
+                const float omt = __fsub_rn(1.0f, t);
+                const int x = rt_trunc_pos(__fadd_rn(__fmul_rn(e.x, t), __fmul_rn(omt, e.z)));
+                const int y = rt_trunc_pos(__fadd_rn(__fmul_rn(e.y, t), __fmul_rn(omt, e.w)));
+                acc |= rt_probe_word(pl, y, x);
+                t = __fadd_rn(t, inv);
+            }
+            acc &= 1u;
+        } else {
+            for (int j = 1; j < P; j++) acc |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+        }
+    }
+    unsigned longmask = __ballot_sync(full, !acc && P > kShortMaxP);
+    while (longmask) {
+        const int src = __ffs(longmask) - 1;
+        longmask &= longmask - 1;
+        const float sx = __shfl_sync(full, e.x, src), sy = __shfl_sync(full, e.y, src);
+        const float tx = __shfl_sync(full, e.z, src), ty = __shfl_sync(full, e.w, src);
+        const int Ps = __shfl_sync(full, P, src);
+        const float inv = rt_inv_pow2(Ps);
+        bool hit = false;
+        for (int j0 = 1; j0 < Ps; j0 += 32) { // warp-uniform trip count, early exit per chunk
+            const int j = j0 + lane;
+            if (j < Ps) hit = rt_probe_interior(pl, sx, sy, tx, ty, __fmul_rn((float)j, inv));
+            if (__any_sync(full, hit)) {
+                hit = true;
+                break;
+            }
+        }
+        if (lane == src) acc = hit;
+    }
+    return __ballot_sync(full, acc != 0);
+}
+
 __global__ void __launch_bounds__(256)
 edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, MarchThresholds mt,
                       uint32_t *__restrict__ out_bits) {
-    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t nwords = (n + 31) >> 5;
     for (size_t w = warp0; w < nwords; w += nwarps) {
         const size_t i = (w << 5) + lane;
-        uint32_t acc = 0; // bit 0 = blocked
-        int P = 1;
-        bool safe = true;
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) {
-            e = ld_stream_f4(edges + i);
-            safe = rt_edge_safe(pl, e.x, e.y, e.z, e.w);
-            if (safe)
-                acc = rt_probe_word(pl, __float2int_rz(e.y), __float2int_rz(e.x)) |
-                      rt_probe_word(pl, __float2int_rz(e.w), __float2int_rz(e.z));
-            else
-                acc = rt_probe(pl, __float2int_rz(e.y), __float2int_rz(e.x)) |
-                      rt_probe(pl, __float2int_rz(e.w), __float2int_rz(e.z));
-            P = rt_march_P(mt, rt_sqlen(e.x, e.y, e.z, e.w));
-        }
-        acc &= 1u;
-        if (!acc && P <= kShortMaxP) {
-            const float inv = rt_inv_pow2(P);
-            if (safe) {
-#pragma unroll 4
-                for (int j = 1; j < P; j++) {
-                    const float t = __fmul_rn((float)j, inv), omt = __fsub_rn(1.0f, t);
-                    const int x = __float2int_rz(__fadd_rn(__fmul_rn(e.x, t), __fmul_rn(omt, e.z)));
-                    const int y = __float2int_rz(__fadd_rn(__fmul_rn(e.y, t), __fmul_rn(omt, e.w)));
-                    acc |= rt_probe_word(pl, y, x);
-                }
-                acc &= 1u;
-            } else {
-                for (int j = 1; j < P; j++) acc |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
-            }
-        }
-        unsigned longmask = __ballot_sync(full, !acc && P > kShortMaxP);
-        while (longmask) {
-            const int src = __ffs(longmask) - 1;
-            longmask &= longmask - 1;
-            const float sx = __shfl_sync(full, e.x, src), sy = __shfl_sync(full, e.y, src);
-            const float tx = __shfl_sync(full, e.z, src), ty = __shfl_sync(full, e.w, src);
-            const int Ps = __shfl_sync(full, P, src);
-            const float inv = rt_inv_pow2(Ps);
-            bool hit = false;
-            for (int j0 = 1; j0 < Ps; j0 += 32) { // warp-uniform trip count, early exit per chunk
-                const int j = j0 + lane;
-                if (j < Ps) hit = rt_probe_interior(pl, sx, sy, tx, ty, __fmul_rn((float)j, inv));
-                if (__any_sync(full, hit)) {
-                    hit = true;
-                    break;
-                }
-            }
-            if (lane == src) acc = hit;
-        }
-        const unsigned bits = __ballot_sync(full, acc != 0);
+        if (i < n) e = ld_stream_f4(edges + i);
+        const unsigned bits = warp_edges_verdict(pl, e, i < n, mt);
         if (lane == 0) out_bits[w] = bits;
     }
 }
@@ -211,33 +218,36 @@ edge_first_hit_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, 
 // (node i -> knn[i][j]) of RewireRoot (AMRRT.cpp:496-500) — so a tick moves no edge list at all:
 // 4 index bytes + two 8-byte coordinate gathers (L2-resident node table) per edge.
 __global__ void __launch_bounds__(256)
-edge_check_resident_kernel(PlaneView pl, const float2 *__restrict__ xy, const cpword *__restrict__ cp, const int *__restrict__ knn,
-                           int n, int k, MarchThresholds mt, uint32_t *__restrict__ out_bits) {
-    const unsigned full = 0xffffffffu;
+edge_check_resident_kernel(PlaneView pl, const float2 *__restrict__ xy, const float2 *__restrict__ sxy, const cpword *__restrict__ cp,
+                           const int *__restrict__ knn_pos, int n, int k, MarchThresholds mt, uint32_t *__restrict__ out_bits) {
     const int lane = threadIdx.x & 31;
-    const size_t n_edges = (size_t)(n - 1) + (size_t)n * k;
+    const size_t n_tree = (size_t)(n - 1), n_edges = n_tree + (size_t)n * k;
     const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t nwords = (n_edges + 31) >> 5;
+    const bool small = n_edges < 0xffffffffull; // 32-bit row arithmetic (always, up to 1.6e8 nodes at k = 25)
     for (size_t w = warp0; w < nwords; w += nwarps) {
         const size_t i = (w << 5) + lane;
-        bool blocked = false;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool valid = false;
         if (i < n_edges) {
-            int a, b;
-            if (i < (size_t)(n - 1)) {
-                b = (int)i + 1;
-                a = cp_parent(cp[b]);
-            } else {
-                const size_t r = i - (size_t)(n - 1);
-                a = (int)(r / k);
-                b = knn[r];
-            }
-            if (a >= 0 && b >= 0) {
-                const float2 pa = xy[a], pb = xy[b];
-                blocked = rt_edge_blocked(pl, pa.x, pa.y, pb.x, pb.y, mt);
+            if (i < n_tree) { // tree edge (parent -> child)
+                const int b = (int)i + 1, a = cp_parent(cp[b]);
+                if (a >= 0) {
+                    const float2 pa = xy[a], pb = xy[b];
+                    e = make_float4(pa.x, pa.y, pb.x, pb.y), valid = true;
+                }
+            } else { // rewire edge (node a -> its j-th neighbour); the neighbour is fetched by sorted position
+                const size_t r = i - n_tree;
+                const int a = small ? (int)((unsigned)r / (unsigned)k) : (int)(r / (unsigned)k);
+                const int bp = knn_pos[r];
+                if (bp >= 0) {
+                    const float2 pa = xy[a], pb = sxy[bp];
+                    e = make_float4(pa.x, pa.y, pb.x, pb.y), valid = true;
+                }
             }
         }
-        const unsigned bits = __ballot_sync(full, blocked);
+        const unsigned bits = warp_edges_verdict(pl, e, valid, mt);
         if (lane == 0) out_bits[w] = bits;
     }
 }
@@ -304,7 +314,7 @@ int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32
     if (!ctx || !d_bits) return RTPP_ERR_INVALID;
     NodeStore *s = ctx->nodes;
     if (!s || !s->knn_table) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_knn_table_build has not been called");
-    if (s->knn_n != s->n) RTPP_FAIL(ctx, RTPP_ERR_STATE, "nodes were appended after rtpp_knn_table_build");
+    if (s->knn_n != s->n || s->n_sorted != s->n) RTPP_FAIL(ctx, RTPP_ERR_STATE, "nodes were appended after rtpp_knn_table_build");
     if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
     PlaneView pv;
     int rc = rtpp_select_plane(ctx, plane_mask, &pv);
@@ -313,7 +323,7 @@ int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32
     if (n_edges) *n_edges = ne;
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
-    edge_check_resident_kernel<<<edge_grid(ctx, ne, 256), 256, 0, ctx->stream>>>(pv, s->xy, s->cp, s->knn_table, s->n, s->knn_k, mt, d_bits);
+    edge_check_resident_kernel<<<edge_grid(ctx, ne, 256), 256, 0, ctx->stream>>>(pv, s->xy, s->sxy, s->cp, s->knn_pos, s->n, s->knn_k, mt, d_bits);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }

@@ -86,7 +86,7 @@ void rtpp_nodes_destroy(rtpp_ctx *ctx) {
     NodeStore *s = ctx->nodes;
     if (!s) return;
     cudaFree(s->xy), cudaFree(s->sxy), cudaFree(s->sid), cudaFree(s->cell_of), cudaFree(s->cell_start), cudaFree(s->cursor);
-    cudaFree(s->knn_table), cudaFree(s->scan_totals), cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
+    cudaFree(s->knn_table), cudaFree(s->knn_pos), cudaFree(s->pos_of), cudaFree(s->scan_totals), cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
     delete s;
     ctx->nodes = nullptr;
 }
@@ -242,6 +242,17 @@ int rtpp_knn(rtpp_ctx *ctx, const double *qxy, size_t nq, int k, int32_t *idx, d
     return RTPP_OK;
 }
 
+__global__ void __launch_bounds__(256) grid_pos_of_kernel(const int *__restrict__ sid, int n, int *__restrict__ pos_of) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) pos_of[sid[p]] = p;
+}
+__global__ void __launch_bounds__(256) grid_knn_pos_kernel(const int *__restrict__ knn, size_t m, const int *__restrict__ pos_of,
+                                                          int *__restrict__ knn_pos) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = knn[e];
+        knn_pos[e] = b >= 0 ? pos_of[b] : -1;
+    }
+}
+
 // resident all-k-NN table of the node set, kept inside the ctx for the tick-level calls
 int rtpp_knn_table_build(rtpp_ctx *ctx, int k) {
     if (!ctx) return RTPP_ERR_INVALID;
@@ -250,15 +261,26 @@ int rtpp_knn_table_build(rtpp_ctx *ctx, int k) {
     if (k < 1 || k > 32) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "k must be in 1..32");
     if (s->knn_table && (s->knn_k != k || s->knn_n < s->n)) {
         RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(s->knn_table);
-        s->knn_table = nullptr;
+        cudaFree(s->knn_table), cudaFree(s->knn_pos);
+        s->knn_table = s->knn_pos = nullptr;
     }
     if (!s->knn_table) {
         RTPP_CK(ctx, cudaMalloc(&s->knn_table, (size_t)s->capacity * k * sizeof(int)));
+        RTPP_CK(ctx, cudaMalloc(&s->knn_pos, (size_t)s->capacity * k * sizeof(int)));
+        if (!s->pos_of) RTPP_CK(ctx, cudaMalloc(&s->pos_of, (size_t)s->capacity * sizeof(int)));
         s->knn_k = k;
     }
     s->knn_n = s->n;
-    return rtpp_knn_nodes_dev(ctx, k, s->knn_table, nullptr);
+    int rc = rtpp_knn_nodes_dev(ctx, k, s->knn_table, nullptr); // also re-sorts the hash: sid covers every node
+    if (rc) return rc;
+    // the same table in cell-sorted positions: neighbours of a node are neighbours in sxy[], so the
+    // tick-level edge kernel gathers their coordinates from a few sectors instead of 32
+    grid_pos_of_kernel<<<grid_for(ctx, s->n), 256, 0, ctx->stream>>>(s->sid, s->n, s->pos_of);
+    RTPP_LAUNCHED(ctx);
+    const size_t m = (size_t)s->n * k;
+    grid_knn_pos_kernel<<<grid_for(ctx, m), 256, 0, ctx->stream>>>(s->knn_table, m, s->pos_of, s->knn_pos);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
 }
 
 int rtpp_knn_table_dev(rtpp_ctx *ctx, const int32_t **d_idx, int *k) {

@@ -43,6 +43,8 @@ struct NodeStore {
     int *counters = nullptr;    // [8]
     int *knn_table = nullptr;   // resident all-k-NN table [n * knn_k] (rtpp_knn_table_build)
     int knn_k = 0, knn_n = 0;
+    int *knn_pos = nullptr;     // the same table in cell-sorted positions (coherent coordinate gathers)
+    int *pos_of = nullptr;      // node id -> cell-sorted position
 };
 
 int rtpp_nodes_build_internal(rtpp_ctx *ctx);
