@@ -463,7 +463,48 @@ def measure_extras(wl, torch):
     out["rewire_to_quiescence_ms"] = (time.perf_counter() - t0) * 1e3
     out["rewire_sweeps"] = sweeps
     out.update(measure_replanning(ctx))
+    out.update(measure_fmt(ctx))
     return out
+
+
+def measure_fmt(ctx, samples=100_000, iters=20_000):
+    """BASELINE configs[2]: RT-FMT on GAME0 with 1e5 free-space samples (the reference ships 2000).
+    GPU: rtpp_fmt_start (hash + static 25-NN table) and `iters` rounds of ExpandFMT + both rewires on
+    the engine; CPU: the oracle port of the same loops (1 thread: one planner instance is sequential)."""
+    import rtpp_b200
+    from oracle import loader as orc
+
+    S = orc.load_map("GAME0")
+    H, W = S.shape
+    o = orc.OrcRTFMT(S)
+    o.set_agent(360.0, 540.0)  # RTFMT/test/test.cpp:56
+    o.set_goal(2000.0, 400.0)
+    t0 = time.perf_counter()
+    o.start(orc.rand31(1, 3 * samples + 1000), samples)
+    cpu_start = time.perf_counter() - t0
+    xy = o.dump()[0]
+    eng = rtpp_b200.FmtEngine(ctx, 1, len(xy) + 32, 5, W, H)
+    eng.set_map(0, 1, S)
+    t0 = time.perf_counter()
+    eng.start(np.zeros(1, np.int32), [xy], np.array([[2000.0, 400.0]], np.float32))
+    ctx.sync()
+    gpu_start = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.tick(update_tree=True, iters=iters, with_rewire=True, get_path=True)
+    ctx.sync()
+    gpu_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    o.update_tree()
+    o.expand(iters, True)
+    cpu_s = time.perf_counter() - t0
+    par, c, cl, st = eng.read_tree(0)
+    oxy, opar, oc, ocl, ost = o.dump()
+    same = bool(np.array_equal(par, opar) and np.array_equal(st, ost) and np.array_equal(c.view(np.uint32), oc.view(np.uint32)))
+    eng.close()
+    o.close()
+    return {"rtfmt_1e5": {"samples": samples, "rounds": iters, "gpu_start_ms": gpu_start * 1e3, "gpu_rounds_per_s": iters / gpu_s,
+                          "cpu_start_ms": cpu_start * 1e3, "cpu_rounds_per_s": iters / cpu_s, "cpu_kind": "port, 1 thread",
+                          "state_matches_cpu": same}}
 
 
 def measure_replanning(ctx, n_inst=4096, ticks=3, dt=5000):

@@ -146,7 +146,7 @@ def tree_propagate(S, D, xy, parent, root, divisor, mask, cost, col):
     return cost, col, r
 
 
-def relax_fixpoint(S, D, xy, knn_idx, divisor, mask, cost, col, parent, max_sweeps=1000):
+def relax_fixpoint(S, D, xy, knn_idx, divisor, mask, cost, col, parent, max_sweeps=1000, free_only=False):
     H, W = (S if S is not None else D).shape
     xy = _c(xy, np.float32).reshape(-1, 2)
     knn_idx = _c(knn_idx, np.int32)
@@ -154,7 +154,7 @@ def relax_fixpoint(S, D, xy, knn_idx, divisor, mask, cost, col, parent, max_swee
     col = _c(col, np.uint8).copy()
     parent = _c(parent, np.int32).copy()
     s = lib().orc_relax_fixpoint(_ptr(S), _ptr(D), W, H, _ptr(xy), len(xy), _ptr(knn_idx), knn_idx.shape[1], divisor, mask,
-                                 _ptr(cost), _ptr(col), _ptr(parent), max_sweeps)
+                                 _ptr(cost), _ptr(col), _ptr(parent), max_sweeps, int(free_only))
     return cost, col, parent, s
 
 

@@ -146,9 +146,10 @@ ORC_EXPORT int orc_tree_propagate(const uint8_t *S, const uint8_t *D, int W, int
 // change — the least fixpoint the wave-synchronous atomicMin kernel must also reach.  The relax
 // is RTRRT.cpp:305-319 (strict <, lexicographic).  Ties on cost keep the incumbent parent, so
 // parents are compared only where costs are unique (tests do that).
+// free_only = 1: AM-RRT* RewireRoot's rule (AMRRT.cpp:500-504): only over free edges, never to a colliding cost.
 ORC_EXPORT int orc_relax_fixpoint(const uint8_t *S, const uint8_t *D, int W, int H, const float *xy, int n,
                                   const int32_t *knn_idx, int k, int divisor, int mask, float *cost, uint8_t *col,
-                                  int32_t *parent, int max_sweeps) {
+                                  int32_t *parent, int max_sweeps, int free_only) {
     Map m = mk_map(S, D, W, H);
     int sweeps = 0;
     for (; sweeps < max_sweeps; sweeps++) {
@@ -159,8 +160,12 @@ ORC_EXPORT int orc_relax_fixpoint(const uint8_t *S, const uint8_t *D, int W, int
                 int s = knn_idx[(size_t)x * k + j];
                 if (s < 0) continue;
                 Pt ps{xy[2 * s], xy[2 * s + 1]};
-                Cost c_new = Cost{col[x] != 0, cost[x]} + Cost{edge_blocked(m, px, ps, divisor, mask), dist(px, ps)};
+                if (s == x) continue;
+                const bool blocked = edge_blocked(m, px, ps, divisor, mask);
+                if (free_only && blocked) continue;
+                Cost c_new = Cost{col[x] != 0, cost[x]} + Cost{blocked, dist(px, ps)};
                 Cost c_old{col[s] != 0, cost[s]};
+                if (free_only && c_new.col) continue;
                 if (c_new < c_old) {
                     cost[s] = c_new.c, col[s] = c_new.col, parent[s] = x;
                     changed = true;

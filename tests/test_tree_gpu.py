@@ -84,7 +84,13 @@ def test_propagate_and_relax(ctx, oracle, name, n, divisor):
     assert np.array_equal(rl, fl)
     free = fl == 0
     assert np.array_equal(rc[free].view(np.uint32), fc[free].view(np.uint32))
-    # every parent explains its child's cost exactly (tree consistency of the relaxed links)
+    # ---- AM-RRT* rule (free edges only, AMRRT.cpp:500-504) from the propagated state
+    ctx.tree_set(par, oc2, ol2)
+    ctx.relax_dev(d_idx, k, divisor, 3, free_only=True)
+    _, ac, al = ctx.tree_get()
+    fc2, fl2, _, _ = oracle.relax_fixpoint(S, D2, xy, idx, divisor, 3, oc2, ol2, par, free_only=True)
+    assert np.array_equal(al, fl2)
+    assert np.array_equal(ac[fl2 == 0].view(np.uint32), fc2[fl2 == 0].view(np.uint32))
     ctx.dev_free(d_idx)
 
 
