@@ -505,3 +505,182 @@ class RefAMRRT(OrcAMRRT):
         ps = np.zeros((len(xyxy), 2), np.float32)
         self.L.ref_amrrt_crash_start(self.h, _ptr(xyxy), C.c_longlong(len(xyxy)), _ptr(out), _ptr(ps))
         return out, ps
+
+
+# ------------------------------------------------------------------ CDRT-RRT* --------------------
+def load_cdrt_fixture(name):
+    """Decomposition graph + id planes of a bundled map (tools/make_cdrt_fixtures.py, reference StartCut + cv2)."""
+    z = np.load(os.path.join(GOLDEN, "cdrt", f"{name}.npz"))
+    H, W = (int(v) for v in z["shape"])
+    graphs = []
+    for g in range(int(z["n_groups"])):
+        graphs.append({k: np.ascontiguousarray(z[f"g{g}_{k}"]) for k in
+                       ["cut_se", "cut_core", "cp_off", "cp", "cc_off", "cc", "pv_off", "pv", "poly_core", "pc_off", "pc", "pp_off", "pp"]})
+    return {"name": name, "W": W, "H": H, "graphs": graphs, "amap": np.ascontiguousarray(z["amap"]),
+            "imap": np.ascontiguousarray(z["imap"]), "resolution": float(z["resolution"])}
+
+
+class CdrtCpu:
+    """One CDRT-RRT* planner on the CPU: impl='oracle' (oracle/cdrt_oracle.hpp) or impl='ref' (the reference's
+    CDRT.cpp compiled in place, oracle/_ref/libref_cdrt.so).  Same calls on both, so tests run them side by side.
+    The reference keeps two function-local static timers (CDRT.cpp:929-930) and the harness one global clock and
+    rand stream: each 'ref' instance loads a private copy of the shared object so that every planner starts fresh."""
+
+    def __init__(self, fx, impl="oracle"):
+        self.impl, self.fx = impl, fx
+        self._tmp = None
+        if impl == "oracle":
+            self.L, self.pre = lib(), "orc_cdrt_"
+        else:
+            import shutil
+            import tempfile
+
+            src = os.path.join(HERE, "_ref", "libref_cdrt.so")
+            if not os.path.exists(src):
+                raise FileNotFoundError(src)
+            fd, self._tmp = tempfile.mkstemp(suffix=".so", prefix="libref_cdrt_")
+            os.close(fd)
+            shutil.copyfile(src, self._tmp)
+            self.L, self.pre = C.CDLL(self._tmp), "ref_cdrt_"
+            self.L.ref_rand_pos.restype = C.c_longlong
+            self.L.ref_clock_reads.restype = C.c_longlong
+        self.f("create").restype = C.c_void_p
+        self.h = C.c_void_p(self.f("create")(fx["W"], fx["H"], C.c_double(0.1), C.c_double(0.5)))
+        for g in fx["graphs"]:
+            ncut, npoly = len(g["cut_se"]), len(g["poly_core"])
+            self.f("set_graph")(self.h, ncut, _ptr(g["cut_se"]), _ptr(g["cut_core"]), _ptr(g["cp_off"]), _ptr(g["cp"]), _ptr(g["cc_off"]),
+                                _ptr(g["cc"]), npoly, _ptr(g["pv_off"]), _ptr(g["pv"]), _ptr(g["poly_core"]), _ptr(g["pc_off"]), _ptr(g["pc"]),
+                                _ptr(g["pp_off"]), _ptr(g["pp"]))
+        self.f("set_planes")(self.h, _ptr(fx["amap"]), _ptr(fx["imap"]))
+        self._rand = None
+
+    def f(self, name):
+        return getattr(self.L, self.pre + name)
+
+    def close(self):
+        if self.h:
+            self.f("destroy")(self.h)
+            self.h = None
+        if self._tmp:
+            os.unlink(self._tmp)
+            self._tmp = None
+
+    def set_params(self, r_th=10.0, p_th=0.85, nearK=20, RewireN=100):
+        self.f("set_params")(self.h, C.c_double(r_th), C.c_double(p_th), nearK, RewireN)
+
+    def set_clock(self, dt_ns, n0=0):
+        if self.impl == "oracle":
+            self.L.orc_cdrt_set_clock(self.h, C.c_longlong(dt_ns), C.c_longlong(n0))
+        else:
+            self.L.ref_set_clock(C.c_longlong(dt_ns), C.c_longlong(n0))
+
+    def clock_reads(self):
+        if self.impl == "oracle":
+            self.L.orc_cdrt_clock_reads.restype = C.c_longlong
+            return self.L.orc_cdrt_clock_reads(self.h)
+        return self.L.ref_clock_reads()
+
+    def set_rand(self, r):
+        self._rand = _c(r, np.int32)
+        if self.impl == "oracle":
+            self.L.orc_cdrt_set_rand(self.h, _ptr(self._rand), C.c_longlong(len(self._rand)))
+        else:
+            self.L.ref_set_rand(_ptr(self._rand), C.c_longlong(len(self._rand)))
+
+    def rand_pos(self):
+        if self.impl == "oracle":
+            self.L.orc_cdrt_rand_pos.restype = C.c_longlong
+            return self.L.orc_cdrt_rand_pos(self.h)
+        return self.L.ref_rand_pos()
+
+    def set_agent(self, x, y):
+        self.f("set_agent")(self.h, C.c_double(x), C.c_double(y))
+
+    def set_goal(self, x, y):
+        self.f("set_goal")(self.h, C.c_double(x), C.c_double(y))
+
+    def add_obstacle(self, num, typ, x, y, angle, radius, outline, check_len=2.0):
+        o = _c(outline, np.float64).reshape(-1, 2)
+        self.f("add_obstacle")(self.h, num, typ, C.c_double(x), C.c_double(y), C.c_double(angle), C.c_double(radius), _ptr(o), len(o),
+                               C.c_double(check_len))
+
+    def move_obstacle(self, num, x, y, angle=0.0):
+        self.f("move_obstacle")(self.h, num, C.c_double(x), C.c_double(y), C.c_double(angle))
+
+    def check_points(self, num, cap=8192):
+        out = np.zeros((cap, 2), np.float64)
+        n = self.f("check_points")(self.h, num, _ptr(out), cap)
+        return out[:n]
+
+    def start(self, resolution=None):
+        self.f("start")(self.h, C.c_double(self.fx["resolution"] if resolution is None else resolution))
+
+    def task(self):
+        self.f("task")(self.h)
+
+    def draw_dobs(self):
+        out = np.zeros((self.fx["H"], self.fx["W"]), np.uint8)
+        self.f("draw_dobs")(self.h, _ptr(out))
+        return out
+
+    def set_dobs(self, plane):
+        self.f("set_dobs")(self.h, _ptr(None if plane is None else _c(plane, np.uint8)))
+
+    def crash_dobs_island(self):
+        self.f("crash_dobs_island")(self.h)
+
+    def update_tree_cost(self):
+        self.f("update_tree_cost")(self.h)
+
+    def crash(self, xyxy, inv_s, inv_e):
+        xyxy = _c(xyxy, np.float64).reshape(-1, 4)
+        inv_s, inv_e = _c(inv_s, np.int32), _c(inv_e, np.int32)
+        out = np.zeros(len(xyxy), np.uint8)
+        self.f("crash")(self.h, _ptr(xyxy), _ptr(inv_s), _ptr(inv_e), C.c_longlong(len(xyxy)), _ptr(out))
+        return out
+
+    def neighbor(self, x, y, invM, cap=4096):
+        out = np.zeros((cap, 2), np.float64)
+        n = self.f("neighbor")(self.h, C.c_double(x), C.c_double(y), C.c_int32(int(np.array(invM & 0xFFFFFFFF, np.uint32).view(np.int32))),
+                               _ptr(out), cap)
+        return out[:n]
+
+    def dump(self):
+        """Nodes in Node_Map order (sorted by (x, y)): xy, parent xy, cost, collision, invM, #children."""
+        n = self.f("num_nodes")(self.h)
+        xy, par = np.zeros((n, 2)), np.zeros((n, 2))
+        cost, col, inv, ns = np.zeros(n), np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        m = self.f("dump")(self.h, _ptr(xy), _ptr(par), _ptr(cost), _ptr(col), _ptr(inv), _ptr(ns))
+        assert m == n
+        return xy, par, cost, col, inv, ns
+
+    def state(self):
+        d, s = np.zeros(4), np.zeros(8, np.int32)
+        self.f("state")(self.h, _ptr(d), _ptr(s))
+        return dict(agent=d[:2].copy(), agent_tag=d[2:].copy(), apl=int(s[0]), island=int(s[1]), queue=int(s[2]), larger=int(s[3]),
+                    smaller=int(s[4]), samples_left=int(s[5]), n_trees=int(s[6]), goal_set=int(s[7]))
+
+    def tree_islands(self, cap=4096):
+        a, b = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        n = self.f("tree_islands")(self.h, _ptr(a), _ptr(b), cap)
+        return a[:n].copy(), b[:n].copy()
+
+    def samples(self, cap=1 << 16):
+        xy, cut = np.zeros((cap, 2)), np.zeros(cap, np.int32)
+        n = self.f("samples")(self.h, _ptr(xy), _ptr(cut), cap)
+        return xy[:n].copy(), cut[:n].copy()
+
+    def get_path(self, cap=2048):
+        xy = np.zeros((cap, 2))
+        col, cost = C.c_int(), C.c_double()
+        n = self.f("get_path")(self.h, _ptr(xy), cap, C.byref(col), C.byref(cost))
+        return xy[: min(n, cap)].copy(), bool(col.value), cost.value
+
+    def counters(self):
+        out = np.zeros(6, np.int64)
+        if self.impl == "oracle":
+            self.L.orc_cdrt_counters(self.h, _ptr(out))
+        return dict(zip(["pops", "rewired", "sampled", "edge_checks", "knn", "pushes"], out.tolist()))
+
+    def error(self):
+        return self.L.orc_cdrt_error(self.h) if self.impl == "oracle" else 0

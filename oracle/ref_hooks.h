@@ -5,6 +5,16 @@
 // headers are included first so that only the reference's own code sees the renamed calls.
 #pragma once
 #include <cstdlib>
+#ifdef REF_HOOK_STD_RAND
+// CDRT.cpp:330 shuffles the cut-line samples with std::random_shuffle, whose libstdc++ body calls
+// std::rand(): define the redirect before <algorithm> is parsed so the shuffle too draws from the
+// injected stream (first + rand() % (i + 1) for i = 1..n-1).
+extern "C" int rtpp_ref_rand(void);
+namespace std { using ::rtpp_ref_rand; }
+#define rand rtpp_ref_rand
+#include <algorithm>
+#undef rand
+#endif
 #include <ctime>
 #include <time.h>
 #include <math.h>

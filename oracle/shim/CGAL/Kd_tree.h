@@ -34,6 +34,8 @@ template <class Traits> class Kd_tree {
     void insert(const Point_d &p) { pts.push_back(p); }
     size_t size() const { return pts.size(); }
     void clear() { pts.clear(); }
+    typename std::vector<Point_d>::const_iterator begin() const { return pts.begin(); } // CDRT.cpp:717
+    typename std::vector<Point_d>::const_iterator end() const { return pts.end(); }
     std::vector<Point_d> pts;
 };
 

@@ -42,6 +42,8 @@ struct Point {
 struct Scalar {
     double v[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : v{a, b, c, d} {}
+    double &operator[](int i) { return v[i]; }
+    const double &operator[](int i) const { return v[i]; }
 };
 
 class Mat {
@@ -54,6 +56,26 @@ class Mat {
     Mat(int r, int c, int t) : rows(r), cols(c), type_(t), buf(std::make_shared<std::vector<uint8_t>>((size_t)r * c * esz(t), 0)) {}
     static int esz(int t) { return t == CV_16U ? 2 : (t == CV_8UC3 ? 3 : 1); }
     static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
+    // CDRT.cpp:123-124 writes cv::Mat::ones(rows, cols, CV_16U) * 0xFFFF: every element = 0xFFFF
+    static Mat ones(int r, int c, int t) {
+        Mat m(r, c, t);
+        if (t == CV_16U) {
+            uint16_t *p = reinterpret_cast<uint16_t *>(m.data());
+            for (size_t i = 0; i < (size_t)r * c; i++) p[i] = 1;
+        } else
+            std::memset(m.data(), 1, m.buf->size());
+        return m;
+    }
+    Mat operator*(double s) const { // saturating scale of a 16U/8U plane
+        Mat m = clone();
+        if (type_ == CV_16U) {
+            uint16_t *p = reinterpret_cast<uint16_t *>(m.data());
+            for (size_t i = 0; i < (size_t)rows * cols; i++) p[i] = (uint16_t)std::min(65535.0, std::max(0.0, std::nearbyint(p[i] * s)));
+        } else if (type_ == CV_8U) {
+            for (size_t i = 0; i < (size_t)rows * cols; i++) m.data()[i] = (uint8_t)std::min(255.0, std::max(0.0, std::nearbyint(m.data()[i] * s)));
+        }
+        return m;
+    }
     bool empty() const { return !buf || rows == 0 || cols == 0; }
     int type() const { return type_; }
     void convertTo(Mat &dst, int) const { dst = clone(); }
@@ -123,6 +145,18 @@ inline void fillPoly(Mat &img, const std::vector<std::vector<Point>> &polys, con
         for (const Point &q : p) xy.push_back(q.x), xy.push_back(q.y);
         shim_fillpoly_hook()(img.data(), img.rows, img.cols, xy.data(), (int)p.size(), (uint8_t)color.v[0]);
     }
+}
+// fillConvexPoly on the 16-bit id planes of BImap::DrawBImap (CDRT.cpp:143-144); other depths: no-op
+typedef void (*shim_fillconvex16_fn)(uint16_t *img, int rows, int cols, const int *xy, int npts, uint16_t value);
+inline shim_fillconvex16_fn &shim_fillconvex16_hook() {
+    static shim_fillconvex16_fn f = nullptr;
+    return f;
+}
+inline void fillConvexPoly(Mat &img, const Point *pts, int npts, const Scalar &color, int = 8, int = 0) {
+    if (!shim_fillconvex16_hook() || img.type() != CV_16U) return;
+    std::vector<int> xy;
+    for (int i = 0; i < npts; i++) xy.push_back(pts[i].x), xy.push_back(pts[i].y);
+    shim_fillconvex16_hook()(reinterpret_cast<uint16_t *>(img.data()), img.rows, img.cols, xy.data(), npts, (uint16_t)color.v[0]);
 }
 inline void line(Mat &, Point, Point, const Scalar &, int = 1) {}
 inline void namedWindow(const std::string &, int = 0) {}
