@@ -254,6 +254,53 @@ RTPP_API int rtpp_fmt_read_tree(rtpp_fmt_engine *e, int inst, int max_nodes, int
                                 uint8_t *state, int *n_out);
 RTPP_API int rtpp_fmt_read_path(rtpp_fmt_engine *e, int inst, int max_len, int32_t *ids, int *len_out);
 
+/* CDRT-RRT* engine (one warp per BImap planner, sequential-exact; reference CDRT2/lib/CDRT/CDRT.cpp).
+ * The convex decomposition (BIgraph: cut lines, free convex polygons and their links, CDRT.h:240-248,
+ * built by StartCut CDRTmapcd.cpp:191-410) and the island id plane (DrawBImap CDRT.cpp:121-175:
+ * island_plane[y*W+x] = BIimap where BIamap == the agent's region, else 0xFFFF) are inputs.  Link
+ * lists are CSR (offsets + values, ascending like the reference's std::set): cp = cut line -> its
+ * polygons, cc = cut line -> adjacent cut lines, pc = polygon -> its cut lines, pv = polygon vertices.
+ *   rtpp_cdrt_create        BImap + the tunables r_th, p_th, nearK, RewireN (CDRT.h:319-322) and the
+ *                           cut-line sampling Resolution of RTRT_start
+ *   rtpp_cdrt_set_agent / set_goal    RTRT_SetAgent / RTRT_SetGoal   CDRT.cpp:384-423 (1 = rejected point)
+ *   rtpp_cdrt_add_obstacle / del_obstacle / move_obstacle
+ *                           RTRT_AddDynamicObstacle :425-500 (derives CheckPoints), RTRT_DelDynamicObstacle,
+ *                           and the demos' in-place writes to DObstacles[num].x/.y/.angle
+ *   rtpp_cdrt_start         RTRT_start :276-383 (cut-line samples, std::random_shuffle on the injected
+ *                           rand() stream, initial tree over the cut-line cores)
+ *   rtpp_cdrt_tick          RTRT_task :927-1068 for every started instance — RTRT_DrawDObsmap,
+ *                           RTRT_CrashDObsIsland, the agent hand-over, RTRT_UpdateTreeCost, larger/smaller
+ *                           sets, RewireN x RTRT_Sampling, the eQr rewiring loop — then GetPath :1076-1123.
+ * Wall-clock gates read the virtual clock (k-th read = k*dt_ns).  status: 0 ok, 1 node store full,
+ * 2 queue full, 3 island slice full, 4 the reference would have hit undefined behaviour (empty
+ * neighbour list / broken path in the agent hand-over), 5 cut-line slice full, 6 set list full. */
+typedef struct rtpp_cdrt_engine rtpp_cdrt_engine;
+RTPP_API int rtpp_cdrt_create(rtpp_ctx *ctx, int n_instances, int node_capacity, int queue_capacity, int W, int H, int ncut,
+                              const double *cut_se, const double *cut_core, const int32_t *cp_off, const int32_t *cp,
+                              const int32_t *cc_off, const int32_t *cc, int npoly, const int32_t *pv_off, const double *pv,
+                              const int32_t *pc_off, const int32_t *pc, const uint16_t *island_plane, double resolution,
+                              double r_th, double p_th, int nearK, int RewireN, int rand_capacity, rtpp_cdrt_engine **out);
+RTPP_API int rtpp_cdrt_destroy(rtpp_cdrt_engine *e);
+RTPP_API int rtpp_cdrt_set_agent(rtpp_cdrt_engine *e, int inst, double x, double y);
+RTPP_API int rtpp_cdrt_set_goal(rtpp_cdrt_engine *e, int inst, double x, double y);
+RTPP_API int rtpp_cdrt_add_obstacle(rtpp_cdrt_engine *e, int inst, int num, int type, double x, double y, double angle,
+                                    double radius, const double *outline_xy, int npts, double check_len);
+RTPP_API int rtpp_cdrt_del_obstacle(rtpp_cdrt_engine *e, int inst, int num);
+RTPP_API int rtpp_cdrt_move_obstacle(rtpp_cdrt_engine *e, int inst, int num, double x, double y, double angle);
+RTPP_API int rtpp_cdrt_start(rtpp_cdrt_engine *e, int inst, const int32_t *rand, int n_rand);
+RTPP_API int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path);
+/* 24 int64 per instance: node ids used, agent id, agent island, clock reads, rand_pos, rand_exhausted, |eQr|,
+ * |largerSet| list, |smallerSet| list, cut-line samples left, islands with a kd-tree, status, pops, rewired,
+ * sampled, pushes, edge checks, path length, path collision, path cost (binary64 bits) */
+RTPP_API int rtpp_cdrt_read_stats(rtpp_cdrt_engine *e, long long *out24);
+/* nodes by id, erased ones included (alive = 0); parent -1 = none; invM as CDRT.h:226-228 */
+RTPP_API int rtpp_cdrt_read_tree(rtpp_cdrt_engine *e, int inst, int max_nodes, double *xy, int32_t *parent, double *cost,
+                                 uint8_t *collision, int32_t *invM, uint8_t *alive, int *n_out);
+/* agent_path of the last GetPath: root ... entry node, goal */
+RTPP_API int rtpp_cdrt_read_path(rtpp_cdrt_engine *e, int inst, int max_len, double *xy, int *len_out);
+/* obsKdtreeMap: per free polygon, whether it holds a kd-tree and how many points */
+RTPP_API int rtpp_cdrt_read_islands(rtpp_cdrt_engine *e, int inst, int32_t *has_tree, int32_t *count);
+
 #ifdef __cplusplus
 }
 #endif

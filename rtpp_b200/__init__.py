@@ -4,4 +4,4 @@ the C++ planner classes above it (rtpp_b200/planners); this Python package is on
 mirror of that ABI for tests and bench.py.  There is no CPU fallback: importing works anywhere,
 but every call needs the built library and a CUDA device.
 """
-from .capi import Ctx, Engine, FmtEngine, RtppError, lib, lib_path, build  # noqa: F401
+from .capi import CdrtEngine, CdrtPlanner, Ctx, Engine, FmtEngine, RtppError, lib, lib_path, build  # noqa: F401

@@ -659,3 +659,149 @@ class PlannerAMRRT:
         col, cost = C.c_int(), C.c_float()
         n = self.L.pl_amrrt_get_path(self.h, _p(xy), cap, C.byref(col), C.byref(cost))
         return xy[: min(n, cap)], bool(col.value), cost.value
+
+
+class CdrtEngine:
+    """ctypes mirror of the rtpp_cdrt_* entry points (CDRT-RRT* engine, one warp per BImap planner).
+    `graph`: dict of the CSR arrays of one BIgraph (cut_se, cut_core, cp_off, cp, cc_off, cc, pv_off, pv, pc_off, pc);
+    `amap`/`imap`: the two 16-bit id planes of DrawBImap; `apl` = the region (graph index) the agents live in."""
+
+    STAT = ["n_ids", "agent_id", "island", "clock_reads", "rand_pos", "rand_exhausted", "queue", "larger", "smaller", "samples_left",
+            "n_trees", "status", "pops", "rewired", "sampled", "pushes", "edge_checks", "path_len", "path_col", "path_cost_bits"]
+
+    def __init__(self, ctx, n_instances, graph, amap, imap, resolution, apl=0, node_capacity=8192, queue_capacity=1 << 20,
+                 r_th=10.0, p_th=0.85, nearK=20, RewireN=100, rand_capacity=1 << 20):
+        self.ctx, self.L, self.n = ctx, ctx.L, n_instances
+        g = {k: np.ascontiguousarray(v) for k, v in graph.items()}
+        isl = np.where(np.asarray(amap) == apl, np.asarray(imap), 0xFFFF).astype(np.uint16)
+        isl = np.ascontiguousarray(isl)
+        H, W = isl.shape
+        self.npoly = len(g["pc_off"]) - 1
+        h = C.c_void_p()
+        ctx._ck(self.L.rtpp_cdrt_create(ctx.h, n_instances, node_capacity, queue_capacity, W, H, len(g["cut_se"]), _p(_c(g["cut_se"], np.float64)),
+                                        _p(_c(g["cut_core"], np.float64)), _p(_c(g["cp_off"], np.int32)), _p(_c(g["cp"], np.int32)),
+                                        _p(_c(g["cc_off"], np.int32)), _p(_c(g["cc"], np.int32)), self.npoly, _p(_c(g["pv_off"], np.int32)),
+                                        _p(_c(g["pv"], np.float64)), _p(_c(g["pc_off"], np.int32)), _p(_c(g["pc"], np.int32)), _p(isl),
+                                        C.c_double(resolution), C.c_double(r_th), C.c_double(p_th), nearK, RewireN, rand_capacity, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.rtpp_cdrt_destroy(self.h)
+            self.h = None
+
+    def set_agent(self, inst, x, y):
+        return self.L.rtpp_cdrt_set_agent(self.h, inst, C.c_double(x), C.c_double(y))
+
+    def set_goal(self, inst, x, y):
+        return self.L.rtpp_cdrt_set_goal(self.h, inst, C.c_double(x), C.c_double(y))
+
+    def add_obstacle(self, inst, num, typ, x, y, angle, radius, outline, check_len=2.0):
+        o = _c(outline, np.float64).reshape(-1, 2)
+        self.ctx._ck(self.L.rtpp_cdrt_add_obstacle(self.h, inst, num, typ, C.c_double(x), C.c_double(y), C.c_double(angle), C.c_double(radius),
+                                                   _p(o), len(o), C.c_double(check_len)))
+
+    def move_obstacle(self, inst, num, x, y, angle=0.0):
+        self.ctx._ck(self.L.rtpp_cdrt_move_obstacle(self.h, inst, num, C.c_double(x), C.c_double(y), C.c_double(angle)))
+
+    def start(self, inst, rand):
+        r = _c(rand, np.int32)
+        self.ctx._ck(self.L.rtpp_cdrt_start(self.h, inst, _p(r), len(r)))
+
+    def tick(self, dt_ns, get_path=True):
+        self.ctx._ck(self.L.rtpp_cdrt_tick(self.h, C.c_longlong(dt_ns), int(get_path)))
+
+    def stats(self):
+        out = np.zeros((self.n, 24), np.int64)
+        self.ctx._ck(self.L.rtpp_cdrt_read_stats(self.h, _p(out)))
+        return out
+
+    def stats_dict(self, inst=0):
+        return dict(zip(self.STAT, self.stats()[inst].tolist()))
+
+    def read_tree(self, inst=0):
+        n = C.c_int()
+        self.ctx._ck(self.L.rtpp_cdrt_read_tree(self.h, inst, 0, None, None, None, None, None, None, C.byref(n)))
+        n = n.value
+        xy, par, cost = np.zeros((n, 2)), np.zeros(n, np.int32), np.zeros(n)
+        col, inv, alive = np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        self.ctx._ck(self.L.rtpp_cdrt_read_tree(self.h, inst, n, _p(xy), _p(par), _p(cost), _p(col), _p(inv), _p(alive), C.byref(C.c_int())))
+        return xy, par, cost, col, inv, alive
+
+    def read_path(self, inst=0, cap=2048):
+        xy = np.zeros((cap, 2))
+        n = C.c_int()
+        self.ctx._ck(self.L.rtpp_cdrt_read_path(self.h, inst, cap, _p(xy), C.byref(n)))
+        return xy[: min(n.value, cap)].copy()
+
+    def read_islands(self, inst=0):
+        a, b = np.zeros(self.npoly, np.int32), np.zeros(self.npoly, np.int32)
+        self.ctx._ck(self.L.rtpp_cdrt_read_islands(self.h, inst, _p(a), _p(b)))
+        return a, b
+
+
+class CdrtPlanner:
+    """One instance of a CdrtEngine behind the BImap-like call surface the scripted demo loop drives
+    (tests/cdrt_scenarios.py): set_params / set_clock / set_rand / add_obstacle / set_agent / set_goal / start / task /
+    get_path / move_obstacle, plus dump() in Node_Map order for parity checks."""
+
+    def __init__(self, ctx, fx, inst=0, engine=None, **kw):
+        self.ctx, self.fx, self.inst, self.kw = ctx, fx, inst, kw
+        self.eng, self.own = engine, engine is None
+        self.params = dict(r_th=10.0, p_th=0.85, nearK=20, RewireN=100)
+        self.dt, self.rand, self._pending = 20000, None, []
+
+    def set_params(self, **p):
+        self.params.update(p)
+
+    def set_clock(self, dt_ns, n0=0):
+        self.dt = dt_ns
+
+    def set_rand(self, r):
+        self.rand = _c(r, np.int32)
+
+    def _engine(self):
+        if self.eng is None:
+            self.eng = CdrtEngine(self.ctx, 1, self.fx["graphs"][0], self.fx["amap"], self.fx["imap"], self.fx["resolution"],
+                                  rand_capacity=len(self.rand), **self.params, **self.kw)
+        return self.eng
+
+    def add_obstacle(self, num, typ, x, y, angle, radius, outline, check_len=2.0):
+        self._engine().add_obstacle(self.inst, num, typ, x, y, angle, radius, outline, check_len)
+
+    def move_obstacle(self, num, x, y, angle=0.0):
+        self.eng.move_obstacle(self.inst, num, x, y, angle)
+
+    def set_agent(self, x, y):
+        self._engine().set_agent(self.inst, x, y)
+
+    def set_goal(self, x, y):
+        self._engine().set_goal(self.inst, x, y)
+
+    def start(self):
+        self._engine().start(self.inst, self.rand)
+
+    def task(self):
+        self.eng.tick(self.dt, get_path=True)
+
+    def get_path(self):
+        s = self.eng.stats_dict(self.inst)
+        cost = np.array(s["path_cost_bits"], np.int64).view(np.float64)
+        return self.eng.read_path(self.inst), bool(s["path_col"]), float(cost)
+
+    def state(self):
+        return self.eng.stats_dict(self.inst)
+
+    def dump(self):
+        """Live nodes in the reference's Node_Map order (sorted by (x, y)): xy, parent xy, cost, collision, invM, #children."""
+        xy, par, cost, col, inv, alive = self.eng.read_tree(self.inst)
+        live = np.flatnonzero(alive)
+        pxy = np.where((par >= 0)[:, None], xy[np.maximum(par, 0)], -1.0)
+        nsub = np.bincount(par[live][par[live] >= 0], minlength=len(xy)).astype(np.int32)
+        order = live[np.lexsort((xy[live, 1], xy[live, 0]))]
+        return xy[order], pxy[order], cost[order], col[order], inv[order], nsub[order]
+
+    def close(self):
+        if self.own and self.eng is not None:
+            self.eng.close()
+            self.eng = None
