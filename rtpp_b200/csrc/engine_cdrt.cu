@@ -40,8 +40,8 @@
 #define FULL 0xffffffffu
 typedef unsigned long long u64;
 
-int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t *circles, int n_circles, const int32_t *poly_xy,
-                     const int32_t *poly_sizes, int n_polys);
+int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int n_planes, int W, int H, const int32_t *circles4,
+                      int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, const int32_t *poly_inst, int n_polys);
 
 static constexpr int kOrigin = 0x40000000;        // originIndexFun, CDRT.h:226
 static constexpr double kDoubleMax = 1.79769e+307; // CDRT.h:359
@@ -58,6 +58,11 @@ struct CdInst {
     int path_len, path_col;
     double path_cost;
     int n_obs, n_chk;
+};
+
+struct CdHdr { // per-tick inputs of one instance
+    double2 tag, goal;
+    int goal_set, n_obs, n_chk, started;
 };
 
 struct CdView {
@@ -83,6 +88,7 @@ struct CdView {
     uint32_t *dplane;
     size_t plane_words;
     int tilesX;
+    const CdHdr *hdr;
 };
 
 struct CdI { // per-instance pointers
@@ -809,7 +815,12 @@ __global__ void __launch_bounds__(128) cdrt_tick_kernel(CdView v, long long dt_n
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= v.n_inst) return;
     CdInst *g = v.inst + w;
-    if (g->status != ST_OK || g->n == 0) return;
+    if (g->status != ST_OK || g->n == 0 || !v.hdr[w].started) return;
+    if (lane == 0) {
+        const CdHdr h = v.hdr[w];
+        g->agent_tag = h.tag, g->goal = h.goal, g->goal_set = h.goal_set, g->n_obs = h.n_obs, g->n_chk = h.n_chk;
+    }
+    __syncwarp();
     CdI in;
     in.g = g;
     const size_t nb = (size_t)w * v.cap;
@@ -938,7 +949,7 @@ struct CdHostInst {
     std::map<int, CdObstacle> obs;
     double agent_tag[2] = {0, 0}, goal[2] = {0, 0};
     int goal_set = 0;
-    bool started = false;
+    bool started = false, check_dirty = true;
 };
 struct CdCut {
     double S[2], E[2], core[2];
@@ -952,6 +963,9 @@ struct rtpp_cdrt_engine {
     std::vector<uint16_t> isl; // host copy of the island plane
     std::vector<CdHostInst> inst;
     std::vector<void *> allocs;
+    std::vector<double> h_pose, h_chk;
+    std::vector<int> h_chk_obs;
+    bool chk_dirty = true;
 };
 
 #define CD_CK(e, call) RTPP_CK((e)->ctx, call)
@@ -1081,6 +1095,9 @@ int rtpp_cdrt_create(rtpp_ctx *ctx, int n_instances, int node_capacity, int queu
     v.rand = drand;
     rc |= cd_alloc(e, &v.pose, N * v.max_obs), rc |= cd_alloc(e, &v.chk, N * v.max_chk), rc |= cd_alloc(e, &v.chk_obs, N * v.max_chk);
     rc |= cd_alloc(e, &v.dplane, N * v.plane_words);
+    CdHdr *dh = nullptr;
+    rc |= cd_alloc(e, &dh, N);
+    v.hdr = dh;
     if (rc) {
         for (void *p : e->allocs) cudaFree(p);
         delete e;
@@ -1121,6 +1138,7 @@ int rtpp_cdrt_add_obstacle(rtpp_cdrt_engine *e, int inst, int num, int type, dou
     CdObstacle &o = e->inst[inst].obs[num];
     o.type = type, o.x = x, o.y = y, o.angle = angle, o.radius = radius;
     o.outline.assign(outline_xy, outline_xy + 2 * npts);
+    e->inst[inst].check_dirty = true;
     if (!(check_len > 0)) return RTPP_OK;
     o.check.clear();
     if (type == 0) {
@@ -1151,6 +1169,7 @@ int rtpp_cdrt_add_obstacle(rtpp_cdrt_engine *e, int inst, int num, int type, dou
 int rtpp_cdrt_del_obstacle(rtpp_cdrt_engine *e, int inst, int num) { // RTRT_DelDynamicObstacle :502-505
     if (!e || inst < 0 || inst >= e->v.n_inst) return RTPP_ERR_INVALID;
     e->inst[inst].obs.erase(num);
+    e->inst[inst].check_dirty = true;
     return RTPP_OK;
 }
 // the demos move an obstacle by writing DObstacles[num].x/.y/.angle (CDRT2/test/testD.cpp:189-190)
@@ -1283,16 +1302,18 @@ int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path) {
     if (!e || dt_ns <= 0) return RTPP_ERR_INVALID;
     rtpp_ctx *ctx = e->ctx;
     CdView &v = e->v;
-    std::vector<double> pose((size_t)v.n_inst * v.max_obs * 4, 0.0), chk((size_t)v.n_inst * v.max_chk * 2, 0.0);
-    std::vector<int> chk_obs((size_t)v.n_inst * v.max_chk, 0);
-    struct Hdr {
-        double2 tag, goal;
-        int goal_set, n_obs, n_chk;
-    };
+    std::vector<double> &pose = e->h_pose, &chk = e->h_chk;
+    std::vector<int> &chk_obs = e->h_chk_obs;
+    pose.assign((size_t)v.n_inst * v.max_obs * 4, 0.0);
+    chk.resize((size_t)v.n_inst * v.max_chk * 2);
+    chk_obs.resize((size_t)v.n_inst * v.max_chk);
+    std::vector<CdHdr> hdr(v.n_inst);
+    std::vector<int32_t> circles, poly_xy, poly_sizes, poly_inst;
     for (int i = 0; i < v.n_inst; i++) {
         CdHostInst &hi = e->inst[i];
+        CdHdr &h = hdr[i];
+        memset(&h, 0, sizeof(h));
         if (!hi.started) continue;
-        std::vector<int32_t> circles, poly_xy, poly_sizes;
         int k = 0;
         size_t nchk = 0;
         if ((int)hi.obs.size() > v.max_obs) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "too many dynamic obstacles");
@@ -1309,7 +1330,7 @@ int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path) {
                 for (size_t p = 0; p + 1 < o.outline.size(); p += 2) {
                     int ix, iy;
                     px(o.outline[p], o.outline[p + 1], &ix, &iy);
-                    circles.push_back(ix), circles.push_back(iy), circles.push_back((int)o.radius);
+                    circles.push_back(ix), circles.push_back(iy), circles.push_back((int)o.radius), circles.push_back(i);
                 }
             } else if (o.type == 1) {
                 for (size_t p = 0; p + 1 < o.outline.size(); p += 2) {
@@ -1317,7 +1338,7 @@ int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path) {
                     px(o.outline[p], o.outline[p + 1], &ix, &iy);
                     poly_xy.push_back(ix), poly_xy.push_back(iy);
                 }
-                poly_sizes.push_back((int)o.outline.size() / 2);
+                poly_sizes.push_back((int)o.outline.size() / 2), poly_inst.push_back(i);
             }
             if (nchk + o.check.size() / 2 > (size_t)v.max_chk) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "too many obstacle check points");
             for (size_t p = 0; p + 1 < o.check.size(); p += 2, nchk++) {
@@ -1326,22 +1347,20 @@ int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path) {
             }
             k++;
         }
-        int rc = rtpp_raster_into(ctx, v.dplane + (size_t)i * v.plane_words, v.W, v.H, circles.data(), (int)circles.size() / 3, poly_xy.data(),
-                                  poly_sizes.data(), (int)poly_sizes.size());
-        if (rc) return rc;
-        Hdr h;
         h.tag = make_double2(hi.agent_tag[0], hi.agent_tag[1]), h.goal = make_double2(hi.goal[0], hi.goal[1]);
-        h.goal_set = hi.goal_set, h.n_obs = k, h.n_chk = (int)nchk;
-        CdInst *g = v.inst + i;
-        CD_CK(e, cudaMemcpyAsync(&g->agent_tag, &h.tag, 16, cudaMemcpyHostToDevice, ctx->stream));
-        CD_CK(e, cudaMemcpyAsync(&g->goal, &h.goal, 16, cudaMemcpyHostToDevice, ctx->stream));
-        CD_CK(e, cudaMemcpyAsync(&g->goal_set, &h.goal_set, 4, cudaMemcpyHostToDevice, ctx->stream));
-        CD_CK(e, cudaMemcpyAsync(&g->n_obs, &h.n_obs, 8, cudaMemcpyHostToDevice, ctx->stream)); // n_obs, n_chk are adjacent
-        CD_CK(e, cudaStreamSynchronize(ctx->stream));
+        h.goal_set = hi.goal_set, h.n_obs = k, h.n_chk = (int)nchk, h.started = 1;
+        if (hi.check_dirty) e->chk_dirty = true, hi.check_dirty = false;
     }
+    int rc = rtpp_raster_batch(ctx, v.dplane, v.plane_words, v.n_inst, v.W, v.H, circles.data(), (int)circles.size() / 4, poly_xy.data(),
+                               poly_sizes.data(), poly_inst.data(), (int)poly_sizes.size());
+    if (rc) return rc;
+    CD_CK(e, cudaMemcpyAsync((void *)v.hdr, hdr.data(), hdr.size() * sizeof(CdHdr), cudaMemcpyHostToDevice, ctx->stream));
     CD_CK(e, cudaMemcpyAsync(v.pose, pose.data(), pose.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CD_CK(e, cudaMemcpyAsync(v.chk, chk.data(), chk.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CD_CK(e, cudaMemcpyAsync(v.chk_obs, chk_obs.data(), chk_obs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (e->chk_dirty) { // the check points only change with RTRT_AddDynamicObstacle
+        CD_CK(e, cudaMemcpyAsync(v.chk, chk.data(), chk.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CD_CK(e, cudaMemcpyAsync(v.chk_obs, chk_obs.data(), chk_obs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        e->chk_dirty = false;
+    }
     cdrt_tick_kernel<<<(v.n_inst * 32 + 127) / 128, 128, 0, ctx->stream>>>(v, dt_ns, do_get_path);
     RTPP_LAUNCHED(ctx);
     CD_CK(e, cudaStreamSynchronize(ctx->stream));

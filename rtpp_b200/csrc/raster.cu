@@ -24,7 +24,13 @@
 struct TileTarget {
     uint32_t *w;
     int W, H, tilesX;
+    size_t stride; // words between the planes of a batch (primitive p draws into plane inst(p))
 };
+__device__ __forceinline__ TileTarget tile_plane(const TileTarget &t, int inst) {
+    TileTarget r = t;
+    r.w = t.w + (size_t)inst * t.stride;
+    return r;
+}
 
 // set pixels [xa, xb] of row y (clipped) with atomicOr on the tile words
 __device__ __forceinline__ void tile_span(const TileTarget &t, int y, int xa, int xb) {
@@ -44,11 +50,12 @@ __device__ __forceinline__ void tile_put(const TileTarget &t, int x, int y) {
 }
 
 // one warp per circle (cx, cy, r): every lane walks the midpoint recurrence, lane q draws span q of the step
-__global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t, const int3 *__restrict__ circles, int n) {
+__global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t0, const int4 *__restrict__ circles, int n) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
-    const int3 c = circles[w];
+    const int4 c = circles[w]; // cx, cy, r, plane
     if (c.z < 0) return;
+    const TileTarget t = tile_plane(t0, c.w);
     int e = 0, dx = c.z, dy = 0, up = 1, down = 2 * c.z - 1, step = 0;
     for (; dx >= dy; dy++, step++) {
         const int q = (lane + 4 * step) & 31; // spread the four spans of consecutive steps over the lanes
@@ -63,15 +70,16 @@ __global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t, const
 
 // polygon vertices: pts[first .. first+count) ; edge k joins vertex k-1 (cyclic) to vertex k
 struct PolyDesc {
-    int first, count, ymin, ymax;
+    int first, count, ymin, ymax, inst;
 };
 
 // outline: one warp per polygon edge, lanes stride over the Bresenham points
-__global__ void __launch_bounds__(128) raster_poly_outline_kernel(TileTarget t, const int2 *__restrict__ pts, const PolyDesc *__restrict__ polys,
+__global__ void __launch_bounds__(128) raster_poly_outline_kernel(TileTarget t0, const int2 *__restrict__ pts, const PolyDesc *__restrict__ polys,
                                                                  const int2 *__restrict__ edge_of, int n_edges) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_edges) return;
     const PolyDesc pd = polys[edge_of[w].x];
+    const TileTarget t = tile_plane(t0, pd.inst);
     const int k = edge_of[w].y;
     int2 a = pts[pd.first + (k + pd.count - 1) % pd.count], b = pts[pd.first + k];
     if (b.x < a.x) {
@@ -91,11 +99,12 @@ __global__ void __launch_bounds__(128) raster_poly_outline_kernel(TileTarget t, 
 
 // fill: one thread per (polygon, row); at most kMaxPolyEdges edges per polygon
 static constexpr int kMaxPolyEdges = 64;
-__global__ void __launch_bounds__(128) raster_poly_fill_kernel(TileTarget t, const int2 *__restrict__ pts, const PolyDesc *__restrict__ polys,
+__global__ void __launch_bounds__(128) raster_poly_fill_kernel(TileTarget t0, const int2 *__restrict__ pts, const PolyDesc *__restrict__ polys,
                                                               const int2 *__restrict__ row_of, int n_rows) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const PolyDesc pd = polys[row_of[r].x];
+    const TileTarget t = tile_plane(t0, pd.inst);
     const int y = row_of[r].y;
     if (y < 0 || y >= t.H) return;
     long long xs[kMaxPolyEdges], sl[kMaxPolyEdges];
@@ -125,24 +134,31 @@ __global__ void __launch_bounds__(256) raster_merge_kernel(const uint4 *__restri
     }
 }
 
-// Draw into an arbitrary tile plane (used by the ctx planes and by the engines' map slots).
-int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t *circles, int n_circles, const int32_t *poly_xy,
-                     const int32_t *poly_sizes, int n_polys) {
+// Draw a batch of planes (n_planes tile planes `stride_words` apart): every plane is cleared
+// (DObsmap = cv::Mat::zeros, RTRRT.cpp:140), then circle c = (cx, cy, r, plane) and polygon p (poly_inst[p])
+// are drawn into their planes with one launch per primitive kind.  Used by the ctx planes, the engines'
+// map slots (one plane) and the CDRT engine (one dynamic plane per planner instance).
+int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int n_planes, int W, int H, const int32_t *circles4,
+                      int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, const int32_t *poly_inst, int n_polys) {
     const int tilesX = (W + 31) >> 5, tilesY = (H + 31) >> 5;
     const size_t words = (size_t)tilesX * tilesY * 32;
-    RTPP_CK(ctx, cudaMemsetAsync(plane, 0, words * 4, ctx->stream)); // DObsmap = cv::Mat::zeros (RTRRT.cpp:140)
-    TileTarget t{plane, W, H, tilesX};
+    if (n_planes > 1 && stride_words == words) {
+        RTPP_CK(ctx, cudaMemsetAsync(planes, 0, words * 4 * (size_t)n_planes, ctx->stream));
+    } else {
+        for (int i = 0; i < n_planes; i++) RTPP_CK(ctx, cudaMemsetAsync(planes + (size_t)i * stride_words, 0, words * 4, ctx->stream));
+    }
+    TileTarget t{planes, W, H, tilesX, stride_words};
     if (n_circles > 0) {
         void *d = nullptr;
-        int rc = rtpp_scratch(ctx, 2, (size_t)n_circles * 12, &d);
+        int rc = rtpp_scratch(ctx, 2, (size_t)n_circles * 16, &d);
         if (rc) return rc;
-        RTPP_CK(ctx, cudaMemcpyAsync(d, circles, (size_t)n_circles * 12, cudaMemcpyHostToDevice, ctx->stream));
-        raster_circles_kernel<<<(n_circles + 3) / 4, 128, 0, ctx->stream>>>(t, (const int3 *)d, n_circles);
+        RTPP_CK(ctx, cudaMemcpyAsync(d, circles4, (size_t)n_circles * 16, cudaMemcpyHostToDevice, ctx->stream));
+        raster_circles_kernel<<<(n_circles + 3) / 4, 128, 0, ctx->stream>>>(t, (const int4 *)d, n_circles);
         RTPP_LAUNCHED(ctx);
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream)); // the caller's buffer may be a temporary
     }
     if (n_polys > 0) {
         // host-side job lists (a handful of polygons with a handful of vertices each)
-        std::string buf;
         size_t npts = 0;
         for (int p = 0; p < n_polys; p++) npts += poly_sizes[p];
         std::vector<PolyDesc> polys(n_polys);
@@ -157,32 +173,41 @@ int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t
                 ymin = y < ymin ? y : ymin, ymax = y > ymax ? y : ymax;
                 edges.push_back(make_int2(p, k));
             }
-            polys[p] = PolyDesc{(int)first, cnt, ymin, ymax};
+            polys[p] = PolyDesc{(int)first, cnt, ymin, ymax, poly_inst ? poly_inst[p] : 0};
             for (int y = (ymin < 0 ? 0 : ymin); y < ymax && y < H; y++) rows.push_back(make_int2(p, y));
             first += cnt;
         }
         const size_t b_pts = npts * 8, b_pol = polys.size() * sizeof(PolyDesc), b_edg = edges.size() * 8, b_row = rows.size() * 8;
+        const size_t o_pol = (b_pts + 15) & ~(size_t)15, o_edg = (o_pol + b_pol + 15) & ~(size_t)15, o_row = (o_edg + b_edg + 15) & ~(size_t)15;
         void *d = nullptr;
-        int rc = rtpp_scratch(ctx, 3, b_pts + b_pol + b_edg + b_row + 64, &d);
+        int rc = rtpp_scratch(ctx, 3, o_row + b_row + 64, &d);
         if (rc) return rc;
         char *base = (char *)d;
         RTPP_CK(ctx, cudaMemcpyAsync(base, poly_xy, b_pts, cudaMemcpyHostToDevice, ctx->stream));
-        RTPP_CK(ctx, cudaMemcpyAsync(base + b_pts, polys.data(), b_pol, cudaMemcpyHostToDevice, ctx->stream));
-        if (b_edg) RTPP_CK(ctx, cudaMemcpyAsync(base + b_pts + b_pol, edges.data(), b_edg, cudaMemcpyHostToDevice, ctx->stream));
-        if (b_row) RTPP_CK(ctx, cudaMemcpyAsync(base + b_pts + b_pol + b_edg, rows.data(), b_row, cudaMemcpyHostToDevice, ctx->stream));
+        RTPP_CK(ctx, cudaMemcpyAsync(base + o_pol, polys.data(), b_pol, cudaMemcpyHostToDevice, ctx->stream));
+        if (b_edg) RTPP_CK(ctx, cudaMemcpyAsync(base + o_edg, edges.data(), b_edg, cudaMemcpyHostToDevice, ctx->stream));
+        if (b_row) RTPP_CK(ctx, cudaMemcpyAsync(base + o_row, rows.data(), b_row, cudaMemcpyHostToDevice, ctx->stream));
         RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors go out of scope
         const int2 *dp = (const int2 *)base;
-        const PolyDesc *dpo = (const PolyDesc *)(base + b_pts);
+        const PolyDesc *dpo = (const PolyDesc *)(base + o_pol);
         if (!edges.empty()) {
-            raster_poly_outline_kernel<<<((int)edges.size() + 3) / 4, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + b_pts + b_pol), (int)edges.size());
+            raster_poly_outline_kernel<<<((int)edges.size() + 3) / 4, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_edg), (int)edges.size());
             RTPP_LAUNCHED(ctx);
         }
         if (!rows.empty()) {
-            raster_poly_fill_kernel<<<((int)rows.size() + 127) / 128, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + b_pts + b_pol + b_edg), (int)rows.size());
+            raster_poly_fill_kernel<<<((int)rows.size() + 127) / 128, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_row), (int)rows.size());
             RTPP_LAUNCHED(ctx);
         }
     }
     return RTPP_OK;
+}
+
+// one plane; circles as (cx, cy, r) triples
+int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t *circles, int n_circles, const int32_t *poly_xy,
+                     const int32_t *poly_sizes, int n_polys) {
+    std::vector<int32_t> c4((size_t)n_circles * 4);
+    for (int i = 0; i < n_circles; i++) c4[4 * i] = circles[3 * i], c4[4 * i + 1] = circles[3 * i + 1], c4[4 * i + 2] = circles[3 * i + 2], c4[4 * i + 3] = 0;
+    return rtpp_raster_batch(ctx, plane, 0, 1, W, H, c4.data(), n_circles, poly_xy, poly_sizes, nullptr, n_polys);
 }
 
 extern "C" {
