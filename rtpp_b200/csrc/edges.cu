@@ -27,31 +27,36 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
     const int lane = threadIdx.x & 31;
     uint32_t acc = 0; // bit 0 = blocked
     int P = 1;
-    bool safe = true;
     if (valid) {
-        safe = rt_edge_safe(pl, e.x, e.y, e.z, e.w);
-        if (safe)
-            acc = rt_probe_word(pl, rt_trunc_pos(e.y), rt_trunc_pos(e.x)) | rt_probe_word(pl, rt_trunc_pos(e.w), rt_trunc_pos(e.z));
-        else
-            acc = rt_probe(pl, __float2int_rz(e.y), __float2int_rz(e.x)) | rt_probe(pl, __float2int_rz(e.w), __float2int_rz(e.z));
         P = rt_march_P(mt, rt_sqlen(e.x, e.y, e.z, e.w));
-    }
-    acc &= 1u;
-    if (!acc && P <= kShortMaxP) {
-        const float inv = rt_inv_pow2(P);
-        if (safe) {
-            float t = inv; // t_j = j/P accumulated exactly (dyadic), no int->float conversion
-#pragma unroll 4
-            for (int j = 1; j < P; j++) {
-                const float omt = __fsub_rn(1.0f, t);
+        if (rt_edge_safe(pl, e.x, e.y, e.z, e.w)) {
+            // The reference's probe set is the dyadic levels t = 1/2 | 1/4, 3/4 | odd/8 | odd/16 ... up to P
+            // (RTRRT.cpp:210-218); the verdict is their OR, so the levels are issued as straight-line groups
+            // with immediate t and 1-t (both exact): no loop counter, no t accumulation, and the first level
+            // (every edge has it: M >= 2) goes out together with the two end-point probes.
+            auto at = [&](const float t, const float omt) -> uint32_t {
                 const int x = rt_trunc_pos(__fadd_rn(__fmul_rn(e.x, t), __fmul_rn(omt, e.z)));
                 const int y = rt_trunc_pos(__fadd_rn(__fmul_rn(e.y, t), __fmul_rn(omt, e.w)));
-                acc |= rt_probe_word(pl, y, x);
-                t = __fadd_rn(t, inv);
+                return rt_probe_word(pl, y, x);
+            };
+            acc = rt_probe_word(pl, rt_trunc_pos(e.y), rt_trunc_pos(e.x)) | rt_probe_word(pl, rt_trunc_pos(e.w), rt_trunc_pos(e.z)) |
+                  at(0.5f, 0.5f);
+            if (P >= 4 && P <= kShortMaxP) {
+                acc |= at(0.25f, 0.75f) | at(0.75f, 0.25f);
+                if (P >= 8) {
+                    acc |= at(0.125f, 0.875f) | at(0.375f, 0.625f) | at(0.625f, 0.375f) | at(0.875f, 0.125f);
+                    if (P >= 16)
+                        acc |= at(0.0625f, 0.9375f) | at(0.1875f, 0.8125f) | at(0.3125f, 0.6875f) | at(0.4375f, 0.5625f) |
+                               at(0.5625f, 0.4375f) | at(0.6875f, 0.3125f) | at(0.8125f, 0.1875f) | at(0.9375f, 0.0625f);
+                }
             }
             acc &= 1u;
         } else {
-            for (int j = 1; j < P; j++) acc |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+            acc = rt_probe(pl, __float2int_rz(e.y), __float2int_rz(e.x)) | rt_probe(pl, __float2int_rz(e.w), __float2int_rz(e.z));
+            if (!acc && P <= kShortMaxP) {
+                const float inv = rt_inv_pow2(P);
+                for (int j = 1; j < P; j++) acc |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+            }
         }
     }
     unsigned longmask = __ballot_sync(full, !acc && P > kShortMaxP);
@@ -76,17 +81,21 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
     return __ballot_sync(full, acc != 0);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, MarchThresholds mt,
                       uint32_t *__restrict__ out_bits) {
     const int lane = threadIdx.x & 31;
     const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t nwords = (n + 31) >> 5;
+    // software pipeline: the next 16-byte edge of this lane is in flight while the current one is marched
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp0 < nwords && (warp0 << 5) + lane < n) nxt = ld_stream_f4(edges + (warp0 << 5) + lane);
     for (size_t w = warp0; w < nwords; w += nwarps) {
         const size_t i = (w << 5) + lane;
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) e = ld_stream_f4(edges + i);
+        const float4 e = nxt;
+        const size_t in = ((w + nwarps) << 5) + lane;
+        if (in < n) nxt = ld_stream_f4(edges + in);
         const unsigned bits = warp_edges_verdict(pl, e, i < n, mt);
         if (lane == 0) out_bits[w] = bits;
     }
@@ -287,9 +296,13 @@ void rtpp_march_thresholds(int divisor, MarchThresholds *out) {
 }
 
 // grid sizing: a multiple of the SM count, enough resident warps to cover L2 latency
-static int edge_grid(rtpp_ctx *ctx, size_t n, int per_block) {
+// Persistent grid-stride kernels: exactly one resident wave (blocks per SM from the occupancy
+// calculator, so a register-count change can never leave a half-empty second wave).
+template <class K> static int edge_grid(rtpp_ctx *ctx, K kernel, size_t n, int per_block) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, per_block, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     size_t need = (n + per_block - 1) / per_block;
-    size_t cap = (size_t)ctx->sm_count * 8;
+    size_t cap = (size_t)ctx->sm_count * per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
@@ -305,7 +318,7 @@ int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divis
     if (n == 0) return RTPP_OK;
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
-    edge_check_f32_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits);
+    edge_check_f32_kernel<<<edge_grid(ctx, edge_check_f32_kernel, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }
@@ -323,7 +336,7 @@ int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32
     if (n_edges) *n_edges = ne;
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
-    edge_check_resident_kernel<<<edge_grid(ctx, ne, 256), 256, 0, ctx->stream>>>(pv, s->xy, s->sxy, s->cp, s->knn_pos, s->n, s->knn_k, mt, d_bits);
+    edge_check_resident_kernel<<<edge_grid(ctx, edge_check_resident_kernel, ne, 256), 256, 0, ctx->stream>>>(pv, s->xy, s->sxy, s->cp, s->knn_pos, s->n, s->knn_k, mt, d_bits);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }
@@ -361,7 +374,7 @@ int rtpp_edges_check_f64_dev(rtpp_ctx *ctx, const double *d_xyxy, size_t n, int 
     int rc = rtpp_select_plane(ctx, plane_mask, &pv);
     if (rc) return rc;
     if (n == 0) return RTPP_OK;
-    edge_check_f64_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const double4 *)d_xyxy, n, (float)divisor, d_bits);
+    edge_check_f64_kernel<<<edge_grid(ctx, edge_check_f64_kernel, n, 256), 256, 0, ctx->stream>>>(pv, (const double4 *)d_xyxy, n, (float)divisor, d_bits);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }
@@ -372,7 +385,7 @@ int rtpp_edges_first_hit_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, uint3
     int rc = rtpp_select_plane(ctx, 3, &pv);
     if (rc) return rc;
     if (n == 0) return RTPP_OK;
-    edge_first_hit_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, d_bits, (float2 *)d_pstart);
+    edge_first_hit_kernel<<<edge_grid(ctx, edge_first_hit_kernel, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, d_bits, (float2 *)d_pstart);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }
@@ -424,7 +437,7 @@ int rtpp_dist(rtpp_ctx *ctx, const float *xyxy, size_t n, float *out) {
     rc = rtpp_scratch(ctx, 1, n * 4, &d_o);
     if (rc) return rc;
     RTPP_CK(ctx, cudaMemcpyAsync(d_e, xyxy, n * 16, cudaMemcpyHostToDevice, ctx->stream));
-    dist_kernel<<<edge_grid(ctx, n, 256), 256, 0, ctx->stream>>>((const float4 *)d_e, n, (float *)d_o);
+    dist_kernel<<<edge_grid(ctx, dist_kernel, n, 256), 256, 0, ctx->stream>>>((const float4 *)d_e, n, (float *)d_o);
     RTPP_LAUNCHED(ctx);
     RTPP_CK(ctx, cudaMemcpyAsync(out, d_o, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
