@@ -16,6 +16,8 @@
 //
 // Roofline: algorithmic bytes per edge = 16 + 4*n_probes + 1/8; the edge list streams
 // from HBM, the bit-plane (0.9-2 MB) is L2/L1 resident.
+#include <stdlib.h>
+
 #include "nodes.cuh"
 
 static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 32 -> warp marches
@@ -81,21 +83,30 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
     return __ballot_sync(full, acc != 0);
 }
 
+// chunk_iters == 0: persistent grid-stride (one resident wave); > 0: block b owns the 8*chunk_iters
+// consecutive 32-edge words starting at b*8*chunk_iters (warps interleaved, so each step of the block
+// reads 4 KB contiguous) and the hardware block scheduler balances the tail.
 __global__ void __launch_bounds__(256, 8)
 edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, MarchThresholds mt,
-                      uint32_t *__restrict__ out_bits) {
+                      uint32_t *__restrict__ out_bits, int chunk_iters) {
     const int lane = threadIdx.x & 31;
-    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t nwords = (n + 31) >> 5;
+    size_t w, stride, end;
+    if (chunk_iters > 0) {
+        const size_t base = (size_t)blockIdx.x * (blockDim.x >> 5) * chunk_iters;
+        w = base + (threadIdx.x >> 5), stride = blockDim.x >> 5;
+        end = min(nwords, base + stride * chunk_iters);
+    } else {
+        w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, stride = ((size_t)gridDim.x * blockDim.x) >> 5, end = nwords;
+    }
     // software pipeline: the next 16-byte edge of this lane is in flight while the current one is marched
     float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp0 < nwords && (warp0 << 5) + lane < n) nxt = ld_stream_f4(edges + (warp0 << 5) + lane);
-    for (size_t w = warp0; w < nwords; w += nwarps) {
+    if (w < end && (w << 5) + lane < n) nxt = ld_stream_f4(edges + (w << 5) + lane);
+    for (; w < end; w += stride) {
         const size_t i = (w << 5) + lane;
         const float4 e = nxt;
-        const size_t in = ((w + nwarps) << 5) + lane;
-        if (in < n) nxt = ld_stream_f4(edges + in);
+        const size_t in = ((w + stride) << 5) + lane;
+        if (w + stride < end && in < n) nxt = ld_stream_f4(edges + in);
         const unsigned bits = warp_edges_verdict(pl, e, i < n, mt);
         if (lane == 0) out_bits[w] = bits;
     }
@@ -226,36 +237,49 @@ edge_first_hit_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, 
 // (parent(e+1) -> e+1) of UpdateTree (AMRRT.cpp:185-199), edge n-1 + i*k + j is the rewire edge
 // (node i -> knn[i][j]) of RewireRoot (AMRRT.cpp:496-500) — so a tick moves no edge list at all:
 // 4 index bytes + two 8-byte coordinate gathers (L2-resident node table) per edge.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 edge_check_resident_kernel(PlaneView pl, const float2 *__restrict__ xy, const float2 *__restrict__ sxy, const cpword *__restrict__ cp,
-                           const int *__restrict__ knn_pos, int n, int k, MarchThresholds mt, uint32_t *__restrict__ out_bits) {
+                           const int *__restrict__ knn_pos, int n, int k, MarchThresholds mt, uint32_t *__restrict__ out_bits,
+                           int chunk_iters) {
     const int lane = threadIdx.x & 31;
     const size_t n_tree = (size_t)(n - 1), n_edges = n_tree + (size_t)n * k;
-    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t nwords = (n_edges + 31) >> 5;
     const bool small = n_edges < 0xffffffffull; // 32-bit row arithmetic (always, up to 1.6e8 nodes at k = 25)
-    for (size_t w = warp0; w < nwords; w += nwarps) {
-        const size_t i = (w << 5) + lane;
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool valid = false;
-        if (i < n_edges) {
-            if (i < n_tree) { // tree edge (parent -> child)
+    const size_t base = (size_t)blockIdx.x * (blockDim.x >> 5) * chunk_iters;
+    const size_t stride = blockDim.x >> 5, end = min(nwords, base + stride * chunk_iters);
+    size_t w = base + (threadIdx.x >> 5);
+    // Two-stage software pipeline over the block's chunk: the node ids of word w+2 and the coordinates of
+    // word w+1 are in flight while word w is marched (the id -> coordinate gather is a dependent pair of
+    // L2 accesses; issued a full step apart, neither stalls the march).
+    auto load_ids = [&](size_t ww) -> int2 { // (a, b): b >= 0 indexes xy (tree edge), b <= -2 encodes sorted position ~b... -1 = none
+        const size_t i = (ww << 5) + lane;
+        int2 r = make_int2(-1, -1);
+        if (ww < end && i < n_edges) {
+            if (i < n_tree) {
                 const int b = (int)i + 1, a = cp_parent(cp[b]);
-                if (a >= 0) {
-                    const float2 pa = xy[a], pb = xy[b];
-                    e = make_float4(pa.x, pa.y, pb.x, pb.y), valid = true;
-                }
-            } else { // rewire edge (node a -> its j-th neighbour); the neighbour is fetched by sorted position
-                const size_t r = i - n_tree;
-                const int a = small ? (int)((unsigned)r / (unsigned)k) : (int)(r / (unsigned)k);
-                const int bp = knn_pos[r];
-                if (bp >= 0) {
-                    const float2 pa = xy[a], pb = sxy[bp];
-                    e = make_float4(pa.x, pa.y, pb.x, pb.y), valid = true;
-                }
+                if (a >= 0) r = make_int2(a, b);
+            } else {
+                const size_t q = i - n_tree;
+                const int a = small ? (int)((unsigned)q / (unsigned)k) : (int)(q / (unsigned)k);
+                const int bp = knn_pos[q];
+                if (bp >= 0) r = make_int2(a, -2 - bp);
             }
         }
+        return r;
+    };
+    auto load_xy = [&](int2 id) -> float4 {
+        if (id.x < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float2 pa = xy[id.x], pb = id.y >= 0 ? xy[id.y] : sxy[-2 - id.y];
+        return make_float4(pa.x, pa.y, pb.x, pb.y);
+    };
+    int2 id1 = load_ids(w), id2 = load_ids(w + stride);
+    float4 e1 = load_xy(id1);
+    bool v1 = id1.x >= 0;
+    for (; w < end; w += stride) {
+        const float4 e = e1;
+        const bool valid = v1;
+        e1 = load_xy(id2), v1 = id2.x >= 0;
+        id2 = load_ids(w + 2 * stride);
         const unsigned bits = warp_edges_verdict(pl, e, valid, mt);
         if (lane == 0) out_bits[w] = bits;
     }
@@ -318,7 +342,15 @@ int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divis
     if (n == 0) return RTPP_OK;
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
-    edge_check_f32_kernel<<<edge_grid(ctx, edge_check_f32_kernel, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits);
+    // blocks of 8 warps x 8 steps (32 KB of the edge list each): small enough that the concurrently running blocks
+    // do not fall into step on the same HBM channels (chunks >= 16 steps measurably do), and the hardware block
+    // scheduler evens out the tail that a one-wave persistent grid leaves (0.186 -> 0.170 ms on the C4 step)
+    static int chunk = getenv("RTPP_K1_CHUNK") ? atoi(getenv("RTPP_K1_CHUNK")) : 8;
+    if (chunk > 0) {
+        const size_t per_block = (size_t)8 * chunk * 32;
+        edge_check_f32_kernel<<<(unsigned)((n + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits, chunk);
+    } else
+        edge_check_f32_kernel<<<edge_grid(ctx, edge_check_f32_kernel, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits, 0);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }
@@ -336,7 +368,10 @@ int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32
     if (n_edges) *n_edges = ne;
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
-    edge_check_resident_kernel<<<edge_grid(ctx, edge_check_resident_kernel, ne, 256), 256, 0, ctx->stream>>>(pv, s->xy, s->sxy, s->cp, s->knn_pos, s->n, s->knn_k, mt, d_bits);
+    const int chunk = 8;
+    const size_t per_block = (size_t)8 * chunk * 32;
+    edge_check_resident_kernel<<<(unsigned)((ne + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, s->xy, s->sxy, s->cp, s->knn_pos, s->n, s->knn_k,
+                                                                                                      mt, d_bits, chunk);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }

@@ -49,23 +49,29 @@ __device__ __forceinline__ void tile_put(const TileTarget &t, int x, int y) {
     atomicOr(&t.w[((((size_t)(y >> 5) * t.tilesX + (x >> 5)) << 5) + (y & 31))], 1u << (x & 31));
 }
 
-// one warp per circle (cx, cy, r): every lane walks the midpoint recurrence, lane q draws span q of the step
-__global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t0, const int4 *__restrict__ circles, int n) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n) return;
-    const int4 c = circles[w]; // cx, cy, r, plane
-    if (c.z < 0) return;
+// Filled circle = cv::circle(FILLED): the midpoint recurrence (err += 2*dy+1; if err > 0: err -= 2*dx-1, dx--)
+// keeps err = dx^2 + dy^2 - r^2, so the half-width drawn at step dy is the closed form
+// dx(dy) = floor(sqrt(r^2 - dy^2)) while dx >= dy (one decrement per step suffices in the first octant).
+// One thread per (circle, step): its four clipped spans.  step_of[j] = (circle, dy).
+__device__ __forceinline__ int isqrt_floor(int v) {
+    int s = (int)sqrtf((float)v);
+    while (s * s > v) s--;
+    while ((s + 1) * (s + 1) <= v) s++;
+    return s;
+}
+__global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t0, const int4 *__restrict__ circles, const int2 *__restrict__ step_of,
+                                                            int n_steps) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_steps) return;
+    const int4 c = circles[step_of[j].x]; // cx, cy, r, plane
+    const int dy = step_of[j].y;
+    const int dx = isqrt_floor(c.z * c.z - dy * dy);
+    if (dx < dy) return;
     const TileTarget t = tile_plane(t0, c.w);
-    int e = 0, dx = c.z, dy = 0, up = 1, down = 2 * c.z - 1, step = 0;
-    for (; dx >= dy; dy++, step++) {
-        const int q = (lane + 4 * step) & 31; // spread the four spans of consecutive steps over the lanes
-        if (q == 0) tile_span(t, c.y - dy, c.x - dx, c.x + dx);
-        if (q == 1) tile_span(t, c.y + dy, c.x - dx, c.x + dx);
-        if (q == 2) tile_span(t, c.y - dx, c.x - dy, c.x + dy);
-        if (q == 3) tile_span(t, c.y + dx, c.x - dy, c.x + dy);
-        e += up, up += 2;
-        if (e > 0) e -= down, dx--, down -= 2;
-    }
+    tile_span(t, c.y - dy, c.x - dx, c.x + dx);
+    tile_span(t, c.y + dy, c.x - dx, c.x + dx);
+    tile_span(t, c.y - dx, c.x - dy, c.x + dy);
+    tile_span(t, c.y + dx, c.x - dy, c.x + dy);
 }
 
 // polygon vertices: pts[first .. first+count) ; edge k joins vertex k-1 (cyclic) to vertex k
@@ -149,13 +155,24 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
     }
     TileTarget t{planes, W, H, tilesX, stride_words};
     if (n_circles > 0) {
-        void *d = nullptr;
-        int rc = rtpp_scratch(ctx, 2, (size_t)n_circles * 16, &d);
-        if (rc) return rc;
-        RTPP_CK(ctx, cudaMemcpyAsync(d, circles4, (size_t)n_circles * 16, cudaMemcpyHostToDevice, ctx->stream));
-        raster_circles_kernel<<<(n_circles + 3) / 4, 128, 0, ctx->stream>>>(t, (const int4 *)d, n_circles);
-        RTPP_LAUNCHED(ctx);
-        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream)); // the caller's buffer may be a temporary
+        std::vector<int2> steps; // every dy with dx(dy) >= dy lies in [0, r*0.7072]
+        for (int c = 0; c < n_circles; c++) {
+            const int r = circles4[4 * c + 2];
+            if (r < 0 || r > 23000) continue; // r^2 must fit the exact integer arithmetic of the kernel
+            for (int dy = 0; dy <= (int)(r * 0.70711) + 1; dy++) steps.push_back(make_int2(c, dy));
+        }
+        if (!steps.empty()) {
+            const size_t b_c = ((size_t)n_circles * 16 + 15) & ~(size_t)15;
+            void *d = nullptr;
+            int rc = rtpp_scratch(ctx, 2, b_c + steps.size() * 8, &d);
+            if (rc) return rc;
+            RTPP_CK(ctx, cudaMemcpyAsync(d, circles4, (size_t)n_circles * 16, cudaMemcpyHostToDevice, ctx->stream));
+            RTPP_CK(ctx, cudaMemcpyAsync((char *)d + b_c, steps.data(), steps.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            raster_circles_kernel<<<((int)steps.size() + 127) / 128, 128, 0, ctx->stream>>>(t, (const int4 *)d, (const int2 *)((char *)d + b_c),
+                                                                                           (int)steps.size());
+            RTPP_LAUNCHED(ctx);
+            RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors (and the caller's buffer) may be temporaries
+        }
     }
     if (n_polys > 0) {
         // host-side job lists (a handful of polygons with a handful of vertices each)
