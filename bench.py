@@ -464,7 +464,19 @@ def measure_extras(wl, torch):
     out["rewire_sweeps"] = sweeps
     out.update(measure_replanning(ctx))
     out.update(measure_fmt(ctx))
+    out.update(measure_cdrt(ctx))
     return out
+
+
+def measure_cdrt(ctx):
+    """BASELINE configs[1]: CDRT-RRT* on bundled GAME0 with its four moving obstacles, continuous replanning on
+    virtual time (tools/cdrt_bench.py): tick latency of one planner and the throughput of 1024 planners (one warp
+    each) against the CPU port on the host threads; states compared bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import cdrt_bench
+    from oracle import loader as orc
+
+    return {"cdrt": {"single": cdrt_bench.single(ctx, orc), "sweep": cdrt_bench.sweep(ctx, orc, n_inst=1024, threads=os.cpu_count() or 1)}}
 
 
 def measure_fmt(ctx, samples=100_000, iters=20_000):

@@ -31,6 +31,8 @@ struct rtpp_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // read-backs that overlap the next kernel slice
+    cudaEvent_t slice_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     long long launches = 0;
     std::string err;
 

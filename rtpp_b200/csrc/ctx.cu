@@ -43,6 +43,12 @@ int rtpp_create(int device, rtpp_ctx **out) {
         return RTPP_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->copy_stream = nullptr;
+    for (int i = 0; i < 5 && ctx->copy_stream; i++)
+        if (cudaEventCreateWithFlags(&ctx->slice_done[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(ctx->copy_stream);
+            ctx->copy_stream = nullptr;
+        }
     *out = ctx;
     return RTPP_OK;
 }
@@ -54,6 +60,12 @@ int rtpp_destroy(rtpp_ctx *ctx) {
     rtpp_nodes_destroy(ctx);
     for (int i = 0; i < 3; i++) cudaFree(ctx->plane[i]);
     for (int i = 0; i < 4; i++) cudaFree(ctx->scratch[i]);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (int i = 0; i < 5; i++)
+            if (ctx->slice_done[i]) cudaEventDestroy(ctx->slice_done[i]);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return RTPP_OK;

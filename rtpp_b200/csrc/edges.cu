@@ -18,6 +18,8 @@
 // from HBM, the bit-plane (0.9-2 MB) is L2/L1 resident.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "nodes.cuh"
 
 static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 32 -> warp marches
@@ -83,33 +85,43 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
     return __ballot_sync(full, acc != 0);
 }
 
-// chunk_iters == 0: persistent grid-stride (one resident wave); > 0: block b owns the 8*chunk_iters
-// consecutive 32-edge words starting at b*8*chunk_iters (warps interleaved, so each step of the block
-// reads 4 KB contiguous) and the hardware block scheduler balances the tail.
+// Block b owns the 8*chunk_iters (<= 64) consecutive 32-edge words starting at b*8*chunk_iters; its 8 warps are
+// interleaved over them, so every step of the block reads 4 KB contiguous, and the hardware block scheduler
+// balances the tail (a one-wave persistent grid measured 0.186 ms on the C4 step, this 0.170 ms; chunks of >= 16
+// steps put the concurrently running blocks in step on the same HBM channels and are measurably slower).
+// The block stages its verdict words and writes them as full lines at the end (256 B per block instead of 64
+// scattered 4-byte stores), which also makes a mapped host buffer a cheap destination.
+// kSentinel: entries whose first coordinate is NaN stand for "no edge" (verdict 0): the materialised tick list.
+template <bool kSentinel>
 __global__ void __launch_bounds__(256, 8)
 edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, MarchThresholds mt,
                       uint32_t *__restrict__ out_bits, int chunk_iters) {
+    __shared__ uint32_t stage[64];
     const int lane = threadIdx.x & 31;
-    const size_t nwords = (n + 31) >> 5;
-    size_t w, stride, end;
-    if (chunk_iters > 0) {
-        const size_t base = (size_t)blockIdx.x * (blockDim.x >> 5) * chunk_iters;
-        w = base + (threadIdx.x >> 5), stride = blockDim.x >> 5;
-        end = min(nwords, base + stride * chunk_iters);
-    } else {
-        w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, stride = ((size_t)gridDim.x * blockDim.x) >> 5, end = nwords;
+    const size_t base = (size_t)blockIdx.x * 8 * chunk_iters; // first word of the block
+    const int n_rel = (int)min((size_t)(256 * chunk_iters), n - (base << 5)); // edges of this block
+    const float4 *ep = edges + (base << 5) + threadIdx.x;
+    // software pipeline through shared memory: the next 16-byte edge of this lane is fetched with cp.async (L2 ->
+    // shared, no L1 allocation, no registers held across the march) while the current one is marched; each thread
+    // only ever reads the slot it filled itself, so cp.async.wait_group is the only synchronisation
+    __shared__ float4 ebuf[2][256];
+    if ((int)threadIdx.x < n_rel)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(&ebuf[0][threadIdx.x])), "l"(ep) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int rel = threadIdx.x; rel - lane < n_rel; rel += 256) { // rel = index of this lane's edge inside the block
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rel < n_rel) e = ebuf[(rel >> 8) & 1][threadIdx.x];
+        ep += 256;
+        if (rel + 256 < n_rel)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(&ebuf[((rel >> 8) & 1) ^ 1][threadIdx.x])), "l"(ep)
+                         : "memory");
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        const unsigned bits = warp_edges_verdict(pl, e, rel < n_rel && (!kSentinel || e.x == e.x), mt);
+        if (lane == 0) stage[rel >> 5] = bits;
     }
-    // software pipeline: the next 16-byte edge of this lane is in flight while the current one is marched
-    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (w < end && (w << 5) + lane < n) nxt = ld_stream_f4(edges + (w << 5) + lane);
-    for (; w < end; w += stride) {
-        const size_t i = (w << 5) + lane;
-        const float4 e = nxt;
-        const size_t in = ((w + stride) << 5) + lane;
-        if (w + stride < end && in < n) nxt = ld_stream_f4(edges + in);
-        const unsigned bits = warp_edges_verdict(pl, e, i < n, mt);
-        if (lane == 0) out_bits[w] = bits;
-    }
+    __syncthreads();
+    if ((int)(threadIdx.x << 5) < n_rel) out_bits[base + threadIdx.x] = stage[threadIdx.x];
 }
 
 // E5b: binary64 end points, binary32 interpolation parameter (CDRT.cpp:586-600).
@@ -285,6 +297,34 @@ edge_check_resident_kernel(PlaneView pl, const float2 *__restrict__ xy, const fl
     }
 }
 
+// The tick's edge list materialised in HBM (16 B/edge, streamed at the K1 rate instead of gathered edge by edge):
+// the node -> k-NN part only changes when the table is rebuilt, the tree part (parent -> child) is refreshed per tick.
+__global__ void __launch_bounds__(256) edge_list_fill_rewire_kernel(const float2 *__restrict__ xy, const float2 *__restrict__ sxy,
+                                                                    const int *__restrict__ knn_pos, int n, int k, float4 *__restrict__ out) {
+    const size_t m = (size_t)n * k;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (size_t)gridDim.x * blockDim.x) {
+        const int a = (int)(r / (unsigned)k), bp = knn_pos[r];
+        float4 e = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        if (bp >= 0) {
+            const float2 pa = xy[a], pb = sxy[bp];
+            e = make_float4(pa.x, pa.y, pb.x, pb.y);
+        }
+        out[r] = e;
+    }
+}
+__global__ void __launch_bounds__(256) edge_list_fill_tree_kernel(const float2 *__restrict__ xy, const cpword *__restrict__ cp, int n,
+                                                                  float4 *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
+        const int b = i + 1, a = cp_parent(cp[b]);
+        float4 e = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        if (a >= 0) {
+            const float2 pa = xy[a], pb = xy[b];
+            e = make_float4(pa.x, pa.y, pb.x, pb.y);
+        }
+        out[i] = e;
+    }
+}
+
 __global__ void __launch_bounds__(256) dist_kernel(const float4 *__restrict__ e, size_t n, float *__restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float4 v = e[i];
@@ -342,21 +382,15 @@ int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divis
     if (n == 0) return RTPP_OK;
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
-    // blocks of 8 warps x 8 steps (32 KB of the edge list each): small enough that the concurrently running blocks
-    // do not fall into step on the same HBM channels (chunks >= 16 steps measurably do), and the hardware block
-    // scheduler evens out the tail that a one-wave persistent grid leaves (0.186 -> 0.170 ms on the C4 step)
-    static int chunk = getenv("RTPP_K1_CHUNK") ? atoi(getenv("RTPP_K1_CHUNK")) : 8;
-    if (chunk > 0) {
-        const size_t per_block = (size_t)8 * chunk * 32;
-        edge_check_f32_kernel<<<(unsigned)((n + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits, chunk);
-    } else
-        edge_check_f32_kernel<<<edge_grid(ctx, edge_check_f32_kernel, n, 256), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits, 0);
+    static int chunk = getenv("RTPP_K1_CHUNK") ? std::max(1, std::min(8, atoi(getenv("RTPP_K1_CHUNK")))) : 8;
+    const size_t per_block = (size_t)8 * chunk * 32;
+    edge_check_f32_kernel<false><<<(unsigned)((n + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits, chunk);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }
 
-int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_bits, size_t *n_edges) {
-    if (!ctx || !d_bits) return RTPP_ERR_INVALID;
+// The tick's kernels; with h_bits != NULL the verdict words are also copied to that (pageable) host buffer.
+static int tick_edges_run(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_bits, size_t *n_edges, uint32_t *h_bits) {
     NodeStore *s = ctx->nodes;
     if (!s || !s->knn_table) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_knn_table_build has not been called");
     if (s->knn_n != s->n || s->n_sorted != s->n) RTPP_FAIL(ctx, RTPP_ERR_STATE, "nodes were appended after rtpp_knn_table_build");
@@ -364,16 +398,53 @@ int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32
     PlaneView pv;
     int rc = rtpp_select_plane(ctx, plane_mask, &pv);
     if (rc) return rc;
-    const size_t ne = (size_t)(s->n - 1) + (size_t)s->n * s->knn_k;
+    const size_t ne = (size_t)(s->n - 1) + (size_t)s->n * s->knn_k, nwords = (ne + 31) / 32;
     if (n_edges) *n_edges = ne;
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
     const int chunk = 8;
     const size_t per_block = (size_t)8 * chunk * 32;
-    edge_check_resident_kernel<<<(unsigned)((ne + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, s->xy, s->sxy, s->cp, s->knn_pos, s->n, s->knn_k,
-                                                                                                      mt, d_bits, chunk);
+    // Large ticks stream a materialised edge list (16 B/edge at the K1 rate beats one gather per edge); it costs
+    // 16 B/edge of HBM, so small ticks — and any tick whose list cannot be allocated — use the gathering kernel.
+    bool use_list = ne >= ((size_t)1 << 20);
+    if (use_list && s->edge_list_cap < ne) {
+        if (s->edge_list) {
+            RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(s->edge_list);
+        }
+        s->edge_list = nullptr, s->edge_list_cap = 0, s->edge_list_n = -1;
+        const size_t want = (size_t)(s->capacity - 1) + s->capacity * s->knn_k;
+        if (cudaMalloc(&s->edge_list, want * sizeof(float4)) == cudaSuccess) s->edge_list_cap = want;
+        else {
+            (void)cudaGetLastError();
+            use_list = false;
+        }
+    }
+    if (!use_list) {
+        edge_check_resident_kernel<<<(unsigned)((ne + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, s->xy, s->sxy, s->cp, s->knn_pos, s->n,
+                                                                                                          s->knn_k, mt, d_bits, chunk);
+        RTPP_LAUNCHED(ctx);
+        if (h_bits) RTPP_CK(ctx, cudaMemcpyAsync(h_bits, d_bits, nwords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        return RTPP_OK;
+    }
+    if (s->edge_list_n != s->n) {
+        edge_list_fill_rewire_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(s->xy, s->sxy, s->knn_pos, s->n, s->knn_k, s->edge_list + (s->n - 1));
+        RTPP_LAUNCHED(ctx);
+        s->edge_list_n = s->n;
+    }
+    if (s->n > 1) {
+        edge_list_fill_tree_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(s->xy, s->cp, s->n, s->edge_list);
+        RTPP_LAUNCHED(ctx);
+    }
+    edge_check_f32_kernel<true><<<(unsigned)((ne + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, s->edge_list, ne, mt, d_bits, chunk);
     RTPP_LAUNCHED(ctx);
+    if (h_bits) RTPP_CK(ctx, cudaMemcpyAsync(h_bits, d_bits, nwords * 4, cudaMemcpyDeviceToHost, ctx->stream));
     return RTPP_OK;
+}
+
+int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_bits, size_t *n_edges) {
+    if (!ctx || !d_bits) return RTPP_ERR_INVALID;
+    return tick_edges_run(ctx, divisor, plane_mask, d_bits, n_edges, nullptr);
 }
 
 // One tick through host buffers: new dynamic plane in (NULL = unchanged), verdict words out.
@@ -392,12 +463,19 @@ int rtpp_tick_edges_check(rtpp_ctx *ctx, const uint8_t *dynamic_plane, int divis
         if (rc) return rc;
     }
     const size_t ne = (size_t)(s->n - 1) + (size_t)s->n * s->knn_k, nwords = (ne + 31) / 32;
-    void *d_b = nullptr;
-    rc = rtpp_scratch(ctx, 1, nwords * 4, &d_b);
+    // A pinned (page-locked, mapped) result buffer is written by the kernel itself, one 256-byte burst per block as
+    // the blocks retire, so the read-back rides under the march instead of following it (3 MB per 26 M-edge tick).
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, blocked_bits) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        rc = tick_edges_run(ctx, divisor, plane_mask, (uint32_t *)at.devicePointer, n_edges, nullptr);
+    } else {
+        (void)cudaGetLastError();
+        void *d_b = nullptr;
+        rc = rtpp_scratch(ctx, 1, nwords * 4, &d_b);
+        if (rc) return rc;
+        rc = tick_edges_run(ctx, divisor, plane_mask, (uint32_t *)d_b, n_edges, blocked_bits);
+    }
     if (rc) return rc;
-    rc = rtpp_tick_edges_check_dev(ctx, divisor, plane_mask, (uint32_t *)d_b, n_edges);
-    if (rc) return rc;
-    RTPP_CK(ctx, cudaMemcpyAsync(blocked_bits, d_b, nwords * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
     return RTPP_OK;
 }

@@ -45,6 +45,9 @@ struct NodeStore {
     int knn_k = 0, knn_n = 0;
     int *knn_pos = nullptr;     // the same table in cell-sorted positions (coherent coordinate gathers)
     int *pos_of = nullptr;      // node id -> cell-sorted position
+    float4 *edge_list = nullptr; // materialised tick edge list (tree edges, then node -> k-NN edges), NaN = no edge
+    size_t edge_list_cap = 0;
+    int edge_list_n = -1;       // node count the node -> k-NN part was built for (-1 = stale)
 };
 
 int rtpp_nodes_build_internal(rtpp_ctx *ctx);

@@ -166,12 +166,13 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
             void *d = nullptr;
             int rc = rtpp_scratch(ctx, 2, b_c + steps.size() * 8, &d);
             if (rc) return rc;
-            RTPP_CK(ctx, cudaMemcpyAsync(d, circles4, (size_t)n_circles * 16, cudaMemcpyHostToDevice, ctx->stream));
+            const std::vector<int32_t> c_stage(circles4, circles4 + (size_t)n_circles * 4); // the caller's buffer may be pinned
+            RTPP_CK(ctx, cudaMemcpyAsync(d, c_stage.data(), (size_t)n_circles * 16, cudaMemcpyHostToDevice, ctx->stream));
             RTPP_CK(ctx, cudaMemcpyAsync((char *)d + b_c, steps.data(), steps.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
             raster_circles_kernel<<<((int)steps.size() + 127) / 128, 128, 0, ctx->stream>>>(t, (const int4 *)d, (const int2 *)((char *)d + b_c),
                                                                                            (int)steps.size());
             RTPP_LAUNCHED(ctx);
-            RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors (and the caller's buffer) may be temporaries
+            // no synchronisation: every source above is pageable host memory, which cudaMemcpyAsync stages before it returns
         }
     }
     if (n_polys > 0) {
@@ -200,11 +201,12 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
         int rc = rtpp_scratch(ctx, 3, o_row + b_row + 64, &d);
         if (rc) return rc;
         char *base = (char *)d;
-        RTPP_CK(ctx, cudaMemcpyAsync(base, poly_xy, b_pts, cudaMemcpyHostToDevice, ctx->stream));
+        const std::vector<int32_t> p_stage(poly_xy, poly_xy + npts * 2);
+        RTPP_CK(ctx, cudaMemcpyAsync(base, p_stage.data(), b_pts, cudaMemcpyHostToDevice, ctx->stream));
         RTPP_CK(ctx, cudaMemcpyAsync(base + o_pol, polys.data(), b_pol, cudaMemcpyHostToDevice, ctx->stream));
         if (b_edg) RTPP_CK(ctx, cudaMemcpyAsync(base + o_edg, edges.data(), b_edg, cudaMemcpyHostToDevice, ctx->stream));
         if (b_row) RTPP_CK(ctx, cudaMemcpyAsync(base + o_row, rows.data(), b_row, cudaMemcpyHostToDevice, ctx->stream));
-        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors go out of scope
+        // (pageable sources are staged by cudaMemcpyAsync before it returns, so the vectors may go out of scope)
         const int2 *dp = (const int2 *)base;
         const PolyDesc *dpo = (const PolyDesc *)(base + o_pol);
         if (!edges.empty()) {

@@ -94,16 +94,18 @@ def test_edges_other_maps(ctx, oracle, name):
         assert np.array_equal(got, oracle.edges_check(S, None, e, divisor, 1, nthreads=8))
 
 
-def test_tick_edges_check_equals_explicit_list(ctx, oracle):
+@pytest.mark.parametrize("n", [20_000, 45_000])
+def test_tick_edges_check_equals_explicit_list(ctx, oracle, n):
     """The tick-level call over the resident tree (parents + k-NN table) returns, edge for edge, the
-    verdicts of the explicit end-point list it stands for, and of the oracle."""
+    verdicts of the explicit end-point list it stands for, and of the oracle.  n = 20 000 takes the gathering
+    kernel, n = 45 000 (>= 2^20 edges) the materialised edge list, twice, with re-parented nodes in between."""
     S = oracle.load_map("MESS6")
     H, W = S.shape
     rng = np.random.default_rng(31)
     D = dyn_plane(S.shape, rng, n_blobs=6)
     ctx.map_set_plane(1, S)
     ctx.map_clear_plane(2)
-    n, k = 20_000, 25
+    k = 25
     xy = (rng.random((n, 2), dtype=np.float32) * np.array([W, H], np.float32)).astype(np.float32)
     ctx.nodes_reset(4, n, W, H)
     ctx.nodes_append(xy)
@@ -119,3 +121,14 @@ def test_tick_edges_check_equals_explicit_list(ctx, oracle):
     assert len(got) == len(e)
     assert np.array_equal(got, ctx.edges_check(e, 2, 3))
     assert np.array_equal(got, oracle.edges_check(S, D, e, 2, 3, nthreads=8))
+    # a second tick after rewires: the tree part of the list follows the parents
+    par2 = rng.integers(0, n, n).astype(np.int32)
+    par2[0] = -1
+    par2[5] = -1  # a detached node: "no edge" -> verdict 0
+    ctx.tree_set(par2, np.zeros(n, np.float32), np.zeros(n, np.uint8))
+    got2 = ctx.tick_edges_check(None, 2, 3)
+    e2 = e.copy()
+    e2[: n - 1] = np.concatenate([xy[par2[1:]], xy[1:]], 1)
+    want2 = oracle.edges_check(S, D, e2, 2, 3, nthreads=8)
+    want2[4] = 0
+    assert np.array_equal(got2, want2)
