@@ -288,6 +288,8 @@ RTPP_API int rtpp_cdrt_add_obstacle(rtpp_cdrt_engine *e, int inst, int num, int 
 RTPP_API int rtpp_cdrt_del_obstacle(rtpp_cdrt_engine *e, int inst, int num);
 RTPP_API int rtpp_cdrt_move_obstacle(rtpp_cdrt_engine *e, int inst, int num, double x, double y, double angle);
 RTPP_API int rtpp_cdrt_start(rtpp_cdrt_engine *e, int inst, const int32_t *rand, int n_rand);
+/* a fresh rand() stream for a running instance (the next draw is rand[0]) */
+RTPP_API int rtpp_cdrt_set_rand(rtpp_cdrt_engine *e, int inst, const int32_t *rand, int n_rand);
 RTPP_API int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path);
 /* 24 int64 per instance: node ids used, agent id, agent island, clock reads, rand_pos, rand_exhausted, |eQr|,
  * |largerSet| list, |smallerSet| list, cut-line samples left, islands with a kd-tree, status, pops, rewired,

@@ -805,3 +805,81 @@ class CdrtPlanner:
         if self.own and self.eng is not None:
             self.eng.close()
             self.eng = None
+
+
+class PlannerCDRT:
+    """The C++ BImap drop-in (rtpp_b200/planners/CDRT.h: same methods as the reference class) driven from Python with
+    the call surface of the scripted demo loop (tests/cdrt_scenarios.py)."""
+
+    def __init__(self, fx, device=0):
+        self.L = planners_lib()
+        self.L.pl_cdrt_create.restype = C.c_void_p
+        h = self.L.pl_cdrt_create(fx["W"], fx["H"], device)
+        if not h:
+            raise RtppError("BImap could not be created (no CUDA device; there is no CPU fallback)")
+        self.h, self.fx = C.c_void_p(h), fx
+        for g in fx["graphs"]:
+            self.L.pl_cdrt_set_graph(self.h, len(g["cut_se"]), _p(g["cut_se"]), _p(g["cut_core"]), _p(g["cp_off"]), _p(g["cp"]), _p(g["cc_off"]),
+                                     _p(g["cc"]), len(g["poly_core"]), _p(g["pv_off"]), _p(g["pv"]), _p(g["poly_core"]), _p(g["pc_off"]),
+                                     _p(g["pc"]), _p(g["pp_off"]), _p(g["pp"]))
+        self._rand = None
+
+    def close(self):
+        if self.h:
+            self.L.pl_cdrt_destroy(self.h)
+            self.h = None
+
+    def draw_bimap(self):
+        a = np.zeros((self.fx["H"], self.fx["W"]), np.uint16)
+        i = np.zeros_like(a)
+        self.L.pl_cdrt_draw_bimap(self.h, _p(a), _p(i))
+        return a, i
+
+    def set_params(self, r_th=10.0, p_th=0.85, nearK=20, RewireN=100):
+        self.L.pl_cdrt_set_params(self.h, C.c_double(r_th), C.c_double(p_th), nearK, RewireN)
+
+    def set_clock(self, dt_ns, n0=0):
+        self.L.pl_cdrt_set_clock(self.h, C.c_longlong(dt_ns))
+
+    def set_rand(self, r):
+        self._rand = _c(r, np.int32)
+        self.L.pl_cdrt_set_rand(self.h, _p(self._rand), C.c_longlong(len(self._rand)))
+
+    def set_agent(self, x, y):
+        self.L.pl_cdrt_set_agent(self.h, C.c_double(x), C.c_double(y))
+
+    def set_goal(self, x, y):
+        self.L.pl_cdrt_set_goal(self.h, C.c_double(x), C.c_double(y))
+
+    def add_obstacle(self, num, typ, x, y, angle, radius, outline, check_len=2.0):
+        o = _c(outline, np.float64).reshape(-1, 2)
+        self.L.pl_cdrt_add_obstacle(self.h, num, typ, C.c_double(x), C.c_double(y), C.c_double(angle), C.c_double(radius), _p(o), len(o),
+                                    C.c_double(check_len))
+
+    def move_obstacle(self, num, x, y, angle=0.0):
+        self.L.pl_cdrt_move_obstacle(self.h, num, C.c_double(x), C.c_double(y), C.c_double(angle))
+
+    def start(self):
+        self.draw_bimap()
+        self.L.pl_cdrt_start(self.h, C.c_double(self.fx["resolution"]))
+
+    def task(self):
+        self.L.pl_cdrt_task(self.h)
+
+    def get_path(self, cap=2048):
+        xy = np.zeros((cap, 2))
+        col, cost = C.c_int(), C.c_double()
+        n = self.L.pl_cdrt_get_path(self.h, _p(xy), cap, C.byref(col), C.byref(cost))
+        return xy[: min(n, cap)].copy(), bool(col.value), cost.value
+
+    def state(self):
+        out = np.zeros(24, np.int64)
+        self.L.pl_cdrt_stats(self.h, _p(out))
+        return dict(zip(CdrtEngine.STAT, out.tolist()))
+
+    def dump(self):
+        n = self.L.pl_cdrt_num_nodes(self.h)
+        xy, par = np.zeros((n, 2)), np.zeros((n, 2))
+        cost, col, inv, ns = np.zeros(n), np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        assert self.L.pl_cdrt_dump(self.h, _p(xy), _p(par), _p(cost), _p(col), _p(inv), _p(ns)) == n
+        return xy, par, cost, col, inv, ns

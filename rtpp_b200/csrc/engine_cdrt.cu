@@ -1295,6 +1295,17 @@ int rtpp_cdrt_start(rtpp_cdrt_engine *e, int inst, const int32_t *rand, int n_ra
     return RTPP_OK;
 }
 
+// a fresh rand() stream for a running instance (the next draw is rand[0])
+int rtpp_cdrt_set_rand(rtpp_cdrt_engine *e, int inst, const int32_t *rand, int n_rand) {
+    if (!e || inst < 0 || inst >= e->v.n_inst || n_rand < 0 || (n_rand && !rand) || n_rand > e->v.rand_cap) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    if (n_rand) CD_CK(e, cudaMemcpyAsync((int *)e->v.rand + (size_t)inst * e->v.rand_cap, rand, (size_t)n_rand * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int hdr[3] = {0, n_rand, 0}; // rand_pos, rand_n, rand_exhausted are adjacent in CdInst
+    CD_CK(e, cudaMemcpyAsync(&e->v.inst[inst].rand_pos, hdr, sizeof(hdr), cudaMemcpyHostToDevice, ctx->stream));
+    CD_CK(e, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
 // RTRT_task for every started instance (+ GetPath when do_get_path): draws each instance's dynamic plane
 // (RTRT_DrawDObsmap :605-636; the outline rotation uses the host's sinf/cosf and binary64 products as
 // written at :617-618), ships the obstacle poses and agent/goal points, runs one kernel.

@@ -217,3 +217,87 @@ PL_EXPORT int pl_amrrt_get_path(void *h, float *out_xy, int cap, int *collision,
     }
     return n;
 }
+
+// ------------------------------------------------------------------------------------- CDRT-RRT*
+#include "CDRT.h"
+PL_EXPORT void *pl_cdrt_create(int W, int H, int device) {
+    BImap *p = new BImap(device);
+    if (!p->ok()) {
+        delete p;
+        return nullptr;
+    }
+    p->SetShape((uint32_t)W, (uint32_t)H);
+    return p;
+}
+PL_EXPORT void pl_cdrt_destroy(void *h) { delete (BImap *)h; }
+PL_EXPORT int pl_cdrt_set_graph(void *h, int ncut, const double *cut_se, const double *cut_core, const int *cp_off, const int *cp, const int *cc_off,
+                                const int *cc, int npoly, const int *pv_off, const double *pv, const double *poly_core, const int *pc_off,
+                                const int *pc, const int *pp_off, const int *pp) {
+    return ((BImap *)h)->SetGraph(ncut, cut_se, cut_core, cp_off, cp, cc_off, cc, npoly, pv_off, pv, poly_core, pc_off, pc, pp_off, pp);
+}
+PL_EXPORT void pl_cdrt_draw_bimap(void *h, uint16_t *amap, uint16_t *imap) {
+    BImap *p = (BImap *)h;
+    p->DrawBImap(false);
+    if (amap) memcpy(amap, p->BIamap.data.data(), p->BIamap.data.size() * 2);
+    if (imap) memcpy(imap, p->BIimap.data.data(), p->BIimap.data.size() * 2);
+}
+PL_EXPORT void pl_cdrt_set_params(void *h, double r_th, double p_th, int nearK, int RewireN) {
+    BImap *p = (BImap *)h;
+    p->r_th = r_th, p->p_th = p_th, p->nearK = nearK, p->RewireN = RewireN;
+}
+PL_EXPORT void pl_cdrt_set_clock(void *h, long long dt) { ((BImap *)h)->SetVirtualClock(dt); }
+PL_EXPORT void pl_cdrt_set_rand(void *h, const int32_t *r, long long n) { ((BImap *)h)->SetRandStream(r, n); }
+PL_EXPORT void pl_cdrt_set_agent(void *h, double x, double y) { ((BImap *)h)->RTRT_SetAgent({x, y}); }
+PL_EXPORT void pl_cdrt_set_goal(void *h, double x, double y) { ((BImap *)h)->RTRT_SetGoal({x, y}); }
+PL_EXPORT void pl_cdrt_add_obstacle(void *h, int num, int type, double x, double y, double angle, double radius, const double *outline_xy, int npts,
+                                    double check_len) {
+    CTrtrt_DynamicObstacle o;
+    o.DObsType = type, o.x = x, o.y = y, o.angle = angle, o.radius = radius, o.sampleRadius = 0;
+    for (int i = 0; i < npts; i++) o.OutLine.push_back({outline_xy[2 * i], outline_xy[2 * i + 1]});
+    ((BImap *)h)->RTRT_AddDynamicObstacle(num, o, check_len);
+}
+PL_EXPORT void pl_cdrt_move_obstacle(void *h, int num, double x, double y, double angle) {
+    CTrtrt_DynamicObstacle &o = ((BImap *)h)->DObstacles[num]; // what the demos do (CDRT2/test/testD.cpp:189-190)
+    o.x = x, o.y = y, o.angle = angle;
+}
+PL_EXPORT void pl_cdrt_start(void *h, double resolution) { ((BImap *)h)->RTRT_start(resolution); }
+PL_EXPORT void pl_cdrt_task(void *h) { ((BImap *)h)->RTRT_task(); }
+PL_EXPORT int pl_cdrt_get_path(void *h, double *out_xy, int cap, int *collision, double *cost) {
+    BImap *p = (BImap *)h;
+    CTrtrt_Cost c = p->GetPath();
+    *collision = c.collision, *cost = c.cost;
+    int n = 0;
+    for (const BIpoint &q : p->agent_path) {
+        if (n < cap) out_xy[2 * n] = q.x, out_xy[2 * n + 1] = q.y;
+        n++;
+    }
+    return n;
+}
+PL_EXPORT int pl_cdrt_stats(void *h, long long *out24) { return ((BImap *)h)->ReadStats(out24); }
+PL_EXPORT int pl_cdrt_num_nodes(void *h) {
+    BImap *p = (BImap *)h;
+    p->SyncNodeMap();
+    return (int)p->Node_Map.size();
+}
+// Node_Map order (after pl_cdrt_num_nodes): xy, parent xy, cost, collision, invM, #children
+PL_EXPORT int pl_cdrt_dump(void *h, double *xy, double *par_xy, double *cost, uint8_t *col, int32_t *invM, int32_t *nsubs) {
+    BImap *p = (BImap *)h;
+    int i = 0;
+    for (const auto &kv : p->Node_Map) {
+        xy[2 * i] = kv.first.x, xy[2 * i + 1] = kv.first.y;
+        par_xy[2 * i] = kv.second.par.x, par_xy[2 * i + 1] = kv.second.par.y;
+        cost[i] = kv.second.cost.cost, col[i] = kv.second.cost.collision, invM[i] = kv.second.invM;
+        nsubs[i] = (int)kv.second.subs.size();
+        i++;
+    }
+    return i;
+}
+// host fillConvexPoly alone (no GPU needed)
+PL_EXPORT void pl_fill_convex16(uint16_t *img, int rows, int cols, const int *xy, int npts, int v) {
+    rtpp::Plane16 p;
+    p.rows = rows, p.cols = cols, p.data.assign(img, img + (size_t)rows * cols);
+    std::vector<std::pair<int, int>> pts;
+    for (int i = 0; i < npts; i++) pts.push_back({xy[2 * i], xy[2 * i + 1]});
+    rtpp::fill_convex_polygon(p, pts, (uint16_t)v);
+    memcpy(img, p.data.data(), p.data.size() * 2);
+}

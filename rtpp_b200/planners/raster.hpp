@@ -36,6 +36,27 @@ struct Plane8 {
     }
 };
 
+// 16-bit id plane (BImap::BIamap / BIimap, CDRT.h:296-297): cv::Mat CV_16U stand-in
+struct Plane16 {
+    int rows = 0, cols = 0;
+    std::vector<uint16_t> data;
+    void create(int r, int c, uint16_t fill) { rows = r, cols = c, data.assign((size_t)r * c, fill); }
+    bool empty() const { return data.empty(); }
+    uint16_t at(int row, int col) const { // at<uint16_t>(row, col) of a continuous matrix; outside the buffer = 0xFFFF
+        long long lin = (long long)row * cols + col;
+        if (lin < 0 || lin >= (long long)rows * cols) return 0xFFFF;
+        return data[(size_t)lin];
+    }
+    void span(int y, int xa, int xb, uint16_t v) {
+        if ((unsigned)y >= (unsigned)rows) return;
+        xa = std::max(xa, 0), xb = std::min(xb, cols - 1);
+        for (int x = xa; x <= xb; x++) data[(size_t)y * cols + x] = v;
+    }
+    void put(int x, int y, uint16_t v) {
+        if ((unsigned)x < (unsigned)cols && (unsigned)y < (unsigned)rows) data[(size_t)y * cols + x] = v;
+    }
+};
+
 inline void fill_circle(Plane8 &im, int cx, int cy, int r, uint8_t v) {
     if (r < 0) return;
     int e = 0, dx = r, dy = 0, up = 1, down = 2 * r - 1;
@@ -47,7 +68,7 @@ inline void fill_circle(Plane8 &im, int cx, int cy, int r, uint8_t v) {
     }
 }
 
-inline void draw_line8(Plane8 &im, int xa, int ya, int xb, int yb, uint8_t v) {
+template <class Im, class T> inline void draw_line8(Im &im, int xa, int ya, int xb, int yb, T v) {
     if (xb < xa) std::swap(xa, xb), std::swap(ya, yb);
     const int ddx = xb - xa, sgn = yb < ya ? -1 : 1, ddy = (yb - ya) * sgn;
     const bool steep = ddy > ddx;
@@ -111,6 +132,57 @@ inline void fill_polygon(Plane8 &im, const std::vector<std::pair<int, int>> &pts
         }
         std::stable_sort(merged.begin(), merged.end(), [&](int p, int q) { return edges[p].x < edges[q].x; });
         active.swap(merged);
+    }
+}
+
+// cv::fillConvexPoly (LINE_8, no shift) for DrawBImap (CDRT.cpp:143-144): the outline as 8-connected lines, then
+// one scan line at a time between a left-going and a right-going chain that both start at the top-most vertex.
+// Chain abscissae are 16.16 fixed point; a chain entering an edge (x0,y) -> (x1,y1) advances per line by
+// (2*(x1-x0) + (y1-y)) / (2*(y1-y)) (C integer division); both span ends round to nearest.
+// Verified pixel-for-pixel against the planes python cv2 4.13 draws (tests/test_planners_cpu.py).
+template <class Im, class T> inline void fill_convex_polygon(Im &im, const std::vector<std::pair<int, int>> &pts, T v) {
+    const int n = (int)pts.size();
+    if (n == 0) return;
+    int top = 0, y_lo = pts[0].second, y_hi = pts[0].second, x_lo = pts[0].first, x_hi = pts[0].first;
+    for (int i = 0; i < n; i++) {
+        const std::pair<int, int> &a = pts[(i + n - 1) % n], &b = pts[i];
+        draw_line8(im, a.first, a.second, b.first, b.second, v);
+        if (b.second < y_lo) y_lo = b.second, top = i;
+        y_hi = std::max(y_hi, b.second), x_lo = std::min(x_lo, b.first), x_hi = std::max(x_hi, b.first);
+    }
+    if (n < 3 || x_hi < 0 || y_hi < 0 || x_lo >= im.cols || y_lo >= im.rows) return;
+    y_hi = std::min(y_hi, im.rows - 1);
+    struct Chain {
+        int vertex, dir, until;
+        long long x, step;
+    };
+    Chain ch[2] = {{top, 1, y_lo, -65536, 0}, {top, n - 1, y_lo, -65536, 0}};
+    int moves_left = n;
+    for (int y = y_lo; y <= y_hi; y++) {
+        for (Chain &c : ch) {
+            if (y < c.until) continue;
+            int a = c.vertex;
+            bool entered = false;
+            while (moves_left-- > 0) {
+                const int b = (a + c.dir) % n;
+                if (pts[b].second > y) {
+                    const long long xa = (long long)pts[a].first * 65536, xb = (long long)pts[b].first * 65536;
+                    const int dy = pts[b].second - y;
+                    c.until = pts[b].second, c.step = (2 * (xb - xa) + dy) / (2 * dy), c.x = xa, c.vertex = b;
+                    entered = true;
+                    break;
+                }
+                a = b;
+            }
+            if (!entered) break;
+        }
+        if (moves_left < 0) return;
+        if (y >= 0) {
+            const long long xl = std::min(ch[0].x, ch[1].x), xr = std::max(ch[0].x, ch[1].x);
+            const int a = (int)((xl + 32768) >> 16), b = (int)((xr + 32768) >> 16);
+            if (b >= 0 && a < im.cols) im.span(y, a, b, v);
+        }
+        ch[0].x += ch[0].step, ch[1].x += ch[1].step;
     }
 }
 

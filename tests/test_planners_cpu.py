@@ -43,3 +43,22 @@ def test_host_rasteriser_matches_live_cv2():
         cv2.fillPoly(a, [pts], 127)
         capi.host_raster_fillpoly(b, pts)
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["MESS6", "MAZE0"])
+def test_host_fill_convex_polygon_matches_cv2_planes(oracle, name):
+    """The planner layer's own fillConvexPoly (planners/raster.hpp, product code) redraws the id planes of DrawBImap
+    (CDRT.cpp:121-175) exactly as the real cv2.fillConvexPoly drew them (tests/golden/cdrt/<MAP>.npz)."""
+    import ctypes as C
+
+    from rtpp_b200 import capi
+
+    L = capi.planners_lib()
+    fx = oracle.load_cdrt_fixture(name)
+    H, W = fx["H"], fx["W"]
+    imap = np.full((H, W), 0xFFFF, np.uint16)
+    g = fx["graphs"][0]
+    for pi in range(len(g["poly_core"])):
+        v = np.ascontiguousarray(g["pv"][g["pv_off"][pi]:g["pv_off"][pi + 1]].astype(np.int32))
+        L.pl_fill_convex16(imap.ctypes.data_as(C.c_void_p), H, W, v.ctypes.data_as(C.c_void_p), len(v), pi)
+    assert np.array_equal(imap, fx["imap"])

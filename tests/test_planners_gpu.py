@@ -153,3 +153,31 @@ def test_cpp_amrrt_planner_reproduces_reference_golden(oracle, case):
         assert np.array_equal(path, g[k + "path"]) and pcol == bool(g[k + "path_col"])
         assert np.float32(pcost).view(np.uint32) == g[k + "path_cost"].view(np.uint32)
     pl.close()
+
+
+def test_cpp_bimap_reproduces_reference_golden(oracle):
+    """The C++ BImap drop-in (planners/CDRT.h) through the reference's own method sequence — DrawBImap, RTRT_AddDynamicObstacle,
+    RTRT_SetAgent/SetGoal, RTRT_start, then RTRT_task + GetPath per frame with obstacles mutated in place and the agent
+    following its path — against the golden vectors the reference's CDRT.cpp produced (tests/golden/cdrt_mess6_g0.npz)."""
+    import cdrt_scenarios as sc
+    from rtpp_b200 import capi
+
+    case = sc.GOLDEN_CASES[0]
+    z = np.load(os.path.join(GOLD, f"cdrt_{case['name']}.npz"))
+    fx = oracle.load_cdrt_fixture(case["map"])
+    pl = capi.PlannerCDRT(fx)
+    amap, imap = pl.draw_bimap()  # host fillConvexPoly == the real cv2's planes
+    assert np.array_equal(amap, fx["amap"]) and np.array_equal(imap, fx["imap"])
+    sc.setup(pl, case["map"], case["goal"], oracle.rand31(case["seed"], case["n_rand"]), dt_ns=case["dt"], params=case["params"])
+    for k in range(case["ticks"]):
+        path, col, cost = sc.tick(pl, case["map"], k)
+        st = pl.state()
+        assert st["status"] == 0
+        r = z["rows"][k]
+        assert (st["queue"], st["rand_pos"], st["clock_reads"], st["island"], st["n_trees"], st["samples_left"], int(col), len(path)) == \
+               tuple(int(v) for v in (r[1], r[2], r[3], r[4], r[5], r[6], r[9], r[10])), f"tick {k}"
+        assert np.array_equal(path, z[f"t{k}_path"]) and np.float64(cost).tobytes() == z[f"t{k}_cost"].tobytes(), f"tick {k} path"
+        if k in case["dump_ticks"]:
+            for i, a in enumerate(pl.dump()):  # Node_Map with parents, costs, invM and subs sizes
+                assert np.array_equal(a.view(np.uint8), z[f"t{k}_dump{i}"].view(np.uint8)), f"tick {k} dump {i}"
+    pl.close()
