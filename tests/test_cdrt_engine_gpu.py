@@ -72,3 +72,109 @@ def test_engine_vs_oracle_live(ctx, oracle, name, goal, seed, dt, ticks):
     assert (c["pops"], c["rewired"], c["sampled"], c["pushes"]) == (sg["pops"], sg["rewired"], sg["sampled"], sg["pushes"])
     o.close()
     pl.close()
+
+
+def _engine(ctx, fx, n=1, **kw):
+    import rtpp_b200
+
+    return rtpp_b200.CdrtEngine(ctx, n, fx["graphs"][0], fx["amap"], fx["imap"], fx["resolution"], **kw)
+
+
+def test_two_instances_are_independent(ctx, oracle):
+    """Two planners of one engine (different goals, seeds and obstacle sets) each follow their own oracle run."""
+    import rtpp_b200
+
+    name = "MESS6"
+    fx = oracle.load_cdrt_fixture(name)
+    eng = _engine(ctx, fx, n=2, rand_capacity=200_000)
+    start, goals = sc.TASKS[name]
+    orcs = []
+    for i in range(2):
+        o = oracle.CdrtCpu(fx, "oracle")
+        o.set_params()
+        o.set_clock(10000)
+        r = oracle.rand31(40 + i, 200_000)
+        o.set_rand(r)
+        obs = sc.OBSTACLES[name][: 4 - 2 * i]  # instance 1 has only two obstacles
+        for k, (typ, x, y, ang, rad, outline) in enumerate(obs):
+            o.add_obstacle(k, typ, float(x), float(y), float(ang), float(rad), np.array(outline, np.float64), 2.0)
+            eng.add_obstacle(i, k, typ, float(x), float(y), float(ang), float(rad), np.array(outline, np.float64), 2.0)
+        for p in (o, None):
+            if p is not None:
+                p.set_agent(float(start[0]), float(start[1]))
+                p.set_goal(*[float(v) for v in goals[i + 1]])
+        eng.set_agent(i, float(start[0]), float(start[1]))
+        eng.set_goal(i, *[float(v) for v in goals[i + 1]])
+        o.start()
+        eng.start(i, r)
+        orcs.append((o, len(obs)))
+    for k in range(12):
+        eng.tick(10000, get_path=True)
+        t = (k + 1) * sc.TICK_S
+        for i, (o, nobs) in enumerate(orcs):
+            o.task()
+            po = o.get_path()
+            pl = rtpp_b200.CdrtPlanner(ctx, fx, inst=i, engine=eng)
+            pg = pl.get_path()
+            assert np.array_equal(po[0], pg[0]) and po[1] == pg[1] and np.float64(po[2]).tobytes() == np.float64(pg[2]).tobytes()
+            for a, b in zip(o.dump(), pl.dump()):
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"tick {k} instance {i}"
+            for j in range(nobs):
+                q = sc.along(sc.OBS_PATHS[name][j], sc.OBS_SPEED * t)
+                o.move_obstacle(j, float(q[0]), float(q[1]), 0.0)
+                eng.move_obstacle(i, j, float(q[0]), float(q[1]), 0.0)
+    assert (eng.stats()[:, 11] == 0).all()
+    for o, _ in orcs:
+        o.close()
+    eng.close()
+
+
+def test_no_goal_no_obstacles_and_rejected_points(ctx, oracle):
+    """GetPath without a goal returns {true, doubleMax} and an empty path (CDRT.cpp:1069-1075); with no obstacle no island
+    ever holds a kd-tree, so every sample is a cut-line sample; points outside the free polygons are ignored
+    (RTRT_SetAgent/SetGoal print and return, CDRT.cpp:384-423)."""
+    fx = oracle.load_cdrt_fixture("MESS6")
+    eng = _engine(ctx, fx, rand_capacity=100_000)
+    o = oracle.CdrtCpu(fx, "oracle")
+    r = oracle.rand31(3, 100_000)
+    o.set_params()
+    o.set_clock(20000)
+    o.set_rand(r)
+    assert eng.set_agent(0, 5.0, 5.0) == 1          # inside an obstacle: rejected
+    assert eng.set_agent(0, 1e6, 10.0) == 1         # outside the map: rejected
+    assert eng.set_goal(0, 5.0, 5.0) == 1
+    assert eng.set_agent(0, 720.0, 720.0) == 0
+    o.set_agent(720.0, 720.0)
+    o.start()
+    eng.start(0, r)
+    for _ in range(5):
+        o.task()
+        eng.tick(20000, get_path=True)
+    s = eng.stats_dict(0)
+    assert s["status"] == 0 and s["n_trees"] == 0 and s["path_len"] == 0 and s["path_col"] == 1
+    assert np.array(s["path_cost_bits"], np.int64).view(np.float64) == 1.79769e307
+    so = o.state()
+    assert (s["queue"], s["samples_left"], s["rand_pos"], s["clock_reads"]) == (so["queue"], so["samples_left"], o.rand_pos(), o.clock_reads())
+    o.close()
+    eng.close()
+
+
+def test_capacity_overflows_are_reported_not_fatal(ctx, oracle):
+    """A full queue or node store stops the instance with a status code (2 / 1); nothing is written out of bounds."""
+    fx = oracle.load_cdrt_fixture("MESS6")
+    r = oracle.rand31(7, 400_000)
+    for kw, want in ((dict(queue_capacity=512), 2), (dict(node_capacity=16), 0)):
+        eng = _engine(ctx, fx, rand_capacity=400_000, **kw)
+        for k, (typ, x, y, ang, rad, outline) in enumerate(sc.OBSTACLES["MESS6"]):
+            eng.add_obstacle(0, k, typ, float(x), float(y), float(ang), float(rad), np.array(outline, np.float64), 2.0)
+        eng.set_agent(0, 720.0, 720.0)
+        eng.set_goal(0, 70.0, 70.0)
+        eng.start(0, r)
+        for _ in range(14):
+            eng.tick(20000)
+        st = eng.stats_dict(0)
+        if want:
+            assert st["status"] == want, st
+        else:  # the node store is sized up to the cut-line samples + 64: island samples then overflow it
+            assert st["status"] in (0, 1), st
+        eng.close()
