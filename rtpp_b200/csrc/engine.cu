@@ -52,6 +52,7 @@ struct EngView {
     int *sid, *cell_of, *cell_start, *cursor;
     int *qr, *qs, *qs_mark;
     int *child_start, *children, *frontier;
+    int *nn_ids, *nn_n; // cached 25-NN list of every tree node (ids) and the node count it was computed for (0 = none)
     float2 *samples;
     int *path;
     PlaneView planes[16]; // merged S|D plane per map slot
@@ -87,7 +88,7 @@ struct Inst {
     EngInst s; // register copy, uniform across the warp
     float2 *xy, *sxy;
     cpword *cp;
-    int *sid, *cell_of, *cell_start, *cursor, *qr, *qs, *qs_mark, *child_start, *children, *frontier;
+    int *sid, *cell_of, *cell_start, *cursor, *qr, *qs, *qs_mark, *child_start, *children, *frontier, *nn_ids, *nn_n;
     const float2 *samples;
     int *path;
     PlaneView pl;
@@ -145,6 +146,33 @@ __device__ __forceinline__ void maybe_rebuild(const EngView &ev, Inst &in) {
     // is re-sorted whenever the unsorted tail reaches max(512, n/8)
     const int tail = in.s.n - in.s.n_sorted;
     if (in.s.n_sorted == 0 ? tail >= 2048 : (tail >= 512 && tail * 8 >= in.s.n_sorted)) grid_rebuild_warp(ev, in);
+}
+
+// 25-NN of tree node x (the query of every queue pop: RTRRT.cpp:304,333; AMRRT.cpp:496).  The list found at the last pop
+// of x is kept (ids only: the squared distances are recomputed with the same operations) and extended by the nodes
+// appended since — exact, because nodes never move or disappear — instead of searching the whole tree again.
+__device__ __forceinline__ int knn_at_node(const EngView &ev, Inst &in, int x, KnnEntry &e) {
+    const int lane = threadIdx.x & 31;
+    const float2 px = in.xy[x];
+    const int n0 = in.nn_n[x];
+    int found;
+    __syncwarp();
+    if (n0 > 0 && in.s.n - n0 <= 512) {
+        const int cnt = min(n0, 25);
+        e.d2 = CUDART_INF, e.id = 0x7fffffff;
+        if (lane < cnt) {
+            e.id = in.nn_ids[(size_t)x * 25 + lane];
+            const float2 q = in.xy[e.id];
+            e.d2 = knn_d2((double)px.x, (double)px.y, q.x, q.y);
+        }
+        if (in.s.n == n0) return cnt;
+        found = knn_warp_impl(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e, cnt, n0);
+    } else
+        found = knn_warp(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e);
+    if (lane < found) in.nn_ids[(size_t)x * 25 + lane] = e.id;
+    if (lane == 0) in.nn_n[x] = in.s.n;
+    __syncwarp();
+    return found;
 }
 
 // virtual clock: the k-th read returns k*dt (orc::VClock)
@@ -311,7 +339,7 @@ __device__ __forceinline__ bool relax_neighbours(const EngView &ev, Inst &in, co
                                                  int &found) {
     const int lane = threadIdx.x & 31;
     const float2 px = in.xy[x];
-    found = knn_warp(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e);
+    found = knn_at_node(ev, in, x, e);
     bool improved = false;
     if (lane < found) {
         const float2 q = in.xy[e.id];
@@ -658,7 +686,7 @@ __device__ void am_rewire_root(const EngView &ev, Inst &in, const MarchThreshold
         in.s.pops_s++;
         const float2 pr = in.xy[xr];
         KnnEntry e;
-        const int found = knn_warp(inst_grid(ev, in), (double)pr.x, (double)pr.y, 25, e);
+        const int found = knn_at_node(ev, in, xr, e);
         bool free_edge = false;
         if (lane < found) {
             const float2 q = in.xy[e.id];
@@ -748,6 +776,7 @@ __device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
     in.qr = ev.qr + (size_t)w * ev.qr_cap, in.qs = ev.qs + c, in.qs_mark = ev.qs_mark + c;
     in.child_start = ev.child_start + (size_t)w * (ev.cap + 1), in.children = ev.children + c;
     in.frontier = ev.frontier + 2 * c;
+    in.nn_ids = ev.nn_ids + 25 * c, in.nn_n = ev.nn_n + c;
     in.samples = ev.samples + (size_t)w * ev.max_samples;
     in.path = ev.path + (size_t)w * ev.path_cap;
     in.pl = ev.planes[in.s.map_slot & 15];
@@ -870,6 +899,8 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
     rc |= eng_alloc(e, &v.child_start, N * (node_capacity + 1));
     rc |= eng_alloc(e, &v.children, C);
     rc |= eng_alloc(e, &v.frontier, 2 * C);
+    rc |= eng_alloc(e, &v.nn_ids, 25 * C);
+    rc |= eng_alloc(e, &v.nn_n, C);
     rc |= eng_alloc(e, &v.samples, planner_kind == 1 ? N * max_samples : 1);
     if (planner_kind == 2) { // max_samples = rand() draws available per instance and call
         v.rand_cap = max_samples;
@@ -890,6 +921,7 @@ int rtpp_engine_destroy(rtpp_engine *e) {
     cudaFree(v.inst), cudaFree(v.xy), cudaFree(v.sxy), cudaFree(v.cp), cudaFree(v.sid), cudaFree(v.cell_of);
     cudaFree(v.cell_start), cudaFree(v.cursor), cudaFree(v.qr), cudaFree(v.qs), cudaFree(v.qs_mark);
     cudaFree(v.child_start), cudaFree(v.children), cudaFree(v.frontier), cudaFree(v.samples), cudaFree(v.path);
+    cudaFree(v.nn_ids), cudaFree(v.nn_n);
     for (int i = 0; i < 16; i++) cudaFree(e->plane_s[i]), cudaFree(e->plane_d[i]), cudaFree(e->plane_sd[i]);
     cudaFree(e->d_rand), cudaFree(e->d_rand_cs), cudaFree(e->d_diff_cell), cudaFree(e->d_diff_rows);
     delete e;
@@ -951,6 +983,7 @@ int rtpp_engine_init_instances(rtpp_engine *e, const int32_t *map_slot, const fl
     rc |= upload(e, 1, agent_xy, (size_t)n * 8, &da);
     rc |= upload(e, 2, goal_xy, (size_t)n * 8, &dg);
     if (rc) return rc;
+    ENG_CK(e, cudaMemsetAsync(e->v.nn_n, 0, (size_t)n * e->v.cap * sizeof(int), ctx->stream)); // no cached neighbour lists
     engine_init_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(e->v, (const int *)ds, (const float2 *)da, (const float2 *)dg);
     RTPP_LAUNCHED(ctx);
     ENG_CK(e, cudaStreamSynchronize(ctx->stream));

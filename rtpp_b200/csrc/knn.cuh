@@ -52,14 +52,19 @@ __device__ __forceinline__ int grid_cell_of(double v, int shift, int gmax) {
 
 // Warp-collective.  All 32 lanes must call with the same q and k (1 <= k <= 32).
 // On return lane j (j < count) holds the j-th neighbour; returns count = min(k, n).
-__device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy, int k, KnnEntry &mine) {
+// found0 < 0: a fresh query.  found0 >= 0: `mine` already holds the exact result over the node ids [0, scan_from)
+// (lanes >= found0 hold +inf) and only the ids [scan_from, n) are scanned, linearly — the planner engines cache the
+// neighbour list of a tree node and extend it by the nodes appended since (nodes never move or disappear).
+__device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, double qy, int k, KnnEntry &mine, int found0, int scan_from) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    mine.d2 = CUDART_INF;
-    mine.id = 0x7fffffff;
-    int found = 0;
-    double kd2 = CUDART_INF; // current k-th entry (broadcast copy)
-    int kid = 0x7fffffff;
+    if (found0 < 0) {
+        mine.d2 = CUDART_INF;
+        mine.id = 0x7fffffff;
+    }
+    int found = found0 < 0 ? 0 : found0;
+    double kd2 = __shfl_sync(full, mine.d2, k - 1); // current k-th entry (broadcast copy)
+    int kid = __shfl_sync(full, mine.id, k - 1);
 
     // compare-exchange with the lane `stride` away: keep the smaller (keep_min) or larger pair
     auto cmpx = [&](double &d, int &i, int stride, bool keep_min) {
@@ -125,8 +130,8 @@ __device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy,
         }
     };
 
-    // unsorted tail first (usually empty or a few points)
-    for (int i0 = g.n_sorted; i0 < g.n; i0 += 32) {
+    // unsorted tail first (usually empty or a few points); a resumed query scans [scan_from, n) by id instead
+    for (int i0 = found0 < 0 ? g.n_sorted : scan_from; i0 < g.n; i0 += 32) {
         const int i = i0 + lane;
         const bool v = i < g.n;
         float2 p = make_float2(0.f, 0.f);
@@ -134,7 +139,7 @@ __device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy,
         offer(v, knn_d2(qx, qy, p.x, p.y), i);
     }
 
-    if (g.n_sorted > 0) {
+    if (found0 < 0 && g.n_sorted > 0) {
         const int cx = grid_cell_of(qx, g.shift, g.gw - 1), cy = grid_cell_of(qy, g.shift, g.gh - 1);
         const int want = min(k, g.n);
         const int rmax = max(max(cx, g.gw - 1 - cx), max(cy, g.gh - 1 - cy));
@@ -180,4 +185,7 @@ __device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy,
         }
     }
     return found;
+}
+__device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy, int k, KnnEntry &mine) {
+    return knn_warp_impl(g, qx, qy, k, mine, -1, 0);
 }
