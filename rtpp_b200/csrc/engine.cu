@@ -28,6 +28,7 @@
 struct EngInst {
     int map_slot;
     int n, n_sorted;
+    int shift, gw, gh; // the instance's current hash resolution (chosen at every re-sort from the node count)
     int root;
     float2 agent, goal;
     float c_base;
@@ -99,19 +100,25 @@ struct Inst {
 __device__ __forceinline__ GridView inst_grid(const EngView &ev, const Inst &in) {
     GridView g;
     g.sxy = in.sxy, g.sid = in.sid, g.cell_start = in.cell_start, g.xy = in.xy;
-    g.gw = ev.gw, g.gh = ev.gh, g.shift = ev.shift, g.n_sorted = in.s.n_sorted, g.n = in.s.n;
+    g.gw = in.s.gw, g.gh = in.s.gh, g.shift = in.s.shift, g.n_sorted = in.s.n_sorted, g.n = in.s.n;
     return g;
 }
 
 // counting sort of all nodes by cell, done by the instance's own warp
 __device__ void grid_rebuild_warp(const EngView &ev, Inst &in) {
     const int lane = threadIdx.x & 31;
-    const int n = in.s.n, m = ev.ncells;
+    const int n = in.s.n;
+    // cell size for about two nodes per cell (a sparse tree on a fine grid makes every query walk hundreds of empty
+    // cells; the result of a query does not depend on the resolution), never finer than the engine's cell_log2
+    int shift = ev.shift;
+    while (shift < 14 && (long long)(((ev.gw << ev.shift) - 1 >> (shift + 1)) + 1) * (((ev.gh << ev.shift) - 1 >> (shift + 1)) + 1) * 2 >= n) shift++;
+    const int gw = (((ev.gw << ev.shift) - 1) >> shift) + 1, gh = (((ev.gh << ev.shift) - 1) >> shift) + 1, m = gw * gh;
+    in.s.shift = shift, in.s.gw = gw, in.s.gh = gh;
     for (int c = lane; c <= m; c += 32) in.cursor[c] = 0;
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
         const float2 p = in.xy[i];
-        const int c = grid_cell_of((double)p.y, ev.shift, ev.gh - 1) * ev.gw + grid_cell_of((double)p.x, ev.shift, ev.gw - 1);
+        const int c = grid_cell_of((double)p.y, shift, gh - 1) * gw + grid_cell_of((double)p.x, shift, gw - 1);
         in.cell_of[i] = c;
         atomicAdd(&in.cursor[c], 1);
     }
@@ -142,10 +149,10 @@ __device__ void grid_rebuild_warp(const EngView &ev, Inst &in) {
 }
 
 __device__ __forceinline__ void maybe_rebuild(const EngView &ev, Inst &in) {
-    // small trees are scanned linearly (cheaper than walking a sparse grid); afterwards the hash
-    // is re-sorted whenever the unsorted tail reaches max(512, n/8)
+    // trees below 128 nodes are scanned linearly (4 chunks); afterwards the hash is re-sorted, at a resolution that
+    // follows the node count, whenever the unsorted tail reaches max(64, n/8)
     const int tail = in.s.n - in.s.n_sorted;
-    if (in.s.n_sorted == 0 ? tail >= 2048 : (tail >= 512 && tail * 8 >= in.s.n_sorted)) grid_rebuild_warp(ev, in);
+    if (in.s.n_sorted == 0 ? tail >= 128 : (tail >= 64 && tail * 8 >= in.s.n_sorted)) grid_rebuild_warp(ev, in);
 }
 
 // 25-NN of tree node x (the query of every queue pop: RTRRT.cpp:304,333; AMRRT.cpp:496).  The list found at the last pop
@@ -785,14 +792,16 @@ __device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
     return true;
 }
 
+// one instantiation per planner kind: the register allocation of one planner's loop is not paid by the other
+template <int KIND>
 __global__ void __launch_bounds__(128) engine_tick_kernel(EngView ev, MarchThresholds mt, int do_update, long long run_ns,
-                                                         long long dt, int do_path) {
+                                                                          long long dt, int do_path) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Inst in;
     if (!load_inst(ev, w, in)) return;
     if (in.s.n > 0) {
         if (do_update) update_tree(ev, in, mt);
-        if (ev.kind == 2) {
+        if (KIND == 2) {
             if (run_ns > 0) am_main_loop(ev, in, mt, dt);
             if (do_path) am_get_path(ev, in, mt);
         } else {
@@ -814,6 +823,7 @@ __global__ void engine_init_kernel(EngView ev, const int *__restrict__ slots, co
     s.agent = agent[w], s.goal = goal[w];
     s.c_base = -1.0f;
     s.n = 1, s.n_sorted = 0, s.root = 0;
+    s.shift = ev.shift, s.gw = ev.gw, s.gh = ev.gh;
     s.path_col = 1, s.path_cost = 3.4e38f;
     ev.xy[(size_t)w * ev.cap] = agent[w];
     ev.cp[(size_t)w * ev.cap] = cp_make(cost_pack(false, 0.0f), -1);
@@ -1091,8 +1101,12 @@ int rtpp_engine_tick(rtpp_engine *e, int do_update_tree, long run_ms, long long 
     rtpp_ctx *ctx = e->ctx;
     const int warps_per_block = e->v.n_inst >= 4 * ctx->sm_count ? 4 : 1;
     const int blocks = (e->v.n_inst + warps_per_block - 1) / warps_per_block;
-    engine_tick_kernel<<<blocks, 32 * warps_per_block, 0, ctx->stream>>>(e->v, e->mt, do_update_tree, (long long)run_ms * 1000000LL,
-                                                                         dt_ns, do_get_path);
+    if (e->v.kind == 2)
+        engine_tick_kernel<2><<<blocks, 32 * warps_per_block, 0, ctx->stream>>>(e->v, e->mt, do_update_tree, (long long)run_ms * 1000000LL, dt_ns,
+                                                                                do_get_path);
+    else
+        engine_tick_kernel<1><<<blocks, 32 * warps_per_block, 0, ctx->stream>>>(e->v, e->mt, do_update_tree, (long long)run_ms * 1000000LL, dt_ns,
+                                                                                do_get_path);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }
