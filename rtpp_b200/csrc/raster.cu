@@ -13,6 +13,7 @@
 //             truncates (one thread per polygon row).
 // This removes the 7-17 MB zero-fill + H2D plane upload per tick: a tick ships a few hundred bytes.
 #include <limits.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -154,69 +155,60 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
         for (int i = 0; i < n_planes; i++) RTPP_CK(ctx, cudaMemsetAsync(planes + (size_t)i * stride_words, 0, words * 4, ctx->stream));
     }
     TileTarget t{planes, W, H, tilesX, stride_words};
-    if (n_circles > 0) {
-        std::vector<int2> steps; // every dy with dx(dy) >= dy lies in [0, r*0.7072]
-        for (int c = 0; c < n_circles; c++) {
-            const int r = circles4[4 * c + 2];
-            if (r < 0 || r > 23000) continue; // r^2 must fit the exact integer arithmetic of the kernel
-            for (int dy = 0; dy <= (int)(r * 0.70711) + 1; dy++) steps.push_back(make_int2(c, dy));
-        }
-        if (!steps.empty()) {
-            const size_t b_c = ((size_t)n_circles * 16 + 15) & ~(size_t)15;
-            void *d = nullptr;
-            int rc = rtpp_scratch(ctx, 2, b_c + steps.size() * 8, &d);
-            if (rc) return rc;
-            const std::vector<int32_t> c_stage(circles4, circles4 + (size_t)n_circles * 4); // the caller's buffer may be pinned
-            RTPP_CK(ctx, cudaMemcpyAsync(d, c_stage.data(), (size_t)n_circles * 16, cudaMemcpyHostToDevice, ctx->stream));
-            RTPP_CK(ctx, cudaMemcpyAsync((char *)d + b_c, steps.data(), steps.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-            raster_circles_kernel<<<((int)steps.size() + 127) / 128, 128, 0, ctx->stream>>>(t, (const int4 *)d, (const int2 *)((char *)d + b_c),
-                                                                                           (int)steps.size());
-            RTPP_LAUNCHED(ctx);
-            // no synchronisation: every source above is pageable host memory, which cudaMemcpyAsync stages before it returns
-        }
+    // host-side job lists (a handful of shapes with a handful of vertices each), packed into ONE upload:
+    // [circles | circle steps | polygon vertices | polygon descriptors | polygon edges | polygon rows]
+    std::vector<int2> steps, edges, rows;
+    std::vector<PolyDesc> polys((size_t)(n_polys > 0 ? n_polys : 0));
+    for (int c = 0; c < n_circles; c++) { // every dy with dx(dy) >= dy lies in [0, r*0.7072]
+        const int r = circles4[4 * c + 2];
+        if (r < 0 || r > 23000) continue; // r^2 must fit the exact integer arithmetic of the kernel
+        for (int dy = 0; dy <= (int)(r * 0.70711) + 1; dy++) steps.push_back(make_int2(c, dy));
     }
-    if (n_polys > 0) {
-        // host-side job lists (a handful of polygons with a handful of vertices each)
-        size_t npts = 0;
-        for (int p = 0; p < n_polys; p++) npts += poly_sizes[p];
-        std::vector<PolyDesc> polys(n_polys);
-        std::vector<int2> edges, rows;
-        size_t first = 0;
-        for (int p = 0; p < n_polys; p++) {
-            const int cnt = poly_sizes[p];
-            if (cnt > kMaxPolyEdges) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "polygon has too many vertices");
-            int ymin = INT_MAX, ymax = INT_MIN;
-            for (int k = 0; k < cnt; k++) {
-                const int y = poly_xy[2 * (first + k) + 1];
-                ymin = y < ymin ? y : ymin, ymax = y > ymax ? y : ymax;
-                edges.push_back(make_int2(p, k));
-            }
-            polys[p] = PolyDesc{(int)first, cnt, ymin, ymax, poly_inst ? poly_inst[p] : 0};
-            for (int y = (ymin < 0 ? 0 : ymin); y < ymax && y < H; y++) rows.push_back(make_int2(p, y));
-            first += cnt;
+    size_t npts = 0;
+    for (int p = 0; p < n_polys; p++) {
+        const int cnt = poly_sizes[p];
+        if (cnt > kMaxPolyEdges) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "polygon has too many vertices");
+        int ymin = INT_MAX, ymax = INT_MIN;
+        for (int k = 0; k < cnt; k++) {
+            const int y = poly_xy[2 * (npts + k) + 1];
+            ymin = y < ymin ? y : ymin, ymax = y > ymax ? y : ymax;
+            edges.push_back(make_int2(p, k));
         }
-        const size_t b_pts = npts * 8, b_pol = polys.size() * sizeof(PolyDesc), b_edg = edges.size() * 8, b_row = rows.size() * 8;
-        const size_t o_pol = (b_pts + 15) & ~(size_t)15, o_edg = (o_pol + b_pol + 15) & ~(size_t)15, o_row = (o_edg + b_edg + 15) & ~(size_t)15;
-        void *d = nullptr;
-        int rc = rtpp_scratch(ctx, 3, o_row + b_row + 64, &d);
-        if (rc) return rc;
-        char *base = (char *)d;
-        const std::vector<int32_t> p_stage(poly_xy, poly_xy + npts * 2);
-        RTPP_CK(ctx, cudaMemcpyAsync(base, p_stage.data(), b_pts, cudaMemcpyHostToDevice, ctx->stream));
-        RTPP_CK(ctx, cudaMemcpyAsync(base + o_pol, polys.data(), b_pol, cudaMemcpyHostToDevice, ctx->stream));
-        if (b_edg) RTPP_CK(ctx, cudaMemcpyAsync(base + o_edg, edges.data(), b_edg, cudaMemcpyHostToDevice, ctx->stream));
-        if (b_row) RTPP_CK(ctx, cudaMemcpyAsync(base + o_row, rows.data(), b_row, cudaMemcpyHostToDevice, ctx->stream));
-        // (pageable sources are staged by cudaMemcpyAsync before it returns, so the vectors may go out of scope)
-        const int2 *dp = (const int2 *)base;
-        const PolyDesc *dpo = (const PolyDesc *)(base + o_pol);
-        if (!edges.empty()) {
-            raster_poly_outline_kernel<<<((int)edges.size() + 3) / 4, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_edg), (int)edges.size());
-            RTPP_LAUNCHED(ctx);
-        }
-        if (!rows.empty()) {
-            raster_poly_fill_kernel<<<((int)rows.size() + 127) / 128, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_row), (int)rows.size());
-            RTPP_LAUNCHED(ctx);
-        }
+        polys[p] = PolyDesc{(int)npts, cnt, ymin, ymax, poly_inst ? poly_inst[p] : 0};
+        for (int y = (ymin < 0 ? 0 : ymin); y < ymax && y < H; y++) rows.push_back(make_int2(p, y));
+        npts += cnt;
+    }
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_cir = 0, o_stp = up16((size_t)n_circles * 16), o_pts = up16(o_stp + steps.size() * 8), o_pol = up16(o_pts + npts * 8),
+                 o_edg = up16(o_pol + polys.size() * sizeof(PolyDesc)), o_row = up16(o_edg + edges.size() * 8), total = up16(o_row + rows.size() * 8);
+    if (steps.empty() && edges.empty() && rows.empty()) return RTPP_OK;
+    std::vector<char> stage(total, 0);
+    if (n_circles > 0) memcpy(stage.data() + o_cir, circles4, (size_t)n_circles * 16);
+    if (!steps.empty()) memcpy(stage.data() + o_stp, steps.data(), steps.size() * 8);
+    if (npts) memcpy(stage.data() + o_pts, poly_xy, npts * 8);
+    if (!polys.empty()) memcpy(stage.data() + o_pol, polys.data(), polys.size() * sizeof(PolyDesc));
+    if (!edges.empty()) memcpy(stage.data() + o_edg, edges.data(), edges.size() * 8);
+    if (!rows.empty()) memcpy(stage.data() + o_row, rows.data(), rows.size() * 8);
+    void *d = nullptr;
+    int rc = rtpp_scratch(ctx, 2, total, &d);
+    if (rc) return rc;
+    // (a pageable source is staged by cudaMemcpyAsync before it returns, so `stage` may go out of scope; no synchronisation)
+    RTPP_CK(ctx, cudaMemcpyAsync(d, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    const char *base = (const char *)d;
+    if (!steps.empty()) {
+        raster_circles_kernel<<<((int)steps.size() + 127) / 128, 128, 0, ctx->stream>>>(t, (const int4 *)(base + o_cir), (const int2 *)(base + o_stp),
+                                                                                       (int)steps.size());
+        RTPP_LAUNCHED(ctx);
+    }
+    const int2 *dp = (const int2 *)(base + o_pts);
+    const PolyDesc *dpo = (const PolyDesc *)(base + o_pol);
+    if (!edges.empty()) {
+        raster_poly_outline_kernel<<<((int)edges.size() + 3) / 4, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_edg), (int)edges.size());
+        RTPP_LAUNCHED(ctx);
+    }
+    if (!rows.empty()) {
+        raster_poly_fill_kernel<<<((int)rows.size() + 127) / 128, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_row), (int)rows.size());
+        RTPP_LAUNCHED(ctx);
     }
     return RTPP_OK;
 }
