@@ -156,30 +156,67 @@ relax_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const int *__r
     }
 }
 
-// relax phase 2: one Bellman-Ford sweep.  c_new = cost[x] + w; if c_new < cost[s] (strict,
-// lexicographic: RTRRT.cpp:311) the word {c_new, x} replaces cost|parent of s by atomicMin.
-// free_only: AM-RRT* RewireRoot relaxes only over free edges and never to a colliding cost
-// (AMRRT.cpp:500-504).
+// relax phase 2: c_new = cost[x] + w; if c_new < cost[s] (strict, lexicographic: RTRRT.cpp:311) the word {c_new, x}
+// replaces cost|parent of s by atomicMin.  free_only: AM-RRT* RewireRoot relaxes only over free edges and never to a
+// colliding cost (AMRRT.cpp:500-504).
+// relax phase 2 as a work list: only the edges out of nodes whose cost fell in the previous round can improve
+// anything, so a round handles the current frontier (one warp per node, lanes = its k edges), collects the nodes it
+// improved (deduplicated by a round stamp) and the whole iteration to quiescence is ONE persistent cooperative kernel
+// with a grid-wide barrier per round — the late rounds of a long improving chain touch a handful of nodes and cost a
+// barrier instead of a 25 M-edge pass and a host round trip.  Same least fixpoint as the sweeps.
+// counters: [0..2] frontier sizes in rotation (current, next, being cleared), [3] rounds done
 __global__ void __launch_bounds__(256)
-relax_sweep_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, size_t n_edges, int k, int free_only,
-                   cpword *cp, int *__restrict__ changed) {
-    bool any = false;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t we = w[e];
-        if (we == 0xffffffffu) continue;
-        if (free_only && (we >> 31)) continue;
-        const int x = (int)(e / k), s = knn[e];
-        const uint32_t hx = cp_hi(((volatile cpword *)cp)[x]);
-        if (hx == 0xffffffffu) continue; // x has no cost yet
-        const uint32_t hn = cost_add(hx, we);
-        if (free_only && (hn >> 31)) continue;
-        if (hn < cp_hi(((volatile cpword *)cp)[s])) {
-            const cpword neww = cp_make(hn, x);
-            const cpword prev = atomicMin(&cp[s], neww);
-            if (prev > neww && cp_hi(prev) > hn) any = true;
+relax_worklist_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, int n, int k, int free_only, cpword *cp, int *fr_a, int *fr_b,
+                      int *stamp, int *counters, int max_rounds) {
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    // round 0: every node that has a cost
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) fr_a[i] = i, stamp[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = n, counters[1] = 0, counters[2] = 0, counters[3] = 0;
+    grid.sync();
+    int *cur = fr_a, *nxt = fr_b;
+    int round = 0;
+    for (; round < max_rounds; round++) {
+        const int m = ((volatile int *)counters)[round % 3];
+        if (m == 0) break;
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[(round + 2) % 3] = 0, counters[3] = round + 1; // next round's target
+        for (int f = warp; f < m; f += nwarps) {
+            const int x = cur[f];
+            const uint32_t hx = cp_hi(((volatile cpword *)cp)[x]);
+            if (hx == 0xffffffffu) continue; // x has no cost yet
+            for (int j0 = 0; j0 < k; j0 += 32) {
+                const int j = j0 + lane;
+                bool improved = false;
+                int sn = -1;
+                if (j < k) {
+                    const size_t e = (size_t)x * k + j;
+                    const uint32_t we = w[e];
+                    if (we != 0xffffffffu && !(free_only && (we >> 31))) {
+                        sn = knn[e];
+                        const uint32_t hn = cost_add(hx, we);
+                        if (!(free_only && (hn >> 31)) && hn < cp_hi(((volatile cpword *)cp)[sn])) {
+                            const cpword neww = cp_make(hn, x);
+                            const cpword prev = atomicMin(&cp[sn], neww);
+                            improved = prev > neww && cp_hi(prev) > hn;
+                        }
+                    }
+                }
+                // a node enters the next frontier once per round
+                if (improved) improved = atomicExch(&stamp[sn], round + 1) != round + 1;
+                const unsigned bal = __ballot_sync(0xffffffffu, improved);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&counters[(round + 1) % 3], __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (improved) nxt[base + __popc(bal & ((1u << lane) - 1u))] = sn;
+                }
+            }
         }
+        int *t = cur;
+        cur = nxt, nxt = t;
+        grid.sync();
     }
-    if (__syncthreads_or(any) && threadIdx.x == 0) *changed = 1;
 }
 
 static int ensure_tree_scratch(rtpp_ctx *ctx, NodeStore *s) {
@@ -343,15 +380,22 @@ int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, 
     relax_weights_kernel<<<grid_for(ctx, ne), 256, 0, ctx->stream>>>(pv, s->xy, d_knn_idx, ne, k, mt, (uint32_t *)dw);
     RTPP_LAUNCHED(ctx);
     int sweeps = 0;
-    for (; sweeps < max_sweeps;) {
-        RTPP_CK(ctx, cudaMemsetAsync(s->counters + 4, 0, 4, ctx->stream));
-        relax_sweep_kernel<<<grid_for(ctx, ne), 256, 0, ctx->stream>>>(d_knn_idx, (const uint32_t *)dw, ne, k, free_only, s->cp, s->counters + 4);
-        RTPP_LAUNCHED(ctx);
-        sweeps++;
-        int changed = 0;
-        RTPP_CK(ctx, cudaMemcpyAsync(&changed, s->counters + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    {
+        int per_sm = 0;
+        RTPP_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_worklist_kernel, 256, 0));
+        int blocks = ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm)); // few blocks: the barrier is the cost of a late round
+        const int need = (int)(((size_t)s->n * 32 + 255) / 256);
+        if (blocks > need) blocks = need < 1 ? 1 : need;
+        const int *knn = d_knn_idx;
+        const uint32_t *ww = (const uint32_t *)dw;
+        cpword *cp = s->cp;
+        int nn = s->n, kk = k, fo = free_only, mr = max_sweeps;
+        int *fa = s->frontier, *fb = s->frontier + s->capacity, *st = s->children, *cn = s->counters;
+        void *args[] = {&knn, &ww, &nn, &kk, &fo, &cp, &fa, &fb, &st, &cn, &mr};
+        RTPP_CK(ctx, cudaLaunchCooperativeKernel((void *)relax_worklist_kernel, dim3(blocks), dim3(256), args, 0, ctx->stream));
+        ctx->launches++;
+        RTPP_CK(ctx, cudaMemcpyAsync(&sweeps, s->counters + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
         RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (!changed) break;
     }
     if (sweeps_done) *sweeps_done = sweeps;
     return RTPP_OK;
