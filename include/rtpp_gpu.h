@@ -293,7 +293,8 @@ RTPP_API int rtpp_cdrt_set_rand(rtpp_cdrt_engine *e, int inst, const int32_t *ra
 RTPP_API int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path);
 /* 24 int64 per instance: node ids used, agent id, agent island, clock reads, rand_pos, rand_exhausted, |eQr|,
  * |largerSet| list, |smallerSet| list, cut-line samples left, islands with a kd-tree, status, pops, rewired,
- * sampled, pushes, edge checks, path length, path collision, path cost (binary64 bits) */
+ * sampled, pushes, edge checks, path length, path collision, path cost (binary64 bits), SM cycles of the last tick spent in
+ * {environment + tree update, larger/smaller sets, sampling, eQr loop} */
 RTPP_API int rtpp_cdrt_read_stats(rtpp_cdrt_engine *e, long long *out24);
 /* nodes by id, erased ones included (alive = 0); parent -1 = none; invM as CDRT.h:226-228 */
 RTPP_API int rtpp_cdrt_read_tree(rtpp_cdrt_engine *e, int inst, int max_nodes, double *xy, int32_t *parent, double *cost,

@@ -667,7 +667,8 @@ class CdrtEngine:
     `amap`/`imap`: the two 16-bit id planes of DrawBImap; `apl` = the region (graph index) the agents live in."""
 
     STAT = ["n_ids", "agent_id", "island", "clock_reads", "rand_pos", "rand_exhausted", "queue", "larger", "smaller", "samples_left",
-            "n_trees", "status", "pops", "rewired", "sampled", "pushes", "edge_checks", "path_len", "path_col", "path_cost_bits"]
+            "n_trees", "status", "pops", "rewired", "sampled", "pushes", "edge_checks", "path_len", "path_col", "path_cost_bits",
+            "cyc_env_tree", "cyc_sets", "cyc_sampling", "cyc_queue"]
 
     def __init__(self, ctx, n_instances, graph, amap, imap, resolution, apl=0, node_capacity=8192, queue_capacity=1 << 20,
                  r_th=10.0, p_th=0.85, nearK=20, RewireN=100, rand_capacity=1 << 20):

@@ -58,6 +58,7 @@ struct CdInst {
     int path_len, path_col;
     double path_cost;
     int n_obs, n_chk;
+    long long t_phase[4]; // SM cycles of the last tick: environment + tree update | larger/smaller sets | sampling | eQr loop
 };
 
 struct CdHdr { // per-tick inputs of one instance
@@ -204,14 +205,9 @@ __device__ bool q_tie_less(const CdI &in, int2 a, int2 b) {
 __device__ __forceinline__ bool q_less(const CdI &in, u64 ka, int2 a, u64 kb, int2 b) {
     return ka < kb || (ka == kb && (a.x != b.x || a.y != b.y) && q_tie_less(in, a, b));
 }
-// warp-collective, uniform arguments
-__device__ void q_push(const CdView &v, CdI &in, u64 key, int S, int E) {
+// warp-collective, uniform arguments: sift the entry up from slot i (slots beyond i may already hold valid entries)
+__device__ void q_sift_up(CdI &in, int i, u64 key, int S, int E) {
     const int lane = threadIdx.x & 31;
-    const int i = in.q_n;
-    if (i >= v.qcap) {
-        in.status = ST_QUEUE_FULL;
-        return;
-    }
     int idx = i, steps = 0;
     while (idx > 0 && steps <= lane) idx = (idx - 1) >> 5, steps++;
     const bool valid = steps == lane + 1; // lane l holds the (l+1)-th ancestor
@@ -231,7 +227,6 @@ __device__ void q_push(const CdView &v, CdI &in, u64 key, int S, int E) {
         const int dst = m == 0 ? i : top;
         in.qkey[dst] = key, in.qse[dst] = make_int2(S, E);
     }
-    in.q_n = i + 1;
     __syncwarp();
 }
 // warp-collective; queue must be non-empty
@@ -390,14 +385,36 @@ __device__ void cd_best_parent(const CdView &v, CdI &in, double px, double py, i
 }
 
 // pushes the qualifying (h, S, E) of a chunk one by one
+// Batched push: the qualifying entries take the next leaf slots; an entry that is not smaller than its slot's parent
+// (the usual case: eQr mostly receives entries far from its head) is final where it lands — one parent load and one
+// coalesced store for the whole chunk; the few that are smaller are sifted up one by one afterwards (ancestor slots
+// only ever decrease, so the entries already placed stay valid).
 __device__ void cd_push_chunk(const CdView &v, CdI &in, bool ok, u64 h, int S, int E) {
-    unsigned bal = __ballot_sync(FULL, ok);
-    while (bal) {
-        const int src = __ffs(bal) - 1;
-        bal &= bal - 1;
-        q_push(v, in, __shfl_sync(FULL, h, src), __shfl_sync(FULL, S, src), __shfl_sync(FULL, E, src));
-        if ((threadIdx.x & 31) == 0) in.g->pushes++;
+    const int lane = threadIdx.x & 31;
+    const unsigned bal = __ballot_sync(FULL, ok);
+    const int cnt = __popc(bal);
+    if (cnt == 0) return;
+    const int n0 = in.q_n;
+    if (n0 + cnt > v.qcap) {
+        in.status = ST_QUEUE_FULL;
+        return;
     }
+    const int pos = n0 + __popc(bal & ((1u << lane) - 1u));
+    bool slow = ok;
+    if (n0 >= 64 && ok) { // (below that a slot's parent could itself be a slot of this chunk)
+        const int par = (pos - 1) >> 5;
+        slow = q_less(in, h, make_int2(S, E), in.qkey[par], in.qse[par]);
+        if (!slow) in.qkey[pos] = h, in.qse[pos] = make_int2(S, E);
+    }
+    in.q_n = n0 + cnt;
+    __syncwarp();
+    unsigned sb = __ballot_sync(FULL, slow);
+    while (sb) {
+        const int src = __ffs(sb) - 1;
+        sb &= sb - 1;
+        q_sift_up(in, __shfl_sync(FULL, pos, src), __shfl_sync(FULL, h, src), __shfl_sync(FULL, S, src), __shfl_sync(FULL, E, src));
+    }
+    if (lane == 0) in.g->pushes += cnt;
 }
 // candidate links of node p against in.xnear[0..m): `larger` = p may get a cheaper parent among them
 // (RTRT_AddPotentialLinks CDRT.cpp:797-830); otherwise p may become their cheaper parent (also the
@@ -852,6 +869,7 @@ __global__ void __launch_bounds__(128) cdrt_tick_kernel(CdView v, long long dt_n
         smaller_old = cd_now(in);
     }
     cd_now(in); // Time0
+    long long tc0 = clock64();
     // (the dynamic plane of this instance was drawn before the launch: RTRT_DrawDObsmap)
     __syncwarp();
     cd_crash_dobs_island(v, in, v.pose + (size_t)w * v.max_obs, v.chk + (size_t)w * v.max_chk, v.chk_obs + (size_t)w * v.max_chk);
@@ -865,6 +883,7 @@ __global__ void __launch_bounds__(128) cdrt_tick_kernel(CdView v, long long dt_n
         if (ag.x != tag.x || ag.y != tag.y) cd_move_agent(v, in);
         if (in.status == ST_OK) cd_update_tree_cost(v, in);
     }
+    long long tc1 = clock64();
     if (in.status == ST_OK) {
         // largerSet (:998-1003)
         const int nl = g->n_larger;
@@ -894,6 +913,7 @@ __global__ void __launch_bounds__(128) cdrt_tick_kernel(CdView v, long long dt_n
             G0(g->n_smaller = 0);
         }
     }
+    long long tc2 = clock64();
     // RewireN samples (:1014-1033)
     for (int s = 0; s < v.RewireN && in.status == ST_OK; s++) {
         int m;
@@ -902,6 +922,7 @@ __global__ void __launch_bounds__(128) cdrt_tick_kernel(CdView v, long long dt_n
         if (lane == 0) g->sampled++;
         cd_links(v, in, x, m, false);
     }
+    long long tc3 = clock64();
     // the eQr loop (:1035-1067)
     if (in.status == ST_OK) {
         const long long t0 = cd_now(in);
@@ -924,8 +945,10 @@ __global__ void __launch_bounds__(128) cdrt_tick_kernel(CdView v, long long dt_n
             cd_add_potential_links(v, in, E, false);
         }
     }
+    long long tc4 = clock64();
     if (do_get_path && in.status == ST_OK) cd_get_path(v, in);
     __syncwarp();
+    if (lane == 0) g->t_phase[0] = tc1 - tc0, g->t_phase[1] = tc2 - tc1, g->t_phase[2] = tc3 - tc2, g->t_phase[3] = tc4 - tc3;
     if (lane == 0) {
         g->agent_id = in.agent_id, g->agent_island = in.agent_island, g->n = in.n, g->q_n = in.q_n;
         g->clk_n = in.clk_n, g->update_old = update_old, g->smaller_old = smaller_old, g->timers_init = 1;
@@ -1392,6 +1415,7 @@ int rtpp_cdrt_read_stats(rtpp_cdrt_engine *e, long long *out24) {
         o[7] = s.n_larger, o[8] = s.n_smaller, o[9] = s.samp_n - s.samp_pos, o[10] = s.n_trees, o[11] = s.status, o[12] = s.pops;
         o[13] = s.rewired, o[14] = s.sampled, o[15] = s.pushes, o[16] = s.checks, o[17] = s.path_len, o[18] = s.path_col;
         memcpy(&o[19], &s.path_cost, 8);
+        for (int k = 0; k < 4; k++) o[20 + k] = s.t_phase[k];
     }
     return RTPP_OK;
 }
@@ -1433,9 +1457,11 @@ int rtpp_cdrt_read_path(rtpp_cdrt_engine *e, int inst, int max_len, double *xy, 
     if (n <= 0 || !xy) return RTPP_OK;
     std::vector<int> ids(n);
     CD_CK(e, cudaMemcpy(ids.data(), e->v.path + (size_t)inst * e->v.path_cap, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    std::vector<double> all(2 * (size_t)g.n); // one copy of the node coordinates, gathered on the host
+    CD_CK(e, cudaMemcpy(all.data(), e->v.xy + (size_t)inst * e->v.cap, (size_t)g.n * 16, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) {
         if (ids[i] == -2) xy[2 * i] = g.goal.x, xy[2 * i + 1] = g.goal.y;
-        else CD_CK(e, cudaMemcpy(xy + 2 * i, e->v.xy + (size_t)inst * e->v.cap + ids[i], 16, cudaMemcpyDeviceToHost));
+        else xy[2 * i] = all[2 * (size_t)ids[i]], xy[2 * i + 1] = all[2 * (size_t)ids[i] + 1];
     }
     return RTPP_OK;
 }
