@@ -210,8 +210,8 @@ RTPP_API int rtpp_engine_tick(rtpp_engine *e, int do_update_tree, long run_ms, l
  * DiffusivityMetric :94-116, choose-parent), RewireRoot :483-519 } under the virtual clock (run_ms > 0
  * enables the loop; its budgets are the reference's 80 / 20 / 5 ms), and GetPath :310-351.  rand() is
  * consumed on the device from an injected stream (`max_samples` of rtpp_engine_create = draws per
- * instance and call).  RewireGoal (:521-585) is only reachable when the goal point itself becomes a
- * tree node; that is reported as status 3 and not run. */
+ * instance and call).  RewireGoal (:521-585) runs, as in the reference, only while the goal point itself is a
+ * collision-free tree node (a caller can put the goal onto a node; Expand never does). */
 RTPP_API int rtpp_engine_set_diffusion(rtpp_engine *e, const int32_t *cells_ij, int ncells, const float *matrix, int dim,
                                        float ratio);
 /* rand: n_inst rows of `max_samples` raw rand() values, n_rand[i] valid; ellipse: 6 floats per instance
@@ -219,8 +219,8 @@ RTPP_API int rtpp_engine_set_diffusion(rtpp_engine *e, const int32_t *cells_ij, 
  * (AMRRT.cpp:418-432; host glibc); outpath_nonempty: OutPath.size() != 0.  NULL = unchanged. */
 RTPP_API int rtpp_engine_set_am_inputs(rtpp_engine *e, const int32_t *rand, const int32_t *n_rand, const float *ellipse,
                                        const int32_t *outpath_nonempty);
-/* 16 int64 per instance: n_nodes, root, samples_used, clock_reads, iterations, pops_r, pops_s,
- * qr_size, qs_size, status (0 ok, 1 node store full, 2 queue overflow, 3 RewireGoal needed),
+/* 16 int64 per instance: n_nodes, root, samples_used, clock_reads, iterations, pops_r (AM-RRT*: RewireGoal pops), pops_s,
+ * qr_size (AM-RRT*: |Sgoal| + |Qgoal|), qs_size, status (0 ok, 1 node store full, 2 queue overflow),
  * path_len, path_collision, path_cost (float bits), c_base (float bits), rand_pos, rand_exhausted */
 RTPP_API int rtpp_engine_read_stats(rtpp_engine *e, long long *out16);
 RTPP_API int rtpp_engine_read_tree(rtpp_engine *e, int inst, int max_nodes, float *xy, int32_t *parent, float *cost,

@@ -41,6 +41,8 @@ struct EngInst {
     float path_cost;
     // AM-RRT* (planner_kind 2): injected rand() stream position and the informed-sampler ellipse
     int rand_pos, rand_n, rand_exhausted, outpath_nonempty;
+    int goal_node;                          // id of the tree node that IS the goal point (Node_Map.find(goal), AMRRT.cpp:606), -1 = none
+    int gs_top, gq_head, gq_tail, g_epoch;  // RewireGoal: Sgoal (stack), Qgoal (FIFO), seen_goal (epoch marks)
     float ell_a, ell_b, ell_cos, ell_sin, ell_mx, ell_my;
 };
 
@@ -54,6 +56,7 @@ struct EngView {
     int *qr, *qs, *qs_mark;
     int *child_start, *children, *frontier;
     int *nn_ids, *nn_n; // cached 25-NN list of every tree node (ids) and the node count it was computed for (0 = none)
+    int *gs, *gq, *g_mark; // AM-RRT* RewireGoal: Sgoal stack, Qgoal queue, seen_goal marks [cap each]
     float2 *samples;
     int *path;
     PlaneView planes[16]; // merged S|D plane per map slot
@@ -89,7 +92,7 @@ struct Inst {
     EngInst s; // register copy, uniform across the warp
     float2 *xy, *sxy;
     cpword *cp;
-    int *sid, *cell_of, *cell_start, *cursor, *qr, *qs, *qs_mark, *child_start, *children, *frontier, *nn_ids, *nn_n;
+    int *sid, *cell_of, *cell_start, *cursor, *qr, *qs, *qs_mark, *child_start, *children, *frontier, *nn_ids, *nn_n, *gs, *gq, *g_mark;
     const float2 *samples;
     int *path;
     PlaneView pl;
@@ -477,9 +480,9 @@ __device__ void get_path(const EngView &ev, Inst &in, const MarchThresholds &mt)
 //   :598-613, DiffusivityMetric :94-116, CrashDetectionStart :287-308, GetPath :310-351.
 // rand() is consumed on the device from the injected stream (its consumption depends on the tree);
 // cosf32/sinf32 of the drawn angles are host-tabulated per stream position so that the glibc
-// results are used bit for bit.  RewireGoal (:521-585) runs only when the goal point itself is a
-// tree node — unreachable through Expand (the goal-bias branch :402-403 never breaks) — and is
-// reported as status 3 instead of being run.
+// results are used bit for bit.  RewireGoal (:521-585) runs only while the goal point itself is a
+// collision-free tree node — Expand cannot put it there (the goal-bias branch :402-403 never breaks), a caller
+// who sets the goal onto an existing node can.
 // =============================================================================================
 __device__ __forceinline__ int am_rand(Inst &in) { // orc::RandStream::next
     if (in.s.rand_pos >= in.s.rand_n) {
@@ -670,8 +673,7 @@ __device__ void am_expand(const EngView &ev, Inst &in, const MarchThresholds &mt
     in.s.n = id + 1;
     __syncwarp();
     maybe_rebuild(ev, in);
-    // MainTask would now call RewireGoal (AMRRT.cpp:604-612: the goal point is a collision-free node)
-    if (x_new.x == in.s.goal.x && x_new.y == in.s.goal.y) in.s.status = 3;
+    if (x_new.x == in.s.goal.x && x_new.y == in.s.goal.y) in.s.goal_node = id; // Node_Map.find(goal) now succeeds (AMRRT.cpp:606)
 }
 
 // RewireRoot (AMRRT.cpp:483-519): Qroot / rewired_root reuse the Qs arrays and epoch marks
@@ -715,12 +717,86 @@ __device__ void am_rewire_root(const EngView &ev, Inst &in, const MarchThreshold
     }
 }
 
+// RewireGoal (AMRRT.cpp:521-585): depth-first from the root through the informed ellipse, each node's 25 neighbours
+// visited in ascending DiffusivityMetric(goal, .) order (std::priority_queue of (float, RTpoint) pairs: ties by point).
+// Sgoal is a stack (push_front / pop_front), Qgoal a FIFO, seen_goal an epoch mark.  Runs only while the goal point
+// itself is a collision-free tree node.
+__device__ void am_rewire_goal(const EngView &ev, Inst &in, const MarchThresholds &mt, long long dt) {
+    const int lane = threadIdx.x & 31;
+    if (in.s.gq_head == in.s.gq_tail && in.s.gs_top == 0) {
+        in.s.g_epoch++; // seen_goal.clear()
+        in.s.gq_head = in.s.gq_tail = 0;
+        if (lane == 0) in.gs[0] = in.s.root;
+        in.s.gs_top = 1;
+        __syncwarp();
+    }
+    const float2 g = in.s.goal, rt = in.xy[in.s.root];
+    const long long t0 = clk_now(in, dt);
+    while (clk_now(in, dt) - t0 < 100000000LL && (in.s.gs_top > 0 || in.s.gq_head != in.s.gq_tail)) {
+        int xr;
+        if (in.s.gs_top > 0) xr = in.gs[--in.s.gs_top];
+        else xr = in.gq[in.s.gq_head++];
+        in.s.pops_r++; // (AM-RRT* has no Qr: the slot counts RewireGoal pops)
+        const float2 pr = in.xy[xr];
+        if (__fadd_rn(rt_dist(rt.x, rt.y, pr.x, pr.y), rt_dist(g.x, g.y, pr.x, pr.y)) <= in.s.c_base) {
+            KnnEntry e;
+            const int found = knn_at_node(ev, in, xr, e);
+            float dk = 0.f;
+            float2 q = make_float2(0.f, 0.f);
+            bool free_edge = false;
+            if (lane < found) {
+                q = in.xy[e.id];
+                dk = am_diffusivity(ev, g.x, g.y, q.x, q.y);
+                free_edge = !rt_edge_blocked(in.pl, q.x, q.y, pr.x, pr.y, mt); // CrashDetection(x_near, x_r)
+                if (free_edge) {
+                    const uint32_t c_new = cost_add(cp_hi(in.cp[xr]), cost_pack(false, rt_dist(q.x, q.y, pr.x, pr.y)));
+                    if (c_new < cp_hi(in.cp[e.id]) && !cost_col(c_new)) in.cp[e.id] = cp_make(c_new, xr);
+                }
+            }
+            __syncwarp();
+            const bool fresh = free_edge && in.g_mark[e.id] != in.s.g_epoch;
+            // position of a fresh neighbour in X_next = number of fresh neighbours that sort before it
+            int before = 0;
+            for (int m = 0; m < found; m++) {
+                const float odk = __shfl_sync(FULL, dk, m), ox = __shfl_sync(FULL, q.x, m), oy = __shfl_sync(FULL, q.y, m);
+                const bool of = __shfl_sync(FULL, fresh, m);
+                const bool less = odk < dk || (odk == dk && (ox != q.x ? ox < q.x : oy < q.y));
+                before += of && less;
+            }
+            const int cnt = __popc(__ballot_sync(FULL, fresh));
+            if (fresh) {
+                in.g_mark[e.id] = in.s.g_epoch;
+                in.gs[in.s.gs_top + before] = e.id; // push_front in X_next order: the last one ends on top
+                in.gq[in.s.gq_tail + before] = e.id;
+            }
+            in.s.gs_top += cnt, in.s.gq_tail += cnt;
+            __syncwarp();
+        }
+        if (in.s.gs_top > 0) {
+            const float2 f = in.xy[in.gs[in.s.gs_top - 1]];
+            if (am_diffusivity(ev, f.x, f.y, g.x, g.y) > am_diffusivity(ev, pr.x, pr.y, g.x, g.y)) in.s.gs_top = 0; // Sgoal.clear()
+        }
+    }
+}
+
 // MainTask loop (AMRRT.cpp:598-613) after UpdateTree
 __device__ void am_main_loop(const EngView &ev, Inst &in, const MarchThresholds &mt, long long dt) {
+    // Node_Map.find(goal): the goal may have been moved onto (or off) a tree node since the last tick
+    {
+        const int lane = threadIdx.x & 31;
+        int hit = -1;
+        if (in.s.goal.x >= 0.0f)
+            for (int i = lane; i < in.s.n; i += 32) {
+                const float2 p = in.xy[i];
+                if (p.x == in.s.goal.x && p.y == in.s.goal.y) hit = i;
+            }
+        in.s.goal_node = __reduce_max_sync(FULL, hit);
+    }
     const long long t0 = clk_now(in, dt);
     while (clk_now(in, dt) - t0 < 80000000LL && !in.s.rand_exhausted && !in.s.status) {
         am_expand(ev, in, mt, dt);
         am_rewire_root(ev, in, mt, dt);
+        if (in.s.goal.x >= 0.0f && in.s.goal_node >= 0 && !cost_col(cp_hi(in.cp[in.s.goal_node]))) am_rewire_goal(ev, in, mt, dt);
     }
 }
 
@@ -784,6 +860,7 @@ __device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
     in.child_start = ev.child_start + (size_t)w * (ev.cap + 1), in.children = ev.children + c;
     in.frontier = ev.frontier + 2 * c;
     in.nn_ids = ev.nn_ids + 25 * c, in.nn_n = ev.nn_n + c;
+    in.gs = ev.gs ? ev.gs + c : nullptr, in.gq = ev.gq ? ev.gq + c : nullptr, in.g_mark = ev.g_mark ? ev.g_mark + c : nullptr;
     in.samples = ev.samples + (size_t)w * ev.max_samples;
     in.path = ev.path + (size_t)w * ev.path_cap;
     in.pl = ev.planes[in.s.map_slot & 15];
@@ -824,6 +901,7 @@ __global__ void engine_init_kernel(EngView ev, const int *__restrict__ slots, co
     s.c_base = -1.0f;
     s.n = 1, s.n_sorted = 0, s.root = 0;
     s.shift = ev.shift, s.gw = ev.gw, s.gh = ev.gh;
+    s.goal_node = -1;
     s.path_col = 1, s.path_cost = 3.4e38f;
     ev.xy[(size_t)w * ev.cap] = agent[w];
     ev.cp[(size_t)w * ev.cap] = cp_make(cost_pack(false, 0.0f), -1);
@@ -911,6 +989,7 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
     rc |= eng_alloc(e, &v.frontier, 2 * C);
     rc |= eng_alloc(e, &v.nn_ids, 25 * C);
     rc |= eng_alloc(e, &v.nn_n, C);
+    if (planner_kind == 2) rc |= eng_alloc(e, &v.gs, C), rc |= eng_alloc(e, &v.gq, C), rc |= eng_alloc(e, &v.g_mark, C);
     rc |= eng_alloc(e, &v.samples, planner_kind == 1 ? N * max_samples : 1);
     if (planner_kind == 2) { // max_samples = rand() draws available per instance and call
         v.rand_cap = max_samples;
@@ -931,7 +1010,7 @@ int rtpp_engine_destroy(rtpp_engine *e) {
     cudaFree(v.inst), cudaFree(v.xy), cudaFree(v.sxy), cudaFree(v.cp), cudaFree(v.sid), cudaFree(v.cell_of);
     cudaFree(v.cell_start), cudaFree(v.cursor), cudaFree(v.qr), cudaFree(v.qs), cudaFree(v.qs_mark);
     cudaFree(v.child_start), cudaFree(v.children), cudaFree(v.frontier), cudaFree(v.samples), cudaFree(v.path);
-    cudaFree(v.nn_ids), cudaFree(v.nn_n);
+    cudaFree(v.nn_ids), cudaFree(v.nn_n), cudaFree(v.gs), cudaFree(v.gq), cudaFree(v.g_mark);
     for (int i = 0; i < 16; i++) cudaFree(e->plane_s[i]), cudaFree(e->plane_d[i]), cudaFree(e->plane_sd[i]);
     cudaFree(e->d_rand), cudaFree(e->d_rand_cs), cudaFree(e->d_diff_cell), cudaFree(e->d_diff_rows);
     delete e;
@@ -1126,7 +1205,8 @@ int rtpp_engine_read_stats(rtpp_engine *e, long long *out16) {
         uint32_t pc, cb;
         memcpy(&pc, &s[i].path_cost, 4), memcpy(&cb, &s[i].c_base, 4);
         o[0] = s[i].n, o[1] = s[i].root, o[2] = s[i].samp_pos, o[3] = s[i].clk_n, o[4] = s[i].iters, o[5] = s[i].pops_r;
-        o[6] = s[i].pops_s, o[7] = s[i].qr_tail - s[i].qr_head, o[8] = s[i].qs_tail - s[i].qs_head, o[9] = s[i].status;
+        o[6] = s[i].pops_s, o[7] = e->v.kind == 2 ? s[i].gs_top + (s[i].gq_tail - s[i].gq_head) : s[i].qr_tail - s[i].qr_head;
+        o[8] = s[i].qs_tail - s[i].qs_head, o[9] = s[i].status;
         o[10] = s[i].path_len, o[11] = s[i].path_col, o[12] = pc, o[13] = cb, o[14] = s[i].rand_pos, o[15] = s[i].rand_exhausted;
     }
     return RTPP_OK;

@@ -118,3 +118,51 @@ def test_am_engine_informed_sampling_against_oracle(ctx, oracle):
         informed += int(found)
     assert informed >= 5
     eng.close()
+
+
+def test_am_engine_rewire_goal_when_the_goal_is_a_tree_node(ctx, oracle):
+    """RewireGoal (AMRRT.cpp:521-585) only runs while the goal point itself is a collision-free tree node, which Expand
+    never produces but a caller can: after a few ticks the goal is moved onto an existing node.  Engine vs oracle,
+    tick by tick (trees, rand() position), and the goal stack / queue must have been in use."""
+    import rtpp_b200
+    from helpers import synthetic_diffusion
+
+    S = oracle.load_map("MESS6")
+    H, W = S.shape
+    cap_rand = 200_000
+    agent, goal = (720.0, 720.0), (1240.0, 1240.0)
+    eng = rtpp_b200.Engine(ctx, 1, 8192, 5, W, H, cap_rand, kind=2)
+    eng.set_map(0, 1, S)
+    cells, mat, ratio = synthetic_diffusion(W)
+    eng.set_diffusion(cells, mat, ratio)
+    eng.init_instances(np.zeros(1, np.int32), np.array([agent], np.float32), np.array([goal], np.float32))
+    orc = oracle.OrcAMRRT(S)
+    orc.set_diffusion(cells, mat, ratio)
+    r = oracle.rand31(77, 3_000_000)
+    orc.set_rand(r)
+    orc.set_clock(500000, 0)
+    orc.set_agent(*agent)
+    orc.set_goal(*goal)
+    pos, used = 0, 0
+    for tick in range(16):
+        if tick == 5:  # move the goal onto a node far from the root
+            xy, _, _, col = eng.read_tree(0)
+            d2 = ((xy - np.array(agent, np.float32)) ** 2).sum(1)
+            j = int(np.argmax(np.where(col == 0, d2, -1.0)))  # a collision-free node far from the root
+            orc.set_goal(float(xy[j, 0]), float(xy[j, 1]))
+            eng.set_inputs(goal_xy=xy[j: j + 1])
+        chunk = np.zeros((1, cap_rand), np.int32)
+        chunk[0] = r[pos: pos + cap_rand]
+        eng.set_am_inputs(rand=chunk, n_rand=np.array([cap_rand], np.int32), outpath_nonempty=np.zeros(1, np.int32))
+        eng.tick(update_tree=True, run_ms=80, dt_ns=500000, get_path=True)
+        orc.main_task()
+        opath, ocol, ocost = orc.get_path()
+        d = dict(zip(eng.STAT, eng.stats()[0].tolist()))
+        pos += d["rand_pos"]
+        assert d["status"] == 0 and pos == orc.rand_pos(), f"tick {tick}"
+        for x, y in zip(orc.dump(), eng.read_tree(0)):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"tick {tick}"
+        assert bool(d["path_col"]) == ocol and np.float32(orc.c_base()).view(np.uint32) == np.uint32(d["c_base_bits"])
+        used = d["pops_r"]
+    assert used > 100  # nodes popped from Sgoal / Qgoal: RewireGoal ran
+    eng.close()
