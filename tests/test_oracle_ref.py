@@ -93,3 +93,50 @@ def test_amrrt_live_with_informed_sampling(oracle):
         for x, y in zip(ref.dump(), orc.dump()):
             assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
     assert informed >= 5
+
+
+def test_amrrt_live_rewire_goal(oracle):
+    """RewireGoal (AMRRT.cpp:521-585) only runs while the goal point itself is a collision-free tree node — Expand
+    never makes it one, a caller can.  After a few ticks the goal is moved onto an existing node: the oracle's
+    RewireGoal against the compiled reference (trees bit for bit, same rand() consumption, same clock reads)."""
+    from helpers import synthetic_diffusion
+
+    S = oracle.load_map("MESS6")
+    ref, orc = oracle.RefAMRRT(S), oracle.OrcAMRRT(S)
+    cells, mat, ratio = synthetic_diffusion(S.shape[1])
+    r = oracle.rand31(77, 3_000_000)
+    for p in (ref, orc):
+        p.set_diffusion(cells, mat, ratio)
+        p.set_rand(r)
+        p.set_clock(500000, 0)
+        p.set_agent(720.0, 720.0)
+        p.set_goal(1240.0, 1240.0)
+    moved = False
+    for tick in range(16):
+        if tick == 5:
+            xy, _, _, col = orc.dump()
+            d2 = ((xy - np.array([720.0, 720.0], np.float32)) ** 2).sum(1)
+            j = int(np.argmax(np.where(col == 0, d2, -1.0)))
+            for p in (ref, orc):
+                p.set_goal(float(xy[j, 0]), float(xy[j, 1]))
+            moved = True
+        for p in (ref, orc):
+            p.main_task()
+        rp, op = ref.get_path(), orc.get_path()
+        assert np.array_equal(rp[0], op[0]) and rp[1:] == op[1:]
+        assert ref.rand_pos() == orc.rand_pos()
+        for x, y in zip(ref.dump(), orc.dump()):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"tick {tick}"
+    assert moved and ref.L.ref_clock_reads() > 0
+    # witness that RewireGoal ran and rewired: without the goal on a node the same stream grows a different tree
+    ctl = oracle.OrcAMRRT(S)
+    ctl.set_diffusion(cells, mat, ratio)
+    ctl.set_rand(r)
+    ctl.set_clock(500000, 0)
+    ctl.set_agent(720.0, 720.0)
+    ctl.set_goal(1240.0, 1240.0)
+    for tick in range(16):
+        ctl.main_task()
+        ctl.get_path()
+    a, b = orc.dump(), ctl.dump()
+    assert len(a[0]) != len(b[0]) or any(not np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(a, b))
