@@ -56,6 +56,8 @@ struct EngView {
     int *qr, *qs, *qs_mark;
     int *child_start, *children, *frontier;
     int *nn_ids, *nn_n; // cached 25-NN list of every tree node (ids) and the node count it was computed for (0 = none)
+    int *nn_blk, *nn_blk_ep; // cached verdict bits of the edges node <-> its cached neighbours, and the plane epoch they hold for
+    int plane_epoch[16];     // bumped whenever a plane of the map slot changes
     int *gs, *gq, *g_mark; // AM-RRT* RewireGoal: Sgoal stack, Qgoal queue, seen_goal marks [cap each]
     float2 *samples;
     int *path;
@@ -93,6 +95,8 @@ struct Inst {
     float2 *xy, *sxy;
     cpword *cp;
     int *sid, *cell_of, *cell_start, *cursor, *qr, *qs, *qs_mark, *child_start, *children, *frontier, *nn_ids, *nn_n, *gs, *gq, *g_mark;
+    int *nn_blk, *nn_blk_ep;
+    int pl_epoch;
     const float2 *samples;
     int *path;
     PlaneView pl;
@@ -176,13 +180,39 @@ __device__ __forceinline__ int knn_at_node(const EngView &ev, Inst &in, int x, K
             e.d2 = knn_d2((double)px.x, (double)px.y, q.x, q.y);
         }
         if (in.s.n == n0) return cnt;
+        const int old_id = e.id;
         found = knn_warp_impl(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e, cnt, n0);
+        if (__all_sync(FULL, e.id == old_id)) { // no appended node entered the list: the cached edge verdicts stay valid
+            if (lane == 0) in.nn_n[x] = in.s.n;
+            __syncwarp();
+            return found;
+        }
     } else
         found = knn_warp(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e);
     if (lane < found) in.nn_ids[(size_t)x * 25 + lane] = e.id;
-    if (lane == 0) in.nn_n[x] = in.s.n;
+    if (lane == 0) in.nn_n[x] = in.s.n, in.nn_blk_ep[x] = -1;
     __syncwarp();
     return found;
+}
+
+// Verdicts of the edges between tree node x and its cached neighbours (lane j = j-th neighbour), from_x = true for
+// CrashDetection(x, neighbour) (RT-RRT*, RTRRT.cpp:310,339), false for CrashDetection(neighbour, x) (AM-RRT*,
+// AMRRT.cpp:500,556; an engine is one kind, so the cached bits have one orientation).  A verdict is a pure function of
+// the planes and the two points: it is kept per node until a plane of the map slot changes (epoch) or the node's
+// neighbour list does — a node is popped many times per tick, so most pops find their 25 verdicts ready.
+__device__ __forceinline__ bool edges_at_node(const EngView &ev, Inst &in, const MarchThresholds &mt, int x, const KnnEntry &e, int found,
+                                              bool from_x) {
+    const int lane = threadIdx.x & 31;
+    if (in.nn_blk_ep[x] == in.pl_epoch) return (in.nn_blk[x] >> lane) & 1;
+    bool blk = false;
+    if (lane < found) {
+        const float2 px = in.xy[x], q = in.xy[e.id];
+        blk = from_x ? rt_edge_blocked(in.pl, px.x, px.y, q.x, q.y, mt) : rt_edge_blocked(in.pl, q.x, q.y, px.x, px.y, mt);
+    }
+    const unsigned bits = __ballot_sync(FULL, blk);
+    if (lane == 0) in.nn_blk[x] = (int)bits, in.nn_blk_ep[x] = in.pl_epoch;
+    __syncwarp();
+    return blk;
 }
 
 // virtual clock: the k-th read returns k*dt (orc::VClock)
@@ -350,10 +380,11 @@ __device__ __forceinline__ bool relax_neighbours(const EngView &ev, Inst &in, co
     const int lane = threadIdx.x & 31;
     const float2 px = in.xy[x];
     found = knn_at_node(ev, in, x, e);
+    const bool blk = edges_at_node(ev, in, mt, x, e, found, true);
     bool improved = false;
     if (lane < found) {
         const float2 q = in.xy[e.id];
-        const uint32_t w = cost_pack(rt_edge_blocked(in.pl, px.x, px.y, q.x, q.y, mt), rt_dist(px.x, px.y, q.x, q.y));
+        const uint32_t w = cost_pack(blk, rt_dist(px.x, px.y, q.x, q.y));
         const uint32_t c_new = cost_add(cp_hi(in.cp[x]), w);
         if (c_new < cp_hi(in.cp[e.id])) {
             in.cp[e.id] = cp_make(c_new, x);
@@ -696,10 +727,11 @@ __device__ void am_rewire_root(const EngView &ev, Inst &in, const MarchThreshold
         const float2 pr = in.xy[xr];
         KnnEntry e;
         const int found = knn_at_node(ev, in, xr, e);
+        const bool blk = edges_at_node(ev, in, mt, xr, e, found, false); // CrashDetection(x_near, x_r)
         bool free_edge = false;
         if (lane < found) {
             const float2 q = in.xy[e.id];
-            free_edge = !rt_edge_blocked(in.pl, q.x, q.y, pr.x, pr.y, mt); // CrashDetection(x_near, x_r)
+            free_edge = !blk;
             if (free_edge) {
                 const uint32_t c_new = cost_add(cp_hi(in.cp[xr]), cost_pack(false, rt_dist(q.x, q.y, pr.x, pr.y)));
                 if (c_new < cp_hi(in.cp[e.id]) && !cost_col(c_new)) in.cp[e.id] = cp_make(c_new, xr);
@@ -741,13 +773,14 @@ __device__ void am_rewire_goal(const EngView &ev, Inst &in, const MarchThreshold
         if (__fadd_rn(rt_dist(rt.x, rt.y, pr.x, pr.y), rt_dist(g.x, g.y, pr.x, pr.y)) <= in.s.c_base) {
             KnnEntry e;
             const int found = knn_at_node(ev, in, xr, e);
+            const bool blk = edges_at_node(ev, in, mt, xr, e, found, false); // CrashDetection(x_near, x_r)
             float dk = 0.f;
             float2 q = make_float2(0.f, 0.f);
             bool free_edge = false;
             if (lane < found) {
                 q = in.xy[e.id];
                 dk = am_diffusivity(ev, g.x, g.y, q.x, q.y);
-                free_edge = !rt_edge_blocked(in.pl, q.x, q.y, pr.x, pr.y, mt); // CrashDetection(x_near, x_r)
+                free_edge = !blk;
                 if (free_edge) {
                     const uint32_t c_new = cost_add(cp_hi(in.cp[xr]), cost_pack(false, rt_dist(q.x, q.y, pr.x, pr.y)));
                     if (c_new < cp_hi(in.cp[e.id]) && !cost_col(c_new)) in.cp[e.id] = cp_make(c_new, xr);
@@ -860,10 +893,12 @@ __device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
     in.child_start = ev.child_start + (size_t)w * (ev.cap + 1), in.children = ev.children + c;
     in.frontier = ev.frontier + 2 * c;
     in.nn_ids = ev.nn_ids + 25 * c, in.nn_n = ev.nn_n + c;
+    in.nn_blk = ev.nn_blk + c, in.nn_blk_ep = ev.nn_blk_ep + c;
     in.gs = ev.gs ? ev.gs + c : nullptr, in.gq = ev.gq ? ev.gq + c : nullptr, in.g_mark = ev.g_mark ? ev.g_mark + c : nullptr;
     in.samples = ev.samples + (size_t)w * ev.max_samples;
     in.path = ev.path + (size_t)w * ev.path_cap;
     in.pl = ev.planes[in.s.map_slot & 15];
+    in.pl_epoch = ev.plane_epoch[in.s.map_slot & 15];
     in.rand_stream = ev.rand_stream ? ev.rand_stream + (size_t)w * ev.rand_cap : nullptr;
     in.rand_cs = ev.rand_cs ? ev.rand_cs + (size_t)w * ev.rand_cap : nullptr;
     return true;
@@ -989,6 +1024,7 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
     rc |= eng_alloc(e, &v.frontier, 2 * C);
     rc |= eng_alloc(e, &v.nn_ids, 25 * C);
     rc |= eng_alloc(e, &v.nn_n, C);
+    rc |= eng_alloc(e, &v.nn_blk, C), rc |= eng_alloc(e, &v.nn_blk_ep, C);
     if (planner_kind == 2) rc |= eng_alloc(e, &v.gs, C), rc |= eng_alloc(e, &v.gq, C), rc |= eng_alloc(e, &v.g_mark, C);
     rc |= eng_alloc(e, &v.samples, planner_kind == 1 ? N * max_samples : 1);
     if (planner_kind == 2) { // max_samples = rand() draws available per instance and call
@@ -1010,7 +1046,7 @@ int rtpp_engine_destroy(rtpp_engine *e) {
     cudaFree(v.inst), cudaFree(v.xy), cudaFree(v.sxy), cudaFree(v.cp), cudaFree(v.sid), cudaFree(v.cell_of);
     cudaFree(v.cell_start), cudaFree(v.cursor), cudaFree(v.qr), cudaFree(v.qs), cudaFree(v.qs_mark);
     cudaFree(v.child_start), cudaFree(v.children), cudaFree(v.frontier), cudaFree(v.samples), cudaFree(v.path);
-    cudaFree(v.nn_ids), cudaFree(v.nn_n), cudaFree(v.gs), cudaFree(v.gq), cudaFree(v.g_mark);
+    cudaFree(v.nn_ids), cudaFree(v.nn_n), cudaFree(v.nn_blk), cudaFree(v.nn_blk_ep), cudaFree(v.gs), cudaFree(v.gq), cudaFree(v.g_mark);
     for (int i = 0; i < 16; i++) cudaFree(e->plane_s[i]), cudaFree(e->plane_d[i]), cudaFree(e->plane_sd[i]);
     cudaFree(e->d_rand), cudaFree(e->d_rand_cs), cudaFree(e->d_diff_cell), cudaFree(e->d_diff_rows);
     delete e;
@@ -1048,6 +1084,7 @@ int rtpp_engine_set_map(rtpp_engine *e, int slot, int plane, const uint8_t *src,
     engine_merge_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
     RTPP_LAUNCHED(ctx);
     ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    e->v.plane_epoch[slot]++; // cached edge verdicts of this slot's instances are stale now
     e->v.planes[slot].w = e->plane_sd[slot];
     e->v.planes[slot].W = W, e->v.planes[slot].H = H, e->v.planes[slot].tilesX = tilesX;
     return RTPP_OK;
