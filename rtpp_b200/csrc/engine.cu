@@ -906,7 +906,7 @@ __device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
 
 // one instantiation per planner kind: the register allocation of one planner's loop is not paid by the other
 template <int KIND>
-__global__ void __launch_bounds__(128) engine_tick_kernel(EngView ev, MarchThresholds mt, int do_update, long long run_ns,
+__global__ void __launch_bounds__(128, KIND == 1 ? 4 : 1) engine_tick_kernel(EngView ev, MarchThresholds mt, int do_update, long long run_ns,
                                                                           long long dt, int do_path) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Inst in;
