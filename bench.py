@@ -375,6 +375,11 @@ def main():
     e2e["explicit_edge_list"] = {"value": wl.n_edges / ((time.perf_counter() - t0) / 5), "h2d_bytes_per_step": wl.n_edges * 16,
                                  "api": "rtpp_edges_check (host buffers, pinned)", "per_rank": True}
 
+    # ---- BASELINE configs[4]: the scenario sweep, sharded by instance id over the ranks (all ranks take part)
+    sweep = None
+    if not args.no_extras:
+        sweep = measure_sweep(ctx, rank, world, torch, dist, wl.dev)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -417,7 +422,7 @@ def main():
 
     extras = {}
     if not args.no_extras:
-        extras = measure_extras(wl, torch)
+        extras = measure_extras(wl, torch, sweep)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -430,7 +435,7 @@ def main():
     return 0
 
 
-def measure_extras(wl, torch):
+def measure_extras(wl, torch, sweep):
     """Neighbour queries/s and tick latencies on the resident C4 state (outside the timed region)."""
     ctx = wl.ctx
     out = {}
@@ -462,7 +467,7 @@ def measure_extras(wl, torch):
     torch.cuda.synchronize()
     out["rewire_to_quiescence_ms"] = (time.perf_counter() - t0) * 1e3
     out["rewire_sweeps"] = sweeps
-    out.update(measure_replanning(ctx))
+    out.update(measure_replanning(ctx, sweep))
     out.update(measure_fmt(ctx))
     out.update(measure_cdrt(ctx))
     out.update(measure_amrrt(ctx))
@@ -585,26 +590,57 @@ def measure_fmt(ctx, samples=100_000, iters=20_000):
                           "state_matches_cpu": same}}
 
 
-def measure_replanning(ctx, n_inst=4096, ticks=3, dt=5000):
-    """Replan iterations/s and tick latency: RT-RRT* engine (one warp per planner instance) over the
-    reference's scripted scenarios (8 bundled maps x 4 goals x seeds), against the CPU oracle port of
-    the same loops on all host threads.  One tick = UpdateTree + ExpandRewiring(50 ms) + GetPath under
-    the virtual clock (dt ns per clock read => 50e6/dt = 10^4 queue pops per tick)."""
+def measure_sweep(ctx, rank, world, torch, dist, dev, n_inst=8192, ticks=3, dt=5000, n_samples=2000):
+    """BASELINE configs[4]: 8192 independent RT-RRT* planner instances (8 bundled maps x the reference's scripted
+    start/goal tables x seeds, tools/sweep_bench.py), sharded by instance id round-robin over the ranks (strong
+    scaling: the instance count is fixed).  One tick = UpdateTree + ExpandRewiring(50 ms) + GetPath under the
+    virtual clock (dt ns per clock read => 50e6/dt = 10^4 queue pops per tick).  No data-path collective; the
+    fixed-size per-scenario result records are all-gathered at the end (NCCL), tick time = max over ranks."""
+    import hashlib
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sweep_bench as sb
+    from oracle import loader as orc
+    from rtpp_b200 import shard
+
+    maps = {name: orc.load_map(name) for name in sb.SCEN}
+    inst = sb.make_instances(n_inst, maps)
+    ids = shard.instance_ids(n_inst, rank, world)
+    lat, st, _ = sb.run_gpu(ctx, orc, [inst[i] for i in ids], maps, n_samples, ticks, dt)
+    t = torch.tensor(lat, dtype=torch.float64, device=dev)
+    # record = n_nodes, samples_used, iters, pops_r, pops_s, status, path_len, path_cost_bits
+    rec = torch.from_numpy(np.ascontiguousarray(st[:, [0, 2, 4, 5, 6, 9, 10, 12]])).to(dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rec = shard.all_gather_records(rec, n_inst)
+    lat = t.cpu().numpy()
+    rec = rec.cpu().numpy()
+    tot = float(lat.sum())
+    return {"inst": inst, "maps": maps, "records": rec, "n_samples": n_samples, "ticks": ticks, "dt": dt,
+            "out": {"planner": "RT-RRT*", "instances": n_inst, "n_gpus": world, "sharding": "instance id mod n_gpus; records all-gathered (NCCL)" if world > 1 else "single GPU",
+                    "scaling": "strong", "ticks": ticks, "virtual_dt_ns": dt,
+                    "gpu_planner_ticks_per_s": n_inst * ticks / tot,
+                    "gpu_iters_per_s": float(rec[:, 2].sum() / tot), "gpu_queue_pops_per_s": float((rec[:, 3] + rec[:, 4]).sum() / tot),
+                    "gpu_sweep_tick_ms_p50": float(np.median(lat) * 1e3), "gpu_status_max": int(rec[:, 5].max()),
+                    "nodes_mean": float(rec[:, 0].mean()), "paths_found": int((rec[:, 6] > 0).sum()),
+                    "records_sha256": hashlib.sha256(rec.tobytes()).hexdigest()[:16]}}
+
+
+def measure_replanning(ctx, sweep):
+    """Replan iterations/s and tick latency: the sweep's engine numbers (measure_sweep, all ranks) against the CPU
+    oracle port of the same loops on all host threads over a sample of the same instances (same maps, start/goal,
+    injected sample streams; node counts and stream positions compared), plus the one-planner tick latency."""
     from concurrent.futures import ThreadPoolExecutor
 
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import sweep_bench as sb
     from oracle import loader as orc
 
-    maps = {name: orc.load_map(name) for name in sb.SCEN}
-    inst = sb.make_instances(n_inst, maps)
-    lat, st, samples = sb.run_gpu(ctx, orc, inst, maps, 2000, ticks, dt)
-    tot = sum(lat)
-    out = {"replan": {"planner": "RT-RRT*", "instances": n_inst, "ticks": ticks, "virtual_dt_ns": dt,
-                      "gpu_iters_per_s": float(st[:, 4].sum() / tot), "gpu_queue_pops_per_s": float((st[:, 5] + st[:, 6]).sum() / tot),
-                      "gpu_sweep_tick_ms_p50": float(np.median(lat) * 1e3)}}
+    inst, maps, rec, ticks, dt, n_samples = sweep["inst"], sweep["maps"], sweep["records"], sweep["ticks"], sweep["dt"], sweep["n_samples"]
+    out = {"replan": dict(sweep["out"])}
     threads = os.cpu_count() or 1
-    m = min(n_inst, 2 * threads)
+    m = min(len(inst), 2 * threads)
+    samples = [sb.uniform_samples(orc, inst[k][4], n_samples, maps[inst[k][1]].shape[1], maps[inst[k][1]].shape[0]) for k in range(m)]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         res = list(ex.map(lambda k: sb.run_cpu_instance(orc, maps[inst[k][1]], inst[k][2], inst[k][3], samples[k], ticks, dt), range(m)))
@@ -613,10 +649,11 @@ def measure_replanning(ctx, n_inst=4096, ticks=3, dt=5000):
         "cpu_iters_per_s": sum(r[1]["iters"] for r in res) / wall,
         "cpu_queue_pops_per_s": sum(r[1]["pops_r"] + r[1]["pops_s"] for r in res) / wall,
         "cpu_threads": threads, "cpu_kind": "port (oracle loops, grid k-NN; the reference rebuilds a kd-tree per insert)",
-        "cpu_sample": f"{m} of the {n_inst} instances",
+        "cpu_sample": f"{m} of the {len(inst)} instances",
         "cpu_single_thread_tick_ms_p50": float(np.median([x for r in res for x in r[0]]) * 1e3),
-        "trees_match_gpu": bool(all(res[k][1]["n_nodes"] == int(st[k, 0]) and res[k][1]["samples_used"] == int(st[k, 2]) for k in range(m)))})
-    lat1, st1, _ = sb.run_gpu(ctx, orc, inst[:1], maps, 2000, 9, dt)
+        "trees_match_gpu": bool(all(res[k][1]["n_nodes"] == int(rec[k, 0]) and res[k][1]["samples_used"] == int(rec[k, 1])
+                                    and res[k][1]["iters"] == int(rec[k, 2]) for k in range(m)))})
+    lat1, st1, _ = sb.run_gpu(ctx, orc, inst[:1], maps, n_samples, 9, dt)
     out["replan"]["gpu_single_instance_tick_ms_p50"] = float(np.median(lat1) * 1e3)
     return out
 
