@@ -296,6 +296,9 @@ RTPP_API int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_pat
  * sampled, pushes, edge checks, path length, path collision, path cost (binary64 bits), SM cycles of the last tick spent in
  * {environment + tree update, larger/smaller sets, sampling, eQr loop} */
 RTPP_API int rtpp_cdrt_read_stats(rtpp_cdrt_engine *e, long long *out24);
+/* profiling read-out of one instance's last tick, eQr loop (CDRT.cpp:1035-1067): SM cycles in {pop, entry filter, edge
+ * check, neighbour list, pushes}, then the counts {edge checks, neighbours listed, rewires} */
+RTPP_API int rtpp_cdrt_read_cycles(rtpp_cdrt_engine *e, int inst, long long *out8);
 /* nodes by id, erased ones included (alive = 0); parent -1 = none; invM as CDRT.h:226-228 */
 RTPP_API int rtpp_cdrt_read_tree(rtpp_cdrt_engine *e, int inst, int max_nodes, double *xy, int32_t *parent, double *cost,
                                  uint8_t *collision, int32_t *invM, uint8_t *alive, int *n_out);

@@ -720,6 +720,11 @@ class CdrtEngine:
     def stats_dict(self, inst=0):
         return dict(zip(self.STAT, self.stats()[inst].tolist()))
 
+    def read_cycles(self, inst=0):
+        out = np.zeros(8, np.int64)
+        self.ctx._ck(self.L.rtpp_cdrt_read_cycles(self.h, inst, _p(out)))
+        return dict(zip(["cyc_pop", "cyc_filter", "cyc_check", "cyc_neighbours", "cyc_push", "checks", "neighbours", "rewires"], out.tolist()))
+
     def read_tree(self, inst=0):
         n = C.c_int()
         self.ctx._ck(self.L.rtpp_cdrt_read_tree(self.h, inst, 0, None, None, None, None, None, None, C.byref(n)))

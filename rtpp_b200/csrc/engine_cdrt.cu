@@ -59,6 +59,7 @@ struct CdInst {
     double path_cost;
     int n_obs, n_chk;
     long long t_phase[4]; // SM cycles of the last tick: environment + tree update | larger/smaller sets | sampling | eQr loop
+    long long t_fine[8];  // eQr loop of the last tick: cycles in pop | entry filter | edge check | neighbour list | pushes; edge checks, neighbours listed, rewires
 };
 
 struct CdHdr { // per-tick inputs of one instance
@@ -923,32 +924,48 @@ __global__ void __launch_bounds__(128) cdrt_tick_kernel(CdView v, long long dt_n
         cd_links(v, in, x, m, false);
     }
     long long tc3 = clock64();
+    long long fine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // the eQr loop (:1035-1067)
     if (in.status == ST_OK) {
         const long long t0 = cd_now(in);
         while (in.q_n > 0 && (double)(cd_now(in) - t0) < 20e6 && in.status == ST_OK) {
             u64 key;
             int2 se;
+            const long long f0 = clock64();
             q_pop(v, in, &key, &se);
+            const long long f1 = clock64();
+            fine[0] += f1 - f0;
             if (lane == 0) g->pops++;
             const int S = se.x, E = se.y;
             if (!(in.flag[S] & F_ALIVE) || !(in.flag[E] & F_ALIVE)) continue;
             const double2 sp = in.xy[S], ep = in.xy[E];
             const u64 hat = cw_add(in.cw[S], false, rt_dist64(sp.x, sp.y, ep.x, ep.y));
-            if (!(in.cw[E] > hat)) continue;
+            const bool stale = !(in.cw[E] > hat);
+            const long long f2 = clock64();
+            fine[1] += f2 - f1;
+            if (stale) continue;
             const u64 tc = cw_add(hat, cd_crash(v, in, sp.x, sp.y, in.inv[S], ep.x, ep.y, in.inv[E]), 0.0);
             if (lane == 0) g->checks++;
-            if (!(in.cw[E] > tc)) continue;
+            const bool keep = in.cw[E] > tc;
+            const long long f3 = clock64();
+            fine[2] += f3 - f2, fine[5]++;
+            if (!keep) continue;
             __syncwarp();
             if (lane == 0) in.cw[E] = tc, in.par[E] = S, g->rewired++;
             __syncwarp();
-            cd_add_potential_links(v, in, E, false);
+            const double2 pp = in.xy[E];
+            const int m = cd_neighbors(v, in, pp.x, pp.y, in.inv[E]);
+            const long long f4 = clock64();
+            cd_links(v, in, E, m, false);
+            fine[3] += f4 - f3, fine[4] += clock64() - f4, fine[6] += m, fine[7]++;
         }
     }
     long long tc4 = clock64();
     if (do_get_path && in.status == ST_OK) cd_get_path(v, in);
     __syncwarp();
     if (lane == 0) g->t_phase[0] = tc1 - tc0, g->t_phase[1] = tc2 - tc1, g->t_phase[2] = tc3 - tc2, g->t_phase[3] = tc4 - tc3;
+    if (lane == 0)
+        for (int k = 0; k < 8; k++) g->t_fine[k] = fine[k];
     if (lane == 0) {
         g->agent_id = in.agent_id, g->agent_island = in.agent_island, g->n = in.n, g->q_n = in.q_n;
         g->clk_n = in.clk_n, g->update_old = update_old, g->smaller_old = smaller_old, g->timers_init = 1;
@@ -1417,6 +1434,15 @@ int rtpp_cdrt_read_stats(rtpp_cdrt_engine *e, long long *out24) {
         memcpy(&o[19], &s.path_cost, 8);
         for (int k = 0; k < 4; k++) o[20 + k] = s.t_phase[k];
     }
+    return RTPP_OK;
+}
+// profiling read-out of the last tick's eQr loop (one instance): SM cycles in {pop, entry filter, edge check, neighbour list,
+// pushes}, then the counts {edge checks, neighbours listed, rewires}
+int rtpp_cdrt_read_cycles(rtpp_cdrt_engine *e, int inst, long long *out8) {
+    if (!e || inst < 0 || inst >= e->v.n_inst || !out8) return RTPP_ERR_INVALID;
+    CdInst g;
+    CD_CK(e, cudaMemcpy(&g, e->v.inst + inst, sizeof(g), cudaMemcpyDeviceToHost));
+    memcpy(out8, g.t_fine, sizeof(g.t_fine));
     return RTPP_OK;
 }
 // nodes by id (dead ones included: alive = 0)

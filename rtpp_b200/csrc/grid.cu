@@ -44,10 +44,12 @@ __global__ void __launch_bounds__(256) knn_query_kernel(GridView g, const double
     const int lane = threadIdx.x & 31;
     const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    __shared__ KnnScratch scratch[8];
     for (size_t w = warp0; w < nq; w += nwarps) {
         const double2 qq = q[w];
         KnnEntry e;
-        const int found = knn_warp(g, qq.x, qq.y, k, e);
+        int found = knn_warp_block3(g, qq.x, qq.y, k, e, scratch[threadIdx.x >> 5]);
+        if (found < 0) found = knn_warp(g, qq.x, qq.y, k, e);
         if (lane < k) {
             idx[w * k + lane] = lane < found ? e.id : -1;
             if (d2) d2[w * k + lane] = lane < found ? e.d2 : CUDART_INF;
@@ -56,28 +58,45 @@ __global__ void __launch_bounds__(256) knn_query_kernel(GridView g, const double
     }
 }
 
-// all-kNN of the node set itself (RT-FMT's static table, C4's rewire sweep): warp w takes the
-// w-th node in CELL-SORTED order, so neighbouring warps scan the same cells (L1/L2 reuse), and
-// writes row sid[w] of the table.
+// all-kNN of the node set itself (RT-FMT's static table, C4's rewire sweep): a warp takes batches of
+// KNN_NODES_BATCH consecutive nodes in CELL-SORTED order, so its queries share their 3x3 block of cells
+// (candidates cached in shared memory, knn.cuh), and writes row sid[w] of the table.
+#define KNN_NODES_BATCH 16
 __global__ void __launch_bounds__(256) knn_nodes_kernel(GridView g, int k, int *__restrict__ idx, double *__restrict__ d2) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t w = warp0; w < (size_t)g.n; w += nwarps) {
-        int node;
-        float2 p;
-        if (w < (size_t)g.n_sorted) {
-            node = g.sid[w];
-            p = g.sxy[w];
-        } else {
-            node = (int)w;
-            p = g.xy[w];
-        }
-        KnnEntry e;
-        const int found = knn_warp(g, (double)p.x, (double)p.y, k, e);
-        if (lane < k) {
-            idx[(size_t)node * k + lane] = lane < found ? e.id : -1;
-            if (d2) d2[(size_t)node * k + lane] = lane < found ? e.d2 : CUDART_INF;
+    __shared__ KnnScratch scratch[8];
+    __shared__ KnnBlockCache cache[8];
+    const bool fast = g.n_sorted == g.n && k <= 28 && g.n >= k;
+    KnnBlockState st;
+    st.cx = st.cy = -1, st.L = -1, st.area = 0.f;
+    st.xlo = st.xhi = st.ylo = st.yhi = 0.0;
+    const size_t nbatch = ((size_t)g.n + KNN_NODES_BATCH - 1) / KNN_NODES_BATCH;
+    for (size_t b = warp0; b < nbatch; b += nwarps) {
+        const size_t wend = min((size_t)g.n, (b + 1) * KNN_NODES_BATCH);
+        for (size_t w = b * KNN_NODES_BATCH; w < wend; w++) {
+            int node;
+            float2 p;
+            if (w < (size_t)g.n_sorted) {
+                node = g.sid[w];
+                p = g.sxy[w];
+            } else {
+                node = (int)w;
+                p = g.xy[w];
+            }
+            KnnEntry e;
+            int found = -1;
+            if (fast) {
+                const int cx = grid_cell_of((double)p.x, g.shift, g.gw - 1), cy = grid_cell_of((double)p.y, g.shift, g.gh - 1);
+                if (cx != st.cx || cy != st.cy) knn_block_fill(g, cx, cy, k, cache[wib], st);
+                if (st.L > 0) found = knn_warp_block3_cached(g, (double)p.x, (double)p.y, k, e, scratch[wib], cache[wib], st);
+            }
+            if (found < 0) found = knn_warp(g, (double)p.x, (double)p.y, k, e);
+            if (lane < k) {
+                idx[(size_t)node * k + lane] = lane < found ? e.id : -1;
+                if (d2) d2[(size_t)node * k + lane] = lane < found ? e.d2 : CUDART_INF;
+            }
         }
     }
 }
@@ -302,8 +321,8 @@ int rtpp_knn_nodes_dev(rtpp_ctx *ctx, int k, int32_t *d_idx, double *d_d2) {
     rc = rtpp_grid_view(ctx, &g);
     if (rc) return rc;
     if (g.n == 0) return RTPP_OK;
-    size_t blocks = ((size_t)g.n + 7) / 8;
-    size_t cap = (size_t)ctx->sm_count * 8;
+    size_t blocks = ((size_t)g.n + 8 * KNN_NODES_BATCH - 1) / (8 * KNN_NODES_BATCH); // one batch per warp, hardware-scheduled
+    size_t cap = (size_t)ctx->sm_count * 64;
     knn_nodes_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(g, k, d_idx, d_d2);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;

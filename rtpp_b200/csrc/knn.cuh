@@ -189,3 +189,233 @@ __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, doubl
 __device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy, int k, KnnEntry &mine) {
     return knn_warp_impl(g, qx, qy, k, mine, -1, 0);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Fast path of the bulk kernels: radius filter + one warp sort.
+// The 3x3 block of cells around the query is three contiguous ranges of the cell-sorted array; the warp reads
+// them as one list (<= 32*KNN_FAST_CHUNKS candidates, d2 kept in registers), finds a threshold T with
+// k <= |{d2 <= T}| <= 32 by a guarded secant iteration on the counts (first guess from the block's density),
+// compacts the survivors to one per lane through shared memory and sorts them once (bitonic, 64-bit key).
+// The k smallest of the block are the answer iff the k-th distance is strictly inside the block (the same
+// certificate as the ring walk at r = 1); anything else — a tail of unsorted nodes, k > 28, a sparse or very dense
+// block, many equal distances, an uncertified result — returns -1 and the caller runs knn_warp.
+// Same result as knn_warp by construction: the k smallest (d2, id) of a superset of the certified disc.
+// ---------------------------------------------------------------------------------------------
+#define KNN_FAST_CHUNKS 10
+struct KnnScratch { // per warp
+    double d2[32];
+    int id[32];
+};
+__device__ __forceinline__ int knn_warp_block3(const GridView &g, double qx, double qy, int k, KnnEntry &mine, KnnScratch &sm) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if (g.n_sorted != g.n || k > 28 || g.n < k) return -1;
+    const int cx = grid_cell_of(qx, g.shift, g.gw - 1), cy = grid_cell_of(qy, g.shift, g.gh - 1);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gw - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, g.gh - 1);
+    // the three rows (a missing row is an empty range)
+    const int ra = y0 * g.gw, rb = min(y0 + 1, y1) * g.gw, rc = y1 * g.gw;
+    const int s0 = g.cell_start[ra + x0], e0 = g.cell_start[ra + x1 + 1];
+    const int s1 = g.cell_start[rb + x0], e1 = (y1 - y0 >= 1) ? g.cell_start[rb + x1 + 1] : s1;
+    const int s2 = g.cell_start[rc + x0], e2 = (y1 - y0 >= 2) ? g.cell_start[rc + x1 + 1] : s2;
+    const int n0 = e0 - s0, n01 = n0 + (e1 - s1), L = n01 + (e2 - s2);
+    if (L < k || L > 32 * KNN_FAST_CHUNKS) return -1;
+    double d[KNN_FAST_CHUNKS];
+    int id[KNN_FAST_CHUNKS];
+#pragma unroll
+    for (int c = 0; c < KNN_FAST_CHUNKS; c++) d[c] = CUDART_INF, id[c] = 0x7fffffff;
+    {
+        // lane-private cursor over the concatenated list: position of candidate j = lane, lane + 32, ...
+        const int nch = (L + 31) >> 5;
+#pragma unroll
+        for (int c = 0; c < KNN_FAST_CHUNKS; c++) {
+            if (c >= nch) break;
+            const int j = 32 * c + lane;
+            if (j < L) {
+                const int pos = j < n0 ? s0 + j : (j < n01 ? s1 + (j - n0) : s2 + (j - n01));
+                const float2 p = g.sxy[pos];
+                id[c] = g.sid[pos];
+                d[c] = knn_d2(qx, qy, p.x, p.y);
+            }
+        }
+    }
+    // threshold with k <= count <= 32
+    const float tgt = 0.5f * (float)(k + 32);
+    const float area = (float)((x1 - x0 + 1) * (y1 - y0 + 1)) * (float)(1 << g.shift) * (float)(1 << g.shift);
+    double T = (double)(tgt * 0.31830987f * area / (float)L), lo = 0.0, hi = CUDART_INF;
+    int cnt = 0, mycnt = 0;
+    bool ok = false;
+    for (int it = 0; it < 6; it++) {
+        mycnt = 0;
+#pragma unroll
+        for (int c = 0; c < KNN_FAST_CHUNKS; c++) mycnt += d[c] <= T ? 1 : 0;
+        cnt = __reduce_add_sync(full, mycnt);
+        if (cnt >= k && cnt <= 32) {
+            ok = true;
+            break;
+        }
+        if (cnt < k) lo = T;
+        else hi = T;
+        double Tn = T * (double)(tgt / (float)max(cnt, 1));
+        if (cnt == 0) Tn = T * 4.0;
+        if (!(Tn > lo && Tn < hi)) Tn = hi == CUDART_INF ? lo * 2.0 : 0.5 * (lo + hi);
+        T = Tn;
+    }
+    if (!ok) return -1;
+    // compaction: one survivor per slot of the scratch list
+    int base = mycnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(full, base, o);
+        if (lane >= o) base += t;
+    }
+    base -= mycnt;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < KNN_FAST_CHUNKS; c++)
+        if (d[c] <= T) sm.d2[base] = d[c], sm.id[base] = id[c], base++;
+    __syncwarp();
+    // one bitonic sort across the lanes on a single 64-bit key: the distance bits (non-negative binary64 values order
+    // like unsigned integers) with the low 5 bits replaced by the slot.  Exact unless two survivors agree in all but
+    // those 5 bits (equal or nearly equal distances): then the (d2, id) order is not decided by the key -> slow path.
+    unsigned long long key = ~0ull;
+    if (lane < cnt) key = ((unsigned long long)__double_as_longlong(sm.d2[lane]) & ~31ull) | (unsigned)lane;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(full, key, stride);
+            const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
+            if ((other < key) == keep_min) key = other;
+        }
+    const unsigned long long prev = __shfl_up_sync(full, key, 1);
+    const bool near_tie = lane > 0 && lane < cnt && ((prev ^ key) >> 5) == 0;
+    if (__any_sync(full, near_tie)) return -1;
+    mine.d2 = CUDART_INF, mine.id = 0x7fffffff;
+    if (lane < k) mine.d2 = sm.d2[key & 31], mine.id = sm.id[key & 31];
+    __syncwarp();
+    // certificate: the k-th distance lies strictly inside the block (open sides only), as in knn_warp at r = 1
+    const double kd2 = __shfl_sync(full, mine.d2, k - 1);
+    double gap = CUDART_INF;
+    const double cell = (double)(1 << g.shift);
+    if (cx - 1 > 0) gap = fmin(gap, __dsub_rd(qx, (double)(cx - 1) * cell));
+    if (cx + 1 < g.gw - 1) gap = fmin(gap, __dsub_rd((double)(cx + 2) * cell, qx));
+    if (cy - 1 > 0) gap = fmin(gap, __dsub_rd(qy, (double)(cy - 1) * cell));
+    if (cy + 1 < g.gh - 1) gap = fmin(gap, __dsub_rd((double)(cy + 2) * cell, qy));
+    if (gap != CUDART_INF && !(gap > 0.0 && kd2 < __dmul_rd(gap, gap))) return -1;
+    return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// All-nodes table: consecutive cell-sorted queries share their cell, hence their 3x3 block.  The warp keeps the
+// block's candidates (coordinates + ids) in shared memory and refills them only when the query cell changes
+// (about once per 20 queries at C4), so a query costs no dependent global load beyond its own coordinates:
+// distances from shared memory, then the same threshold / compaction / sort / certificate as knn_warp_block3.
+// ---------------------------------------------------------------------------------------------
+struct KnnBlockCache { // per warp
+    float2 xy[32 * KNN_FAST_CHUNKS];
+    int id[32 * KNN_FAST_CHUNKS];
+};
+struct KnnBlockState { // warp-uniform registers
+    int cx, cy, L; // cached cell (-1: none) and its candidate count (-1: block unusable for the fast path)
+    float area;
+    double xlo, xhi, ylo, yhi; // the block's open sides (-inf / +inf where the block reaches the grid border)
+};
+// (re)fills the cache for cell (cx, cy); warp-collective
+__device__ __forceinline__ void knn_block_fill(const GridView &g, int cx, int cy, int k, KnnBlockCache &cache, KnnBlockState &st) {
+    const int lane = threadIdx.x & 31;
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gw - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, g.gh - 1);
+    const int ra = y0 * g.gw, rb = min(y0 + 1, y1) * g.gw, rc = y1 * g.gw;
+    const int s0 = g.cell_start[ra + x0], e0 = g.cell_start[ra + x1 + 1];
+    const int s1 = g.cell_start[rb + x0], e1 = (y1 - y0 >= 1) ? g.cell_start[rb + x1 + 1] : s1;
+    const int s2 = g.cell_start[rc + x0], e2 = (y1 - y0 >= 2) ? g.cell_start[rc + x1 + 1] : s2;
+    const int n0 = e0 - s0, n01 = n0 + (e1 - s1), L = n01 + (e2 - s2);
+    st.cx = cx, st.cy = cy;
+    st.area = (float)((x1 - x0 + 1) * (y1 - y0 + 1)) * (float)(1 << g.shift) * (float)(1 << g.shift);
+    st.L = (L < k || L > 32 * KNN_FAST_CHUNKS) ? -1 : L;
+    const double cell = (double)(1 << g.shift);
+    st.xlo = cx - 1 > 0 ? (double)(cx - 1) * cell : -CUDART_INF;
+    st.xhi = cx + 1 < g.gw - 1 ? (double)(cx + 2) * cell : CUDART_INF;
+    st.ylo = cy - 1 > 0 ? (double)(cy - 1) * cell : -CUDART_INF;
+    st.yhi = cy + 1 < g.gh - 1 ? (double)(cy + 2) * cell : CUDART_INF;
+    __syncwarp();
+    if (st.L > 0)
+        for (int j = lane; j < L; j += 32) {
+            const int pos = j < n0 ? s0 + j : (j < n01 ? s1 + (j - n0) : s2 + (j - n01));
+            cache.xy[j] = g.sxy[pos];
+            cache.id[j] = g.sid[pos];
+        }
+    __syncwarp();
+}
+// the query must lie in the cached cell and st.L must be > 0; returns k or -1 (caller runs knn_warp)
+__device__ __forceinline__ int knn_warp_block3_cached(const GridView &g, double qx, double qy, int k, KnnEntry &mine, KnnScratch &sm,
+                                                      const KnnBlockCache &cache, const KnnBlockState &st) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int L = st.L, nch = (L + 31) >> 5;
+    double d[KNN_FAST_CHUNKS];
+#pragma unroll
+    for (int c = 0; c < KNN_FAST_CHUNKS; c++) d[c] = CUDART_INF;
+#pragma unroll
+    for (int c = 0; c < KNN_FAST_CHUNKS; c++) {
+        if (c >= nch) break;
+        const int j = 32 * c + lane;
+        if (j < L) {
+            const float2 p = cache.xy[j];
+            d[c] = knn_d2(qx, qy, p.x, p.y);
+        }
+    }
+    const float tgt = 0.5f * (float)(k + 32);
+    double T = (double)(tgt * 0.31830987f * st.area / (float)L), lo = 0.0, hi = CUDART_INF;
+    int cnt = 0, mycnt = 0;
+    bool ok = false;
+    for (int it = 0; it < 6; it++) {
+        mycnt = 0;
+#pragma unroll
+        for (int c = 0; c < KNN_FAST_CHUNKS; c++) mycnt += d[c] <= T ? 1 : 0;
+        cnt = __reduce_add_sync(full, mycnt);
+        if (cnt >= k && cnt <= 32) {
+            ok = true;
+            break;
+        }
+        if (cnt < k) lo = T;
+        else hi = T;
+        double Tn = T * (double)(tgt / (float)max(cnt, 1));
+        if (cnt == 0) Tn = T * 4.0;
+        if (!(Tn > lo && Tn < hi)) Tn = hi == CUDART_INF ? lo * 2.0 : 0.5 * (lo + hi);
+        T = Tn;
+    }
+    if (!ok) return -1;
+    int base = mycnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(full, base, o);
+        if (lane >= o) base += t;
+    }
+    base -= mycnt;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < KNN_FAST_CHUNKS; c++)
+        if (d[c] <= T) sm.d2[base] = d[c], sm.id[base] = 32 * c + lane, base++;
+    __syncwarp();
+    unsigned long long key = ~0ull;
+    if (lane < cnt) key = ((unsigned long long)__double_as_longlong(sm.d2[lane]) & ~31ull) | (unsigned)lane;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(full, key, stride);
+            const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
+            if ((other < key) == keep_min) key = other;
+        }
+    const unsigned long long prev = __shfl_up_sync(full, key, 1);
+    const bool near_tie = lane > 0 && lane < cnt && ((prev ^ key) >> 5) == 0;
+    if (__any_sync(full, near_tie)) return -1;
+    mine.d2 = CUDART_INF, mine.id = 0x7fffffff;
+    if (lane < k) mine.d2 = sm.d2[key & 31], mine.id = cache.id[sm.id[key & 31]];
+    __syncwarp();
+    const double kd2 = __shfl_sync(full, mine.d2, k - 1);
+    // squared gap to the nearest open side, rounded toward zero (x - (-inf) = +inf: closed sides drop out)
+    const double gap = fmin(fmin(__dsub_rd(qx, st.xlo), __dsub_rd(st.xhi, qx)), fmin(__dsub_rd(qy, st.ylo), __dsub_rd(st.yhi, qy)));
+    if (gap != CUDART_INF && !(gap > 0.0 && kd2 < __dmul_rd(gap, gap))) return -1;
+    return k;
+}
