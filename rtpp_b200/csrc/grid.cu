@@ -62,16 +62,16 @@ __global__ void __launch_bounds__(256) knn_query_kernel(GridView g, const double
 // KNN_NODES_BATCH consecutive nodes in CELL-SORTED order, so its queries share their 3x3 block of cells
 // (candidates cached in shared memory, knn.cuh), and writes row sid[w] of the table.
 #define KNN_NODES_BATCH 16
-__global__ void __launch_bounds__(256) knn_nodes_kernel(GridView g, int k, int *__restrict__ idx, double *__restrict__ d2) {
+#define KNN_NODES_WARPS 4
+__global__ void __launch_bounds__(32 * KNN_NODES_WARPS) knn_nodes_kernel(GridView g, int k, int *__restrict__ idx, double *__restrict__ d2) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    __shared__ KnnScratch scratch[8];
-    __shared__ KnnBlockCache cache[8];
+    __shared__ KnnBlockCache cache[KNN_NODES_WARPS];
     const bool fast = g.n_sorted == g.n && k <= 28 && g.n >= k;
     KnnBlockState st;
-    st.cx = st.cy = -1, st.L = -1, st.area = 0.f;
-    st.xlo = st.xhi = st.ylo = st.yhi = 0.0;
+    st.cx = st.cy = -1, st.L = -1, st.T0 = 0.f;
+    st.xlo = st.xhi = st.ylo = st.yhi = 0.f;
     const size_t nbatch = ((size_t)g.n + KNN_NODES_BATCH - 1) / KNN_NODES_BATCH;
     for (size_t b = warp0; b < nbatch; b += nwarps) {
         const size_t wend = min((size_t)g.n, (b + 1) * KNN_NODES_BATCH);
@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(256) knn_nodes_kernel(GridView g, int k, int *
             KnnEntry e;
             int found = -1;
             if (fast) {
-                const int cx = grid_cell_of((double)p.x, g.shift, g.gw - 1), cy = grid_cell_of((double)p.y, g.shift, g.gh - 1);
+                const int cx = grid_cell_of_f32(p.x, g.shift, g.gw - 1), cy = grid_cell_of_f32(p.y, g.shift, g.gh - 1);
                 if (cx != st.cx || cy != st.cy) knn_block_fill(g, cx, cy, k, cache[wib], st);
-                if (st.L > 0) found = knn_warp_block3_cached(g, (double)p.x, (double)p.y, k, e, scratch[wib], cache[wib], st);
+                if (st.L > 0) found = knn_warp_block3_cached(p.x, p.y, k, e, cache[wib], st);
             }
             if (found < 0) found = knn_warp(g, (double)p.x, (double)p.y, k, e);
             if (lane < k) {
@@ -321,9 +321,9 @@ int rtpp_knn_nodes_dev(rtpp_ctx *ctx, int k, int32_t *d_idx, double *d_d2) {
     rc = rtpp_grid_view(ctx, &g);
     if (rc) return rc;
     if (g.n == 0) return RTPP_OK;
-    size_t blocks = ((size_t)g.n + 8 * KNN_NODES_BATCH - 1) / (8 * KNN_NODES_BATCH); // one batch per warp, hardware-scheduled
-    size_t cap = (size_t)ctx->sm_count * 64;
-    knn_nodes_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(g, k, d_idx, d_d2);
+    size_t blocks = ((size_t)g.n + KNN_NODES_WARPS * KNN_NODES_BATCH - 1) / (KNN_NODES_WARPS * KNN_NODES_BATCH); // one batch per warp, hardware-scheduled
+    size_t cap = (size_t)ctx->sm_count * 128;
+    knn_nodes_kernel<<<(int)(blocks < cap ? blocks : cap), 32 * KNN_NODES_WARPS, 0, ctx->stream>>>(g, k, d_idx, d_d2);
     RTPP_LAUNCHED(ctx);
     return RTPP_OK;
 }

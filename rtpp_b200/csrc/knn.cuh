@@ -312,14 +312,20 @@ __device__ __forceinline__ int knn_warp_block3(const GridView &g, double qx, dou
 // distances from shared memory, then the same threshold / compaction / sort / certificate as knn_warp_block3.
 // ---------------------------------------------------------------------------------------------
 struct KnnBlockCache { // per warp
-    float2 xy[32 * KNN_FAST_CHUNKS];
+    double2 xy[32 * KNN_FAST_CHUNKS]; // candidate coordinates widened once per fill
     int id[32 * KNN_FAST_CHUNKS];
+    double2 surv[32]; // survivors of the radius filter: (d2, candidate index as bits)
 };
 struct KnnBlockState { // warp-uniform registers
-    int cx, cy, L; // cached cell (-1: none) and its candidate count (-1: block unusable for the fast path)
-    float area;
-    double xlo, xhi, ylo, yhi; // the block's open sides (-inf / +inf where the block reaches the grid border)
+    int cx, cy, L;            // cached cell (-1: none) and its candidate count (-1: block unusable for the fast path)
+    float T0;                 // first threshold guess: the radius^2 that holds (k + 32) / 2 points at the block's mean density
+    float xlo, xhi, ylo, yhi; // the block's open sides (-inf / +inf where the block reaches the grid border); exact in binary32
 };
+// cell of a binary32 coordinate; equals grid_cell_of((double)v, ...) for every v
+__device__ __forceinline__ int grid_cell_of_f32(float v, int shift, int gmax) {
+    int c = (v > 0.f) ? (__float2int_rd(fminf(v, 1073741760.f)) >> shift) : 0;
+    return min(c, gmax);
+}
 // (re)fills the cache for cell (cx, cy); warp-collective
 __device__ __forceinline__ void knn_block_fill(const GridView &g, int cx, int cy, int k, KnnBlockCache &cache, KnnBlockState &st) {
     const int lane = threadIdx.x & 31;
@@ -330,28 +336,30 @@ __device__ __forceinline__ void knn_block_fill(const GridView &g, int cx, int cy
     const int s2 = g.cell_start[rc + x0], e2 = (y1 - y0 >= 2) ? g.cell_start[rc + x1 + 1] : s2;
     const int n0 = e0 - s0, n01 = n0 + (e1 - s1), L = n01 + (e2 - s2);
     st.cx = cx, st.cy = cy;
-    st.area = (float)((x1 - x0 + 1) * (y1 - y0 + 1)) * (float)(1 << g.shift) * (float)(1 << g.shift);
-    st.L = (L < k || L > 32 * KNN_FAST_CHUNKS) ? -1 : L;
-    const double cell = (double)(1 << g.shift);
-    st.xlo = cx - 1 > 0 ? (double)(cx - 1) * cell : -CUDART_INF;
-    st.xhi = cx + 1 < g.gw - 1 ? (double)(cx + 2) * cell : CUDART_INF;
-    st.ylo = cy - 1 > 0 ? (double)(cy - 1) * cell : -CUDART_INF;
-    st.yhi = cy + 1 < g.gh - 1 ? (double)(cy + 2) * cell : CUDART_INF;
+    st.L = (L < k || L > 32 * KNN_FAST_CHUNKS || g.shift > 20) ? -1 : L;
+    const float cell = (float)(1 << min(g.shift, 20));
+    const float area = (float)((x1 - x0 + 1) * (y1 - y0 + 1)) * cell * cell;
+    st.T0 = 0.5f * (float)(k + 32) * 0.31830987f * area / (float)max(L, 1);
+    st.xlo = cx - 1 > 0 ? (float)(cx - 1) * cell : -CUDART_INF_F;
+    st.xhi = cx + 1 < g.gw - 1 ? (float)(cx + 2) * cell : CUDART_INF_F;
+    st.ylo = cy - 1 > 0 ? (float)(cy - 1) * cell : -CUDART_INF_F;
+    st.yhi = cy + 1 < g.gh - 1 ? (float)(cy + 2) * cell : CUDART_INF_F;
     __syncwarp();
     if (st.L > 0)
         for (int j = lane; j < L; j += 32) {
             const int pos = j < n0 ? s0 + j : (j < n01 ? s1 + (j - n0) : s2 + (j - n01));
-            cache.xy[j] = g.sxy[pos];
+            const float2 p = g.sxy[pos];
+            cache.xy[j] = make_double2((double)p.x, (double)p.y);
             cache.id[j] = g.sid[pos];
         }
     __syncwarp();
 }
-// the query must lie in the cached cell and st.L must be > 0; returns k or -1 (caller runs knn_warp)
-__device__ __forceinline__ int knn_warp_block3_cached(const GridView &g, double qx, double qy, int k, KnnEntry &mine, KnnScratch &sm,
-                                                      const KnnBlockCache &cache, const KnnBlockState &st) {
+// the binary32 query must lie in the cached cell and st.L must be > 0; returns k or -1 (caller runs knn_warp)
+__device__ __forceinline__ int knn_warp_block3_cached(float qxf, float qyf, int k, KnnEntry &mine, KnnBlockCache &cache, const KnnBlockState &st) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int L = st.L, nch = (L + 31) >> 5;
+    const double qx = (double)qxf, qy = (double)qyf;
     double d[KNN_FAST_CHUNKS];
 #pragma unroll
     for (int c = 0; c < KNN_FAST_CHUNKS; c++) d[c] = CUDART_INF;
@@ -360,15 +368,19 @@ __device__ __forceinline__ int knn_warp_block3_cached(const GridView &g, double 
         if (c >= nch) break;
         const int j = 32 * c + lane;
         if (j < L) {
-            const float2 p = cache.xy[j];
-            d[c] = knn_d2(qx, qy, p.x, p.y);
+            const double2 p = cache.xy[j];
+            const double dx = __dsub_rn(qx, p.x), dy = __dsub_rn(qy, p.y); // = knn_d2
+            d[c] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         }
     }
+    // threshold with k <= count <= 32 (guarded secant on the counts; the guesses are heuristics, binary32 is enough)
     const float tgt = 0.5f * (float)(k + 32);
-    double T = (double)(tgt * 0.31830987f * st.area / (float)L), lo = 0.0, hi = CUDART_INF;
+    float Tf = st.T0, lo = 0.f, hi = CUDART_INF_F;
+    double T = 0.0;
     int cnt = 0, mycnt = 0;
     bool ok = false;
     for (int it = 0; it < 6; it++) {
+        T = (double)Tf;
         mycnt = 0;
 #pragma unroll
         for (int c = 0; c < KNN_FAST_CHUNKS; c++) mycnt += d[c] <= T ? 1 : 0;
@@ -377,28 +389,36 @@ __device__ __forceinline__ int knn_warp_block3_cached(const GridView &g, double 
             ok = true;
             break;
         }
-        if (cnt < k) lo = T;
-        else hi = T;
-        double Tn = T * (double)(tgt / (float)max(cnt, 1));
-        if (cnt == 0) Tn = T * 4.0;
-        if (!(Tn > lo && Tn < hi)) Tn = hi == CUDART_INF ? lo * 2.0 : 0.5 * (lo + hi);
-        T = Tn;
+        if (cnt < k) lo = Tf;
+        else hi = Tf;
+        float Tn = cnt == 0 ? Tf * 4.f : Tf * __fdividef(tgt, (float)cnt);
+        if (!(Tn > lo && Tn < hi)) Tn = hi == CUDART_INF_F ? lo * 2.f : 0.5f * (lo + hi);
+        Tf = Tn;
     }
     if (!ok) return -1;
+    // compaction: survivor -> its own slot (exclusive prefix of the per-lane counts)
     int base = mycnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(full, base, o);
         if (lane >= o) base += t;
     }
-    base -= mycnt;
+    double2 *dst = cache.surv + (base - mycnt);
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < KNN_FAST_CHUNKS; c++)
-        if (d[c] <= T) sm.d2[base] = d[c], sm.id[base] = 32 * c + lane, base++;
+    for (int c = 0; c < KNN_FAST_CHUNKS; c++) {
+        if (c >= nch) break;
+        if (d[c] <= T) {
+            *dst = make_double2(d[c], __longlong_as_double((long long)(32 * c + lane)));
+            dst++;
+        }
+    }
     __syncwarp();
+    // one bitonic sort across the lanes on a single 64-bit key: the distance bits (non-negative binary64 values order
+    // like unsigned integers) with the low 5 bits replaced by the slot.  Exact unless two survivors agree in all but
+    // those 5 bits (equal or nearly equal distances): then the (d2, id) order is not decided by the key -> slow path.
     unsigned long long key = ~0ull;
-    if (lane < cnt) key = ((unsigned long long)__double_as_longlong(sm.d2[lane]) & ~31ull) | (unsigned)lane;
+    if (lane < cnt) key = ((unsigned long long)__double_as_longlong(cache.surv[lane].x) & ~31ull) | (unsigned)lane;
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1)
 #pragma unroll
@@ -411,11 +431,15 @@ __device__ __forceinline__ int knn_warp_block3_cached(const GridView &g, double 
     const bool near_tie = lane > 0 && lane < cnt && ((prev ^ key) >> 5) == 0;
     if (__any_sync(full, near_tie)) return -1;
     mine.d2 = CUDART_INF, mine.id = 0x7fffffff;
-    if (lane < k) mine.d2 = sm.d2[key & 31], mine.id = cache.id[sm.id[key & 31]];
+    if (lane < k) {
+        const double2 sv = cache.surv[key & 31];
+        mine.d2 = sv.x, mine.id = cache.id[(int)__double_as_longlong(sv.y)];
+    }
     __syncwarp();
-    const double kd2 = __shfl_sync(full, mine.d2, k - 1);
-    // squared gap to the nearest open side, rounded toward zero (x - (-inf) = +inf: closed sides drop out)
-    const double gap = fmin(fmin(__dsub_rd(qx, st.xlo), __dsub_rd(st.xhi, qx)), fmin(__dsub_rd(qy, st.ylo), __dsub_rd(st.yhi, qy)));
-    if (gap != CUDART_INF && !(gap > 0.0 && kd2 < __dmul_rd(gap, gap))) return -1;
+    // certificate (sufficient, in binary32 rounded toward zero): the k-th distance lies strictly inside the block.
+    // x - (-inf) = +inf, so closed sides drop out and a block that covers the grid certifies everything.
+    const float kd2 = __double2float_ru(__shfl_sync(full, mine.d2, k - 1));
+    const float gap = fminf(fminf(__fsub_rd(qxf, st.xlo), __fsub_rd(st.xhi, qxf)), fminf(__fsub_rd(qyf, st.ylo), __fsub_rd(st.yhi, qyf)));
+    if (!(gap > 0.f && kd2 < __fmul_rd(gap, gap))) return -1;
     return k;
 }
