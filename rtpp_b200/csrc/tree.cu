@@ -71,15 +71,29 @@ __global__ void __launch_bounds__(256) tree_children_kernel(const cpword *__rest
 // [(L+1)%3] and clears [(L+2)%3].  flags (optional): bit0 = collision went 0 -> 1 (RT-FMT's N_b,
 // RTFMT.cpp:170-171), bit1 = cost grew, bit2 = cost shrank (CDRT's larger/smaller sets,
 // CDRT.cpp:781-790).  counters[3] = number of nodes reached.
+// Fan-out decides who expands a frontier node: its own thread (<= 8 children), its warp (<= kTreeBig: the
+// children are spread over the lanes), or — a root that thousands of nodes hang from — the whole grid after the
+// level's barrier (counters[4 + (L&1)] = how many such nodes level L met, listed behind the counters).
+static constexpr int kTreeBig = 2048;
+__device__ __forceinline__ void tree_visit(int c, int p, uint32_t hp, const uint32_t *__restrict__ w, cpword *__restrict__ cp,
+                                           uint8_t *__restrict__ flags) {
+    const uint32_t hn = cost_add(hp, w[c]);
+    if (flags) {
+        const uint32_t ho = cp_hi(cp[c]);
+        flags[c] = (uint8_t)(((hn >> 31) & ~(ho >> 31) & 1u) | ((hn > ho) ? 2u : 0u) | ((hn < ho) ? 4u : 0u));
+    }
+    cp[c] = cp_make(hn, p);
+}
 __global__ void __launch_bounds__(256)
 tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int *__restrict__ children,
                 const uint32_t *__restrict__ w, cpword *__restrict__ cp, int *__restrict__ frontier, int capacity,
-                int *__restrict__ counters, uint8_t *__restrict__ flags) {
+                int *__restrict__ counters, uint8_t *__restrict__ flags, int big_cap) {
     cg::grid_group grid = cg::this_grid();
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, lane = tid & 31;
+    int *big_list = counters + 8; // [2][big_cap]
     if (tid == 0) {
         frontier[0] = root;
-        counters[0] = 1, counters[1] = 0, counters[2] = 0, counters[3] = 1;
+        counters[0] = 1, counters[1] = 0, counters[2] = 0, counters[3] = 1, counters[4] = 0, counters[5] = 0;
     }
     grid.sync();
     for (int level = 0;; level++) {
@@ -88,10 +102,11 @@ tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int 
         int *cnt_next = &counters[(level + 1) % 3];
         const int *cur = frontier + (size_t)(level & 1) * capacity;
         int *nxt = frontier + (size_t)((level + 1) & 1) * capacity;
+        int *big = big_list + (size_t)(level & 1) * big_cap;
         if (tid == 0) counters[(level + 2) % 3] = 0;
         // one frontier node per thread; the warp reserves its children's slots with ONE atomicAdd
         for (int f0 = (tid & ~31); f0 < cur_n; f0 += nth) {
-            const int f = f0 + (tid & 31);
+            const int f = f0 + lane;
             int p = -1, s = 0, e = 0;
             uint32_t hp = 0;
             if (f < cur_n) {
@@ -99,29 +114,61 @@ tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int 
                 hp = cp_hi(cp[p]);
                 s = child_start[p], e = child_start[p + 1];
             }
-            const int cnt = e - s;
+            int cnt = e - s;
+            if (cnt > kTreeBig) { // expanded by the grid after the barrier
+                const int k = atomicAdd(&counters[4 + (level & 1)], 1);
+                if (k < big_cap) big[k] = p;
+                cnt = 0;
+            }
             int x = cnt;
             for (int off = 1; off < 32; off <<= 1) {
                 const int y = __shfl_up_sync(0xffffffffu, x, off);
-                if ((tid & 31) >= off) x += y;
+                if (lane >= off) x += y;
             }
             const int total = __shfl_sync(0xffffffffu, x, 31);
             int base = 0;
-            if ((tid & 31) == 31 && total) base = atomicAdd(cnt_next, total);
+            if (lane == 31 && total) base = atomicAdd(cnt_next, total);
             base = __shfl_sync(0xffffffffu, base, 31) + x - cnt;
-            for (int j = 0; j < cnt; j++) {
-                const int c = children[s + j];
-                const uint32_t hn = cost_add(hp, w[c]);
-                if (flags) {
-                    const uint32_t ho = cp_hi(cp[c]);
-                    flags[c] = (uint8_t)(((hn >> 31) & ~(ho >> 31) & 1u) | ((hn > ho) ? 2u : 0u) | ((hn < ho) ? 4u : 0u));
+            if (cnt <= 8)
+                for (int j = 0; j < cnt; j++) {
+                    const int c = children[s + j];
+                    tree_visit(c, p, hp, w, cp, flags);
+                    nxt[base + j] = c;
                 }
-                cp[c] = cp_make(hn, p);
-                nxt[base + j] = c;
+            unsigned wide = __ballot_sync(0xffffffffu, cnt > 8);
+            while (wide) {
+                const int o = __ffs(wide) - 1;
+                wide &= wide - 1;
+                const int po = __shfl_sync(0xffffffffu, p, o), so = __shfl_sync(0xffffffffu, s, o), co = __shfl_sync(0xffffffffu, cnt, o);
+                const int bo = __shfl_sync(0xffffffffu, base, o);
+                const uint32_t ho = __shfl_sync(0xffffffffu, hp, o);
+                for (int j = lane; j < co; j += 32) {
+                    const int c = children[so + j];
+                    tree_visit(c, po, ho, w, cp, flags);
+                    nxt[bo + j] = c;
+                }
             }
-            if ((tid & 31) == 31 && total) atomicAdd(&counters[3], total);
+            if (lane == 31 && total) atomicAdd(&counters[3], total);
         }
         grid.sync();
+        const int nb = min(counters[4 + (level & 1)], big_cap);
+        if (nb) { // uniform: every thread reads the same count after the barrier
+            int off = *cnt_next;
+            for (int b = 0; b < nb; b++) {
+                const int p = big[b];
+                const uint32_t hp = cp_hi(cp[p]);
+                const int s = child_start[p], cnt = child_start[p + 1] - s;
+                for (int j = tid; j < cnt; j += nth) {
+                    const int c = children[s + j];
+                    tree_visit(c, p, hp, w, cp, flags);
+                    nxt[off + j] = c;
+                }
+                off += cnt;
+            }
+            grid.sync(); // every thread has read *cnt_next and written its share
+            if (tid == 0) counters[3] += off - *cnt_next, *cnt_next = off, counters[4 + (level & 1)] = 0;
+            grid.sync();
+        }
     }
 }
 
@@ -225,7 +272,7 @@ static int ensure_tree_scratch(rtpp_ctx *ctx, NodeStore *s) {
     RTPP_CK(ctx, cudaMalloc(&s->child_start, (s->capacity + 2) * 4));
     RTPP_CK(ctx, cudaMalloc(&s->children, s->capacity * 4));
     RTPP_CK(ctx, cudaMalloc(&s->frontier, 2 * s->capacity * 4));
-    RTPP_CK(ctx, cudaMalloc(&s->counters, 8 * 4));
+    RTPP_CK(ctx, cudaMalloc(&s->counters, (8 + 2 * (s->capacity / kTreeBig + 1)) * 4)); // + the two lists of wide nodes
     return RTPP_OK;
 }
 
@@ -329,8 +376,8 @@ int rtpp_tree_propagate_dev(rtpp_ctx *ctx, int root, int divisor, int plane_mask
     const uint32_t *w = s->edge_w;
     cpword *cp = s->cp;
     int *fr = s->frontier, *cn = s->counters;
-    int nn = n, rr = root;
-    void *args[] = {&nn, &rr, &cs, &ch, &w, &cp, &fr, &cap, &cn, &d_flags};
+    int nn = n, rr = root, big_cap = (int)(s->capacity / kTreeBig + 1);
+    void *args[] = {&nn, &rr, &cs, &ch, &w, &cp, &fr, &cap, &cn, &d_flags, &big_cap};
     RTPP_CK(ctx, cudaLaunchCooperativeKernel((void *)tree_bfs_kernel, dim3(blocks), dim3(256), args, 0, ctx->stream));
     ctx->launches++;
     if (reached) {
