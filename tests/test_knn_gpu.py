@@ -101,3 +101,38 @@ def test_knn_all_nodes_table(ctx, oracle):
     assert np.array_equal(idx, oi)
     assert np.array_equal(d2.view(np.uint64), od.view(np.uint64))
     assert np.array_equal(idx[:, 0], np.arange(n))  # the query node itself comes back first at d2 = 0
+
+
+@pytest.mark.parametrize("k", [1, 7, 25, 28, 29])
+def test_knn_all_nodes_table_dense_fast_path(ctx, oracle, k):
+    """The radius-filter fast path of the bulk kernels (3x3 cell block, threshold, one warp sort, certificate) and its
+    fall-backs: blocks with more candidates than the fast path holds, exact duplicates and lattice points (equal
+    distances -> the (d2, id) rule), nodes on the domain border, k above the fast path's limit (29)."""
+    rng = np.random.default_rng(1000 + k)
+    w = h = 700
+    dense = _pts(rng, 60_000, w, h)                                   # ~280 candidates per 3x3 block of 16-px cells
+    clump = (_pts(rng, 3000, 40, 40) + np.float32(300)).astype(np.float32)  # a block far above the candidate limit
+    xs, ys = np.meshgrid(np.arange(0, 40, dtype=np.float32) * 2 + 100, np.arange(0, 40, dtype=np.float32) * 2 + 500)
+    lattice = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.float32)
+    border = np.array([[0, 0], [0, 350.5], [699.99, 699.99], [350.25, 0], [699.5, 10]], np.float32)
+    pts = np.concatenate([dense, clump, lattice, dense[:500], border])  # dense[:500] again = exact duplicates
+    pts = np.ascontiguousarray(pts[rng.permutation(len(pts))])
+    n = len(pts)
+    ctx.nodes_reset(4, n, w, h)
+    ctx.nodes_append(pts)
+    d_idx = ctx.dev_alloc(n * k * 4)
+    d_d2 = ctx.dev_alloc(n * k * 8)
+    ctx.knn_nodes_dev(k, d_idx, d_d2)
+    idx = np.zeros((n, k), np.int32)
+    d2 = np.zeros((n, k), np.float64)
+    ctx.d2h(idx, d_idx)
+    ctx.d2h(d2, d_d2)
+    ctx.sync()
+    ctx.dev_free(d_idx)
+    ctx.dev_free(d_d2)
+    oi, od, _ = oracle.knn(pts, pts.astype(np.float64), k, grid=(w, h, 16), nthreads=8)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint64), od.view(np.uint64))
+    # the same through the query kernel (arbitrary binary64 queries take the uncached fast path)
+    q = np.concatenate([pts[:20_000].astype(np.float64), rng.random((20_000, 2)) * np.array([w, h])])
+    _check(ctx, oracle, pts, q, k, grid=(w, h, 16))

@@ -134,3 +134,38 @@ def test_reroot_matches_oracle_planner(ctx, oracle):
     assert np.array_equal(gp, opar)
     assert np.array_equal(gl, ocol)
     assert np.array_equal(gc.view(np.uint32), ocost.view(np.uint32))
+
+
+def test_propagate_fan_out_shapes(ctx, oracle):
+    """R3 on a tree whose nodes have 0, a few, hundreds and thousands of children (thread-, warp- and grid-expanded
+    frontier nodes of tree_bfs_kernel) plus a long chain: costs, flags and the reached count vs the oracle."""
+    S = oracle.load_map("MESS6")
+    H, W = S.shape
+    rng = np.random.default_rng(77)
+    D = dyn_plane(S.shape, rng, n_blobs=6)
+    ctx.map_set_plane(1, S)
+    ctx.map_set_plane(2, D)
+    n = 20000
+    xy = _free_points(rng, S, n)
+    par = np.zeros(n, np.int32)
+    par[0] = -1
+    par[1:6001] = 0                                  # 6000 children of the root (grid-expanded)
+    par[6001:7501] = 1                               # 1500 children of node 1 (warp-expanded)
+    par[7501:7521] = 2                               # 20 children of node 2 (warp-expanded)
+    par[7521:7529] = 3                               # 8 children of node 3 (thread-expanded)
+    par[7529:9529] = np.arange(7528, 9528)           # a 2000-node chain
+    par[9529:] = rng.integers(1, 9529, n - 9529)     # the rest hang anywhere below
+    par[15000:15010] = -1                            # detached nodes are never reached
+    cost0 = np.full(n, 3.4e38, np.float32)
+    col0 = np.ones(n, np.uint8)
+    cost0[0], col0[0] = 0.0, 0
+    ctx.nodes_reset(4, n, W, H)
+    ctx.nodes_append(xy)
+    ctx.tree_set(par, cost0, col0)
+    reached, flags = ctx.tree_propagate(0, 5, 3, want_flags=True)
+    gp, gc, gl = ctx.tree_get()
+    oc, ol, oreached = oracle.tree_propagate(S, D, xy, par, 0, 5, 3, cost0, col0)
+    assert reached == oreached
+    assert np.array_equal(gp, par)
+    assert np.array_equal(gl, ol)
+    assert np.array_equal(gc.view(np.uint32), oc.view(np.uint32))
