@@ -478,7 +478,7 @@ def measure_extras(wl, torch, sweep):
 def measure_amrrt(ctx, n_inst=1024, ticks=4, dt=20000, cap_rand=60_000):
     """AM-RRT* MainTask (UpdateTree + {Expand with Steer and the diffusion metric, RewireRoot} for 80 ms of virtual time + GetPath)
     on bundled MESS6 with a synthetic diffusion table: 1024 planners (own rand() streams) on the engine against the CPU port on
-    the host threads; trees compared bit for bit."""
+    the host threads, then one planner alone (tick latency); trees compared bit for bit."""
     from concurrent.futures import ThreadPoolExecutor
 
     import rtpp_b200
@@ -491,25 +491,30 @@ def measure_amrrt(ctx, n_inst=1024, ticks=4, dt=20000, cap_rand=60_000):
     H, W = S.shape
     cells, mat, ratio = synthetic_diffusion(W)
     goals = [(70.0, 70.0), (1240.0, 70.0), (1240.0, 1240.0), (70.0, 1240.0)]  # RTRRT/test/testD.cpp:47
-    eng = rtpp_b200.Engine(ctx, n_inst, 4096, 5, W, H, cap_rand, kind=2)
-    eng.set_map(0, 1, S)
-    eng.set_diffusion(cells, mat, ratio)
-    agent = np.tile(np.array([[720.0, 720.0]], np.float32), (n_inst, 1))
-    goal = np.array([goals[i % 4] for i in range(n_inst)], np.float32)
-    eng.init_instances(np.zeros(n_inst, np.int32), agent, goal)
     streams = [orc.rand31(500 + i, cap_rand * ticks) for i in range(n_inst)]
-    pos = np.zeros(n_inst, np.int64)
-    lat = []
-    for _ in range(ticks):
-        chunk = np.stack([streams[i][pos[i]: pos[i] + cap_rand] for i in range(n_inst)])
-        eng.set_am_inputs(rand=chunk, n_rand=np.full(n_inst, cap_rand, np.int32), outpath_nonempty=np.zeros(n_inst, np.int32))
-        ctx.sync()
-        t0 = time.perf_counter()
-        eng.tick(update_tree=True, run_ms=80, dt_ns=dt, get_path=True)
-        ctx.sync()
-        lat.append(time.perf_counter() - t0)
-        st = eng.stats()
-        pos += st[:, 14]
+
+    def gpu(n):
+        eng = rtpp_b200.Engine(ctx, n, 4096, 5, W, H, cap_rand, kind=2)
+        eng.set_map(0, 1, S)
+        eng.set_diffusion(cells, mat, ratio)
+        agent = np.tile(np.array([[720.0, 720.0]], np.float32), (n, 1))
+        goal = np.array([goals[i % 4] for i in range(n)], np.float32)
+        eng.init_instances(np.zeros(n, np.int32), agent, goal)
+        pos = np.zeros(n, np.int64)
+        lat = []
+        for _ in range(ticks):
+            chunk = np.stack([streams[i][pos[i]: pos[i] + cap_rand] for i in range(n)])
+            eng.set_am_inputs(rand=chunk, n_rand=np.full(n, cap_rand, np.int32), outpath_nonempty=np.zeros(n, np.int32))
+            ctx.sync()
+            t0 = time.perf_counter()
+            eng.tick(update_tree=True, run_ms=80, dt_ns=dt, get_path=True)
+            ctx.sync()
+            lat.append(time.perf_counter() - t0)
+            st = eng.stats()
+            pos += st[:, 14]
+        return eng, lat, st
+
+    eng, lat, st = gpu(n_inst)
     iters_gpu, status = int(st[:, 4].sum()), int(st[:, 9].max())
     threads = os.cpu_count() or 1
     m = min(n_inst, threads)
@@ -521,23 +526,31 @@ def measure_amrrt(ctx, n_inst=1024, ticks=4, dt=20000, cap_rand=60_000):
         o.set_clock(dt, 0)
         o.set_agent(720.0, 720.0)
         o.set_goal(*goals[i % 4])
+        tl = []
         for _ in range(ticks):
+            t0 = time.perf_counter()
             o.main_task()
             o.get_path()
+            tl.append(time.perf_counter() - t0)
         d = o.dump()
         o.close()
-        return d
+        return d, tl
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
-        dumps = list(ex.map(cpu, range(m)))
+        res = list(ex.map(cpu, range(m)))
     cpu_s = time.perf_counter() - t0
-    same = all(all(np.array_equal(a.view(np.uint8), b.view(np.uint8)) for a, b in zip(dumps[i], eng.read_tree(i))) for i in range(m))
+    same = all(all(np.array_equal(a.view(np.uint8), b.view(np.uint8)) for a, b in zip(res[i][0], eng.read_tree(i))) for i in range(m))
     eng.close()
+    _, cpu_alone = cpu(0)  # one planner on an otherwise idle host
+    eng1, lat1, _ = gpu(1)
+    eng1.close()
     return {"amrrt": {"map": "MESS6", "instances": n_inst, "ticks": ticks, "virtual_dt_ns": dt, "gpu_status_max": status,
                       "gpu_sweep_tick_ms_p50": float(np.median(lat) * 1e3), "gpu_planner_ticks_per_s": n_inst * ticks / sum(lat),
                       "gpu_expand_iters_per_s": iters_gpu / sum(lat), "cpu_instances": m, "cpu_threads": threads,
-                      "cpu_planner_ticks_per_s": m * ticks / cpu_s, "cpu_kind": "port (oracle loops)", "trees_match_cpu": bool(same)}}
+                      "cpu_planner_ticks_per_s": m * ticks / cpu_s, "cpu_kind": "port (oracle loops)", "trees_match_cpu": bool(same),
+                      "gpu_single_instance_tick_ms_p50": float(np.median(lat1) * 1e3),
+                      "cpu_single_thread_tick_ms_p50": float(np.median(cpu_alone) * 1e3)}}
 
 
 def measure_cdrt(ctx):
