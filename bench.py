@@ -249,7 +249,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": f"{n} rewire edges (node -> 25-NN of the first nodes) per step"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_edges):
@@ -260,6 +260,19 @@ def workload_config(n_edges):
 
 
 # ------------------------------------------------------------------------------------ main
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,6 +281,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: native libraries (NCCL prints its version with printf) write to
+    # file descriptor 1, so point that at stderr for the run and keep the real stdout for the result line
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -284,7 +303,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = Workload(local_rank, seed=rank)
     ctx = wl.ctx
@@ -378,8 +396,11 @@ def main():
 
     # ---- BASELINE configs[4]: the scenario sweep, sharded by instance id over the ranks (all ranks take part)
     sweep = None
+    sharded_batch = None
     if not args.no_extras:
         sweep = measure_sweep(ctx, rank, world, torch, dist, wl.dev)
+        if world > 1:
+            sharded_batch = measure_sharded_batch(wl, rank, world, torch, dist)
 
     if rank != 0:
         if world > 1:
@@ -424,12 +445,14 @@ def main():
     extras = {}
     if not args.no_extras:
         extras = measure_extras(wl, torch, sweep)
+        if sharded_batch:
+            extras["sharded_edge_batch"] = sharded_batch
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(wl.n_edges), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -602,6 +625,60 @@ def measure_fmt(ctx, samples=100_000, iters=20_000):
     return {"rtfmt_1e5": {"samples": samples, "rounds": iters, "gpu_start_ms": gpu_start * 1e3, "gpu_rounds_per_s": iters / gpu_s,
                           "cpu_start_ms": cpu_start * 1e3, "cpu_rounds_per_s": iters / cpu_s, "cpu_kind": "port, 1 thread",
                           "state_matches_cpu": same}}
+
+
+def measure_sharded_batch(wl, rank, world, torch, dist, reps=20):
+    """SURVEY 8(e) grain 2: ONE candidate-edge batch (rank 0's 26 M C4 edges, broadcast once, outside the timed region)
+    split into contiguous ranges of 32-edge words over the ranks, planes replicated, the verdict words all-gathered
+    over NCCL; strong scaling, time = max over ranks per (check + all-gather), result compared with rank 0's
+    single-GPU verdicts."""
+    from rtpp_b200 import shard
+
+    n_edges = torch.tensor([wl.n_edges], dtype=torch.int64, device=wl.dev)
+    dist.broadcast(n_edges, 0)
+    ne = int(n_edges.item())
+    edges = wl.edges if rank == 0 else torch.empty((ne, 4), dtype=torch.float32, device=wl.dev)
+    dist.broadcast(edges, 0)
+    w0, nw, e0, ne_local = shard.word_range(ne, rank, world)
+    local = torch.zeros(max(nw, 1), dtype=torch.int32, device=wl.dev)
+    sub = edges[e0: e0 + ne_local]
+
+    def step():
+        wl.ctx.edges_check_dev(sub.data_ptr(), ne_local, DIVISOR, 3, local.data_ptr())
+        return shard.all_gather_words(local[:nw], ne)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(wl.stream)
+        for _ in range(reps):
+            out = fn()
+        ev1.record(wl.stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1) / reps], dtype=torch.float64, device=wl.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    ms_nccl, full = timed(step)
+    # the same batch with the all-gather fused into the check: verdict words stored into every peer's buffer by the
+    # kernel itself (NVLink P2P, rtpp_edges_check_allgather_dev), no collective call on the data path
+    peer = shard.PeerEdgeBatch(wl.ctx, ne)
+    ms_fused, d_words = timed(lambda: peer.check(edges.data_ptr(), DIVISOR, 3))
+    fused_words = peer.read(d_words)
+    same = same_fused = None
+    if rank == 0:
+        wl.step()  # rank 0's own single-GPU verdicts of the same edges
+        torch.cuda.synchronize()
+        same = bool((full == wl.bits).all().item())
+        same_fused = bool(np.array_equal(fused_words, wl.bits.cpu().numpy()))
+    peer.close()
+    return {"edges": ne, "n_gpus": world, "scaling": "strong",
+            "fused_p2p": {"ms_per_batch": ms_fused, "edges_per_s": ne / (ms_fused * 1e-3), "matches_single_gpu": same_fused,
+                          "how": "2048-edge blocks round-robin over the ranks; K1 stores each block's verdict words into every rank's result buffer (CUDA IPC mappings, NVLink) + device-side flag exchange"},
+            "nccl": {"ms_per_batch": ms_nccl, "edges_per_s": ne / (ms_nccl * 1e-3), "matches_single_gpu": same,
+                     "how": "contiguous word ranges (rank 0's holds the long tree edges); K1 + all_gather_into_tensor of the verdict words, %d bytes per rank" % (4 * (((ne + 31) // 32 + world - 1) // world))}}
 
 
 def measure_sweep(ctx, rank, world, torch, dist, dev, n_inst=8192, ticks=3, dt=5000, n_samples=2000):

@@ -100,6 +100,23 @@ RTPP_API int rtpp_map_draw_dynamic(rtpp_ctx *ctx, const int32_t *circles, int n_
  * xyxy: n edges as (ps.x, ps.y, pe.x, pe.y) binary32. */
 RTPP_API int rtpp_edges_check(rtpp_ctx *ctx, const float *xyxy, size_t n, int divisor, int plane_mask,
                               uint32_t *blocked_bits);
+/* --- one candidate-edge batch over the GPUs of a node (SURVEY 8(e) grain 2; one process per GPU) ---
+ * rtpp_peer_alloc: device memory other ranks can map (CUDA IPC; zero-filled); exchange the 64-byte handle with any
+ * host-side transport (rtpp_b200/shard.py uses torch.distributed) and map it with rtpp_peer_open.
+ * rtpp_edges_check_allgather_dev: every rank holds the whole batch of n edges (the tree is replicated) and checks its
+ * share — the 2048-edge blocks g with g mod world == rank, round-robin because an edge's cost varies with its length by
+ * two orders of magnitude — and every block stores its verdict words into the same word range of every rank's result
+ * buffer (bits_all[r], as mapped in this process; plain stores over NVLink), then the rank signals its peers and waits
+ * for theirs (flags_all[r]: world int32 per rank, `epoch` must grow by one per call): when the stream reaches the end of
+ * the call, bits_all[rank] holds the verdict words of the whole batch, as rtpp_edges_check_dev on one GPU writes them.
+ * Alternate two result buffers (epoch parity) so that a fast peer never overwrites words still being read. */
+#define RTPP_MAX_PEERS 8
+RTPP_API int rtpp_peer_alloc(rtpp_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64]);
+RTPP_API int rtpp_peer_open(rtpp_ctx *ctx, const unsigned char handle[64], void **peer_ptr);
+RTPP_API int rtpp_peer_close(rtpp_ctx *ctx, void *peer_ptr);
+RTPP_API int rtpp_edges_check_allgather_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divisor, int plane_mask,
+                                            uint32_t *const *bits_all, int32_t *const *flags_all, int rank, int world,
+                                            int epoch);
 RTPP_API int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divisor, int plane_mask,
                                   uint32_t *d_blocked_bits);
 /* E5b, the ray-march inside BImap::RTRT_CrashDetection CDRT.cpp:584-601: binary64 points,

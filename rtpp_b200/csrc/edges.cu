@@ -26,7 +26,13 @@ static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 3
 
 // The warp-level body of K1: every lane brings one edge (e = ps.x, ps.y, pe.x, pe.y; valid = false
 // for padding lanes) and gets the ballot word of the 32 verdicts.
-__device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, const float4 e, const bool valid, const MarchThresholds &mt) {
+// defer_list != nullptr (multi-GPU batches): edges with >= kDeferP march steps are not marched here but appended to the list
+// (their verdict bit stays 0) and marched one warp per edge by edge_deferred_kernel, which ORs their bits in afterwards —
+// a block that meets a run of thousand-pixel edges otherwise becomes the kernel's critical path once the batch is split.
+static constexpr int kDeferP = 128;
+__device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, const float4 e, const bool valid, const MarchThresholds &mt,
+                                                       uint32_t *defer_list = nullptr, unsigned *defer_count = nullptr,
+                                                       uint32_t edge_index = 0) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     uint32_t acc = 0; // bit 0 = blocked
@@ -64,6 +70,16 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
         }
     }
     unsigned longmask = __ballot_sync(full, !acc && P > kShortMaxP);
+    if (defer_list) {
+        const unsigned dm = __ballot_sync(full, !acc && P >= kDeferP);
+        if (dm) {
+            unsigned at = 0;
+            if (lane == 0) at = atomicAdd(defer_count, (unsigned)__popc(dm));
+            at = __shfl_sync(full, at, 0);
+            if (dm >> lane & 1u) defer_list[at + __popc(dm & ((1u << lane) - 1u))] = edge_index;
+            longmask &= ~dm;
+        }
+    }
     while (longmask) {
         const int src = __ffs(longmask) - 1;
         longmask &= longmask - 1;
@@ -92,13 +108,27 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
 // The block stages its verdict words and writes them as full lines at the end (256 B per block instead of 64
 // scattered 4-byte stores), which also makes a mapped host buffer a cheap destination.
 // kSentinel: entries whose first coordinate is NaN stand for "no edge" (verdict 0): the materialised tick list.
-template <bool kSentinel>
+// kPeers: the check fused with its all-gather (SURVEY 8(e) grain 2): the block's 256-byte burst of verdict words also
+// goes, with plain stores over NVLink, to the same word range of every peer GPU's result buffer (CUDA IPC mappings),
+// so the exchange rides under the march instead of following it as a collective.
+// The ranks take the batch's 2048-edge blocks round-robin (block g belongs to rank g mod world): the cost of an edge
+// varies by two orders of magnitude with its length (the C4 batch starts with 1e6 tree edges, 40 k of them thousands of
+// pixels long), and contiguous ranges left one of two GPUs with 63 % of the work.
+struct PeerBits {
+    uint32_t *p[RTPP_MAX_PEERS - 1];
+    int n;
+    int blk_stride, blk_first; // this launch's block b is block b * blk_stride + blk_first of the batch
+    uint32_t *defer_list;      // very long edges, marched by edge_deferred_kernel
+    unsigned *defer_count;
+};
+template <bool kSentinel, bool kPeers = false>
 __global__ void __launch_bounds__(256, 8)
 edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, MarchThresholds mt,
-                      uint32_t *__restrict__ out_bits, int chunk_iters) {
+                      uint32_t *__restrict__ out_bits, int chunk_iters, PeerBits peers = PeerBits()) {
     __shared__ uint32_t stage[64];
     const int lane = threadIdx.x & 31;
-    const size_t base = (size_t)blockIdx.x * 8 * chunk_iters; // first word of the block
+    const size_t blk = kPeers ? (size_t)blockIdx.x * peers.blk_stride + peers.blk_first : (size_t)blockIdx.x;
+    const size_t base = blk * 8 * chunk_iters; // first word of the block
     const int n_rel = (int)min((size_t)(256 * chunk_iters), n - (base << 5)); // edges of this block
     const float4 *ep = edges + (base << 5) + threadIdx.x;
     // software pipeline through shared memory: the next 16-byte edge of this lane is fetched with cp.async (L2 ->
@@ -117,11 +147,73 @@ edge_check_f32_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, 
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(&ebuf[((rel >> 8) & 1) ^ 1][threadIdx.x])), "l"(ep)
                          : "memory");
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        const unsigned bits = warp_edges_verdict(pl, e, rel < n_rel && (!kSentinel || e.x == e.x), mt);
+        const unsigned bits = kPeers ? warp_edges_verdict(pl, e, rel < n_rel && (!kSentinel || e.x == e.x), mt, peers.defer_list, peers.defer_count,
+                                                          (uint32_t)((base << 5) + rel))
+                                     : warp_edges_verdict(pl, e, rel < n_rel && (!kSentinel || e.x == e.x), mt);
         if (lane == 0) stage[rel >> 5] = bits;
     }
     __syncthreads();
-    if ((int)(threadIdx.x << 5) < n_rel) out_bits[base + threadIdx.x] = stage[threadIdx.x];
+    if ((int)(threadIdx.x << 5) < n_rel) {
+        const uint32_t v = stage[threadIdx.x];
+        out_bits[base + threadIdx.x] = v;
+        if (kPeers) {
+#pragma unroll
+            for (int k = 0; k < RTPP_MAX_PEERS - 1; k++)
+                if (k < peers.n) peers.p[k][base + threadIdx.x] = v;
+        }
+    }
+}
+
+// One warp per deferred edge: lane-strided probes with an early exit per 32-probe chunk (the same probe set as the
+// in-kernel march); a blocked edge ORs its bit into this rank's and every peer's result word.
+__global__ void __launch_bounds__(256)
+edge_deferred_kernel(PlaneView pl, const float4 *__restrict__ edges, MarchThresholds mt, uint32_t *__restrict__ out_bits, PeerBits peers) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5, count = *peers.defer_count;
+    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < count; i += nwarps) {
+        const uint32_t idx = peers.defer_list[i];
+        const float4 e = edges[idx];
+        const int P = rt_march_P(mt, rt_sqlen(e.x, e.y, e.z, e.w));
+        const float inv = rt_inv_pow2(P);
+        bool hit = false;
+        for (int j0 = 1; j0 < P; j0 += 32) {
+            const int j = j0 + lane;
+            if (j < P) hit = rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+            if (__any_sync(full, hit)) {
+                hit = true;
+                break;
+            }
+        }
+        if (hit && lane == 0) {
+            const uint32_t bit = 1u << (idx & 31);
+            atomicOr(out_bits + (idx >> 5), bit);
+#pragma unroll
+            for (int k = 0; k < RTPP_MAX_PEERS - 1; k++)
+                if (k < peers.n) atomicOr(peers.p[k] + (idx >> 5), bit);
+        }
+    }
+}
+
+// After a rank's fused check has finished (stream order), tell every peer (its flag slot `rank` := epoch, system scope)
+// and wait until every peer has told us: from then on this rank's result buffer holds the whole batch's verdict words.
+struct PeerFlags {
+    int *p[RTPP_MAX_PEERS];
+};
+__global__ void peer_signal_wait_kernel(PeerFlags flags_all, int rank, int world, int epoch) {
+    const int r = threadIdx.x;
+    int *theirs = nullptr, *mine = nullptr;
+#pragma unroll
+    for (int k = 0; k < RTPP_MAX_PEERS; k++) {
+        if (k == r) theirs = flags_all.p[k] + rank;
+        if (k == rank) mine = flags_all.p[k] + r;
+    }
+    const bool peer = r < world && r != rank;
+    if (peer) *(volatile int *)theirs = epoch;
+    __threadfence_system();
+    if (peer) // bounded (about a second): a peer that never arrives must not hang the GPU; the caller's result check fails instead
+        for (int it = 0; *(volatile int *)mine < epoch && it < (1 << 23); it++) __nanosleep(100);
+    __threadfence_system();
 }
 
 // E5b: binary64 end points, binary32 interpolation parameter (CDRT.cpp:586-600).
@@ -386,6 +478,74 @@ int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divis
     const size_t per_block = (size_t)8 * chunk * 32;
     edge_check_f32_kernel<false><<<(unsigned)((n + per_block - 1) / per_block), 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, d_bits, chunk);
     RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+// Fused check + all-gather over peer memory.  bits_all[r] / flags_all[r]: rank r's result buffer (whole batch) and flag
+// array (world ints) as mapped in THIS process (rtpp_peer_alloc / rtpp_peer_open).  Every rank holds the whole batch
+// (the tree is replicated) and checks its share of the blocks.
+int rtpp_edges_check_allgather_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divisor, int plane_mask, uint32_t *const *bits_all,
+                                   int32_t *const *flags_all, int rank, int world, int epoch) {
+    if (!ctx || !bits_all || !flags_all || (n && !d_xyxy)) return RTPP_ERR_INVALID;
+    if (world < 1 || world > RTPP_MAX_PEERS || rank < 0 || rank >= world) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad rank / world size");
+    if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    PlaneView pv;
+    int rc = rtpp_select_plane(ctx, plane_mask, &pv);
+    if (rc) return rc;
+    const int chunk = 8;
+    const size_t per_block = (size_t)8 * chunk * 32, blocks = (n + per_block - 1) / per_block;
+    const size_t mine = blocks > (size_t)rank ? (blocks - rank + world - 1) / world : 0;
+    if (mine) {
+        MarchThresholds mt;
+        rtpp_march_thresholds(divisor, &mt);
+        // deferral list (worst case: every edge of this rank's share) with its counter in front (scratch is shared with
+        // other entry points, so nothing is assumed to survive between calls)
+        void *d_list = nullptr;
+        rc = rtpp_scratch(ctx, 3, (mine * per_block + 64) * 4 + 16, &d_list);
+        if (rc) return rc;
+        RTPP_CK(ctx, cudaMemsetAsync(d_list, 0, 16, ctx->stream));
+        PeerBits peers;
+        peers.n = 0, peers.blk_stride = world, peers.blk_first = rank;
+        peers.defer_count = (unsigned *)d_list, peers.defer_list = (uint32_t *)d_list + 4;
+        for (int r = 0; r < world; r++)
+            if (r != rank) peers.p[peers.n++] = bits_all[r];
+        edge_check_f32_kernel<false, true><<<(unsigned)mine, 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, n, mt, bits_all[rank], chunk, peers);
+        RTPP_LAUNCHED(ctx);
+        edge_deferred_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(pv, (const float4 *)d_xyxy, mt, bits_all[rank], peers);
+        RTPP_LAUNCHED(ctx);
+    }
+    if (world > 1) {
+        PeerFlags pf;
+        for (int r = 0; r < RTPP_MAX_PEERS; r++) pf.p[r] = r < world ? flags_all[r] : nullptr;
+        peer_signal_wait_kernel<<<1, 32, 0, ctx->stream>>>(pf, rank, world, epoch);
+        RTPP_LAUNCHED(ctx);
+    }
+    return RTPP_OK;
+}
+
+// peer-visible device memory: cudaMalloc + an IPC handle other ranks on this node can open
+int rtpp_peer_alloc(rtpp_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64]) {
+    if (!ctx || !dptr || !handle) return RTPP_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    RTPP_CK(ctx, cudaSetDevice(ctx->device));
+    RTPP_CK(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+    RTPP_CK(ctx, cudaMemset(*dptr, 0, bytes ? bytes : 1));
+    cudaIpcMemHandle_t h;
+    RTPP_CK(ctx, cudaIpcGetMemHandle(&h, *dptr));
+    memcpy(handle, &h, 64);
+    return RTPP_OK;
+}
+int rtpp_peer_open(rtpp_ctx *ctx, const unsigned char handle[64], void **peer_ptr) {
+    if (!ctx || !handle || !peer_ptr) return RTPP_ERR_INVALID;
+    RTPP_CK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    RTPP_CK(ctx, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTPP_OK;
+}
+int rtpp_peer_close(rtpp_ctx *ctx, void *peer_ptr) {
+    if (!ctx) return RTPP_ERR_INVALID;
+    RTPP_CK(ctx, cudaIpcCloseMemHandle(peer_ptr));
     return RTPP_OK;
 }
 

@@ -132,3 +132,61 @@ def test_tick_edges_check_equals_explicit_list(ctx, oracle, n):
     want2 = oracle.edges_check(S, D, e2, 2, 3, nthreads=8)
     want2[4] = 0
     assert np.array_equal(got2, want2)
+
+
+def _peer_alloc(c, nbytes):
+    import ctypes as C
+
+    ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+    c._ck(c.L.rtpp_peer_alloc(c.h, C.c_size_t(nbytes), C.byref(ptr), h))
+    return ptr.value
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_edges_check_allgather_protocol_on_one_gpu(oracle, world):
+    """rtpp_edges_check_allgather_dev (SURVEY 8(e) grain 2) with every 'rank' on this GPU: one ctx (own stream) per rank,
+    each checks its round-robin share of the blocks, stores the verdict words into every rank's buffer, defers the very
+    long edges to the warp-per-edge kernel and exchanges flags; every rank's buffer must then hold exactly the verdicts
+    of the oracle.  (Across processes the buffers are CUDA IPC mappings: bench.py --gpus N / tools/peer_batch_bench.py.)"""
+    import ctypes as C
+
+    import rtpp_b200
+
+    S = oracle.load_map("MESS6")
+    H, W = S.shape
+    rng = np.random.default_rng(50 + world)
+    D = dyn_plane(S.shape, rng)
+    n = 300_001
+    e = edge_mix(rng, n, W, H, long_frac=0.2)  # 60 k edges up to ~1800 px: well past the deferral threshold
+    want = oracle.edges_check(S, D, e, 2, 3)
+    ctxs = [rtpp_b200.Ctx(0) for _ in range(world)]
+    d_edges, bits, flags = [], [], []
+    try:
+        nwords = (n + 31) // 32
+        for c in ctxs:
+            c.map_set_plane(1, S)
+            c.map_set_plane(2, D)
+            p = c.dev_alloc(n * 16)
+            c.h2d(p, e)
+            d_edges.append(p)
+            bits.append([_peer_alloc(c, nwords * 4), _peer_alloc(c, nwords * 4)])
+            flags.append(_peer_alloc(c, 64))
+            c.sync()
+        ftab = (C.c_void_p * world)(*flags)
+        for epoch in (1, 2, 3):
+            btab = (C.c_void_p * world)(*[b[epoch & 1] for b in bits])
+            for r, c in enumerate(ctxs):  # asynchronous launches: the ranks' kernels overlap on the device
+                c._ck(c.L.rtpp_edges_check_allgather_dev(c.h, C.c_void_p(d_edges[r]), C.c_size_t(n), 2, 3, btab, ftab, r, world, epoch))
+            for r, c in enumerate(ctxs):
+                c.sync()
+            for r, c in enumerate(ctxs):
+                got = np.zeros(nwords, np.uint32)
+                c.d2h(got, bits[r][epoch & 1])
+                c.sync()
+                assert np.array_equal(rtpp_b200.Ctx.unpack_bits(got, n), want), (world, epoch, r)
+    finally:
+        for r, c in enumerate(ctxs):
+            if r < len(flags):
+                for p in (d_edges[r], bits[r][0], bits[r][1], flags[r]):
+                    c.dev_free(p)
+            c.close()
