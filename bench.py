@@ -431,6 +431,18 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, burst)" if peaks else "fallback 6650",
                 "algorithmic_bytes_per_edge": 16 + 4 * probes_per_edge + 0.125, "mean_probes_per_edge": probes_per_edge,
                 "stream_only_GBs": wl.n_edges * 16.125 / (ms_step * 1e-3) / 1e9}
+    # the L2 form of the same launch (one 32-byte sector per probe) against the L2 gather rate measured in
+    # this run, and the other same-run denominators (L2 line stream, FP32 FFMA issue, HBM copy) next to MEASURED_PEAKS
+    try:
+        mp = ctx.measure_peaks(8 << 20, 5)
+        l2_achieved = wl.n_edges * probes_per_edge * 32 / (ms_step * 1e-3) / 1e9
+        roofline["l2_form"] = {"achieved": l2_achieved, "peak": mp["l2_sector_gather_gbs"], "unit": "GB/s",
+                               "frac": l2_achieved / mp["l2_sector_gather_gbs"],
+                               "definition": "32 B x probes / launch time vs random 32-byte-sector loads (ld.global.cg) out of an "
+                                             "8 MiB L2-resident buffer; K1's probes hit L1 about half of the time, so this is an upper bound on its L2 use"}
+        roofline["same_run_peaks"] = mp
+    except Exception as exc:  # the bench line must survive a failed microbenchmark
+        roofline["same_run_peaks"] = {"error": str(exc)}
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same edges)
     threads = os.cpu_count() or 1
@@ -479,6 +491,7 @@ def measure_extras(wl, torch, sweep):
     ms = timed(lambda: ctx.knn_nodes_dev(KNN, wl.knn_idx.data_ptr()), 5)
     out["knn_queries_per_s"] = n / (ms * 1e-3)
     out["knn_all_nodes_ms"] = ms
+    out["knn_algorithmic_GBs"] = n * (16 + KNN * 20) / (ms * 1e-3) / 1e9  # 516 B per 25-NN query
     cost0 = np.full(n, 3.4e38, np.float32)
     col0 = np.ones(n, np.uint8)
     cost0[0], col0[0] = 0.0, 0

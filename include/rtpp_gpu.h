@@ -62,6 +62,12 @@ RTPP_API int rtpp_sync(rtpp_ctx *ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 RTPP_API long long rtpp_kernel_launches(rtpp_ctx *ctx);
 RTPP_API int rtpp_device_sm_count(rtpp_ctx *ctx, int *sm_count);
+/* Roofline denominators measured in the same run as the kernels they bound (L2 bandwidth and the FP32
+ * issue peak are not in MEASURED_PEAKS.json).  l2_bytes = size of the L2-resident test buffer (power of two; use the
+ * bit-plane size class, e.g. 8 MiB).  out[0] = L2 random 32-byte-sector gather GB/s (L1 bypassed: the cost of a
+ * bit-plane probe that misses L1), out[1] = L2 coalesced-line read GB/s, out[2] = FP32 FFMA issue TFLOP/s,
+ * out[3] = HBM copy GB/s (read + write bytes over a 1 GiB buffer).  Best of `reps` timed launches after warm-up. */
+RTPP_API int rtpp_measure_peaks(rtpp_ctx *ctx, size_t l2_bytes, int reps, double out[4]);
 
 /* device / pinned-host buffers for resident workflows (bench.py, planner host code) */
 RTPP_API int rtpp_dev_alloc(rtpp_ctx *ctx, size_t bytes, void **dptr);

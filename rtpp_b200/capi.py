@@ -101,6 +101,12 @@ class Ctx:
         self.call("device_sm_count", C.byref(n))
         return n.value
 
+    def measure_peaks(self, l2_bytes=8 << 20, reps=5):
+        """Same-run roofline denominators (rtpp_measure_peaks): L2 sector-gather / L2 stream / HBM copy GB/s, FP32 TFLOP/s."""
+        out = (C.c_double * 4)()
+        self.call("measure_peaks", C.c_size_t(l2_bytes), C.c_int(reps), out)
+        return {"l2_sector_gather_gbs": out[0], "l2_stream_gbs": out[1], "fp32_ffma_tflops": out[2], "hbm_copy_gbs": out[3]}
+
     def dev_alloc(self, nbytes):
         p = C.c_void_p()
         self.call("dev_alloc", C.c_size_t(nbytes), C.byref(p))
