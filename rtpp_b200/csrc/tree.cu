@@ -204,62 +204,217 @@ relax_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const int *__r
 }
 
 // relax phase 2: c_new = cost[x] + w; if c_new < cost[s] (strict, lexicographic: RTRRT.cpp:311) the word {c_new, x}
-// replaces cost|parent of s by atomicMin.  free_only: AM-RRT* RewireRoot relaxes only over free edges and never to a
-// colliding cost (AMRRT.cpp:500-504).
-// relax phase 2 as a work list: only the edges out of nodes whose cost fell in the previous round can improve
-// anything, so a round handles the current frontier (one warp per node, lanes = its k edges), collects the nodes it
-// improved (deduplicated by a round stamp) and the whole iteration to quiescence is ONE persistent cooperative kernel
-// with a grid-wide barrier per round — the late rounds of a long improving chain touch a handful of nodes and cost a
-// barrier instead of a 25 M-edge pass and a host round trip.  Same least fixpoint as the sweeps.
-// counters: [0..2] frontier sizes in rotation (current, next, being cleared), [3] rounds done
-__global__ void __launch_bounds__(256)
-relax_worklist_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, int n, int k, int free_only, cpword *cp, int *fr_a, int *fr_b,
-                      int *stamp, int *counters, int max_rounds) {
-    cg::grid_group grid = cg::this_grid();
+// replaces cost|parent of s by atomicMin (equal costs: the smaller parent id, so the result does not depend on the
+// schedule).  free_only: AM-RRT* RewireRoot relaxes only over free edges and never to a colliding cost
+// (AMRRT.cpp:500-504).
+//
+// Schedule.  Only the edges out of a node whose cost fell can improve anything, so the iteration is a work list of
+// such nodes, and the least fixpoint does not depend on the order in which it is drained (every update is an
+// atomicMin).  Two measured facts shape the order (C4, 1e6 nodes, 25 M edges, longest improving chain ~740 hops):
+// a wave-synchronous drain pays one grid barrier per hop (~25 us each with the counter and frontier round trips
+// through L2: 20 ms), and draining without any order lets provisional costs run ahead and be corrected over and over
+// (28 ms at 32 unordered hops per barrier, 95 ms at 128).  So the drain is ordered by cost bucket, near-far /
+// delta-stepping style: an outer round (one grid barrier) has a threshold T = (smallest queued cost) + delta; a block
+// relaxes its share of the queued nodes with cost <= T and CHASES the nodes it improves — those with a new cost <= T go
+// to a queue in its shared memory and are relaxed in the next inner round after a __syncthreads (a hop costs the L2
+// latency chain of one node, not a barrier), everything else waits in the global list for a later bucket.
+// queued[x] = 1 while x sits in some list; the warp that takes x clears it BEFORE it reads cost[x], so an improvement
+// that lands later re-queues x (asynchronous work-list protocol).  The packed cost word is the bucket key: colliding
+// costs (bit 31) sort after every free cost and are drained last, in one bucket.
+// counters: [0..2] list sizes in rotation (current, next, being cleared), [3] outer rounds done, [4..6] smallest key of
+// the list, same rotation
+constexpr int kRelaxQ = 1024;     // entries per shared-memory queue
+constexpr int kRelaxSpill = 2048; // block-local staging of the entries bound for the global list
+
+struct RelaxBlock { // shared memory of one block
+    int q[2][kRelaxQ];
+    int spill[kRelaxSpill];
+    int qn[2];
+    int spill_n;
+    uint32_t spill_min;
+    int base;
+};
+
+__device__ __forceinline__ uint32_t relax_threshold(uint32_t min_key, float delta) {
+    if (min_key >> 31) return 0xffffffffu; // only colliding costs are left: one last bucket
+    return __float_as_uint(__fadd_rn(__uint_as_float(min_key), delta));
+}
+
+// lanes with `go`: stage node sn (bucket key `key`) for the global list
+__device__ __forceinline__ void relax_defer(RelaxBlock &sm, bool go, int sn, uint32_t key, int *nxt, int *nxt_count, uint32_t *nxt_min) {
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    // round 0: every node that has a cost
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) fr_a[i] = i, stamp[i] = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = n, counters[1] = 0, counters[2] = 0, counters[3] = 0;
-    grid.sync();
-    int *cur = fr_a, *nxt = fr_b;
-    int round = 0;
-    for (; round < max_rounds; round++) {
-        const int m = ((volatile int *)counters)[round % 3];
-        if (m == 0) break;
-        if (blockIdx.x == 0 && threadIdx.x == 0) counters[(round + 2) % 3] = 0, counters[3] = round + 1; // next round's target
-        for (int f = warp; f < m; f += nwarps) {
-            const int x = cur[f];
-            const uint32_t hx = cp_hi(((volatile cpword *)cp)[x]);
-            if (hx == 0xffffffffu) continue; // x has no cost yet
-            for (int j0 = 0; j0 < k; j0 += 32) {
-                const int j = j0 + lane;
-                bool improved = false;
-                int sn = -1;
-                if (j < k) {
-                    const size_t e = (size_t)x * k + j;
-                    const uint32_t we = w[e];
-                    if (we != 0xffffffffu && !(free_only && (we >> 31))) {
-                        sn = knn[e];
-                        const uint32_t hn = cost_add(hx, we);
-                        if (!(free_only && (hn >> 31)) && hn < cp_hi(((volatile cpword *)cp)[sn])) {
-                            const cpword neww = cp_make(hn, x);
-                            const cpword prev = atomicMin(&cp[sn], neww);
-                            improved = prev > neww && cp_hi(prev) > hn;
-                        }
-                    }
-                }
-                // a node enters the next frontier once per round
-                if (improved) improved = atomicExch(&stamp[sn], round + 1) != round + 1;
-                const unsigned bal = __ballot_sync(0xffffffffu, improved);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&counters[(round + 1) % 3], __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (improved) nxt[base + __popc(bal & ((1u << lane) - 1u))] = sn;
+    const unsigned bal = __ballot_sync(0xffffffffu, go);
+    if (!bal) return;
+    const uint32_t mk = __reduce_min_sync(0xffffffffu, go ? key : 0xffffffffu);
+    int base = 0;
+    if (lane == 0) {
+        base = atomicAdd(&sm.spill_n, __popc(bal));
+        atomicMin(&sm.spill_min, mk);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (go) {
+        const int pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (pos < kRelaxSpill) sm.spill[pos] = sn;
+        else nxt[atomicAdd(nxt_count, 1)] = sn; // staging full: straight to the list (its key is in spill_min)
+    }
+}
+
+// block-collective: move the staged entries to the global list
+__device__ __forceinline__ void relax_flush(RelaxBlock &sm, int *nxt, int *nxt_count) {
+    __syncthreads();
+    const int cnt = min(sm.spill_n, kRelaxSpill);
+    if (cnt > 0) {
+        if (threadIdx.x == 0) sm.base = atomicAdd(nxt_count, cnt);
+        __syncthreads();
+        for (int f = threadIdx.x; f < cnt; f += blockDim.x) nxt[sm.base + f] = sm.spill[f];
+        __syncthreads();
+        if (threadIdx.x == 0) sm.spill_n = 0;
+    }
+    __syncthreads();
+}
+
+// warp-collective: relax the k edges out of x (its queued mark is already cleared and hx read after that); improved,
+// not yet queued neighbours go to the shared-memory queue qo when their new cost is in the bucket, else to the staging
+__device__ __forceinline__ void relax_node(RelaxBlock &sm, int x, uint32_t hx, uint32_t T, const int *__restrict__ knn,
+                                           const uint32_t *__restrict__ w, int k, int free_only, cpword *cp, int *queued, int qo,
+                                           int *nxt, int *nxt_count, uint32_t *nxt_min) {
+    const int lane = threadIdx.x & 31;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+        const int j = j0 + lane;
+        bool improved = false;
+        int sn = -1;
+        uint32_t hn = 0xffffffffu;
+        if (j < k) {
+            const size_t e = (size_t)x * k + j;
+            const uint32_t we = w[e];
+            if (we != 0xffffffffu && !(free_only && (we >> 31))) {
+                sn = knn[e];
+                hn = cost_add(hx, we);
+                const cpword neww = cp_make(hn, x);
+                if (!(free_only && (hn >> 31)) && neww < ((volatile cpword *)cp)[sn]) {
+                    const cpword prev = atomicMin(&cp[sn], neww);
+                    improved = cp_hi(prev) > hn; // a change of parent at equal cost moves no other cost
                 }
             }
         }
+        if (improved) {
+            __threadfence();
+            improved = atomicExch(&queued[sn], 1) == 0;
+        }
+        bool near = improved && hn <= T;
+        const unsigned bal = __ballot_sync(0xffffffffu, near);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sm.qn[qo], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (near) {
+                const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                if (pos < kRelaxQ) sm.q[qo][pos] = sn;
+                else near = false; // queue full: to the global list
+            }
+        }
+        relax_defer(sm, improved && !near, sn, hn, nxt, nxt_count, nxt_min);
+    }
+}
+
+// warp-collective: take x off its list: clear the mark, then read the cost
+__device__ __forceinline__ uint32_t relax_take(int x, const cpword *cp, int *queued) {
+    if ((threadIdx.x & 31) == 0) {
+        ((volatile int *)queued)[x] = 0;
+        __threadfence();
+    }
+    __syncwarp();
+    return cp_hi(((const volatile cpword *)cp)[x]);
+}
+
+__global__ void __launch_bounds__(256)
+relax_chase_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, int n, int k, int free_only, cpword *cp, int *fr_a, int *fr_b,
+                   int *queued, int *counters, int max_rounds, int chase, float delta) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ RelaxBlock sm;
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *mins = (uint32_t *)counters + 4;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counters[0] = counters[1] = counters[2] = counters[3] = 0;
+        mins[0] = mins[1] = mins[2] = 0xffffffffu;
+    }
+    if (threadIdx.x == 0) sm.spill_n = 0, sm.spill_min = 0xffffffffu;
+    grid.sync();
+    // list 0: every node that can relax an edge at all
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < n; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        uint32_t h = 0xffffffffu;
+        if (i < n) h = cp_hi(cp[i]);
+        const bool go = i < n && h != 0xffffffffu && !(free_only && (h >> 31));
+        if (i < n) queued[i] = go;
+        relax_defer(sm, go, i, h, fr_a, &counters[0], &mins[0]);
+    }
+    relax_flush(sm, fr_a, &counters[0]);
+    if (threadIdx.x == 0 && sm.spill_min != 0xffffffffu) atomicMin(&mins[0], sm.spill_min);
+    grid.sync();
+    int *cur = fr_a, *nxt = fr_b;
+    for (int round = 0; round < max_rounds; round++) {
+        const int m = ((volatile int *)counters)[round % 3];
+        if (m == 0) break;
+        const uint32_t T = relax_threshold(((volatile uint32_t *)mins)[round % 3], delta);
+        int *nxt_count = &counters[(round + 1) % 3];
+        uint32_t *nxt_min = &mins[(round + 1) % 3];
+        if (blockIdx.x == 0 && threadIdx.x == 0) counters[(round + 2) % 3] = 0, mins[(round + 2) % 3] = 0xffffffffu, counters[3] = round + 1;
+        if (threadIdx.x < 2) sm.qn[threadIdx.x] = 0;
+        if (threadIdx.x == 0) sm.spill_min = 0xffffffffu;
+        __syncthreads();
+        // this block's share of the list: entries of the bucket go to the block's queue, the others wait.  A short
+        // list is dealt one entry per warp, blocks first, so that every block gets some of it to chase.
+        {
+            const int total_warps = wpb * gridDim.x, gw = wib * gridDim.x + blockIdx.x;
+            const int g = min(32, (m + total_warps - 1) / total_warps);
+            for (int f0 = gw * g; f0 < m; f0 += total_warps * g) {
+                const int f = f0 + lane;
+                const bool have = lane < g && f < m;
+                int x = -1;
+                uint32_t h = 0xffffffffu;
+                if (have) x = cur[f], h = cp_hi(((volatile cpword *)cp)[x]);
+                bool near = have && h <= T;
+                const unsigned bal = __ballot_sync(0xffffffffu, near);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.qn[0], __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (near) {
+                        const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                        if (pos < kRelaxQ) sm.q[0][pos] = x;
+                        else near = false;
+                    }
+                }
+                relax_defer(sm, have && !near, x, h, nxt, nxt_count, nxt_min);
+            }
+        }
+        int p = 0;
+        for (int it = 0;; it++) {
+            relax_flush(sm, nxt, nxt_count); // (also the barrier that completes q[p])
+            const int cnt = min(sm.qn[p], kRelaxQ);
+            if (cnt == 0) break;
+            if (it == chase) { // hand the rest to the next outer round (entries stay marked as queued)
+                for (int f0 = wib * 32; f0 < cnt; f0 += blockDim.x) {
+                    const int f = f0 + lane;
+                    int x = -1;
+                    uint32_t h = 0xffffffffu;
+                    if (f < cnt) x = sm.q[p][f], h = cp_hi(((volatile cpword *)cp)[x]);
+                    relax_defer(sm, f < cnt, x, h, nxt, nxt_count, nxt_min);
+                }
+                relax_flush(sm, nxt, nxt_count);
+                break;
+            }
+            if (threadIdx.x == 0) sm.qn[p ^ 1] = 0;
+            __syncthreads();
+            for (int f = wib; f < cnt; f += wpb) {
+                const int x = sm.q[p][f];
+                const uint32_t hx = relax_take(x, cp, queued);
+                relax_node(sm, x, hx, T, knn, w, k, free_only, cp, queued, p ^ 1, nxt, nxt_count, nxt_min);
+            }
+            p ^= 1;
+        }
+        if (threadIdx.x == 0 && sm.spill_min != 0xffffffffu) atomicMin(nxt_min, sm.spill_min);
         int *t = cur;
         cur = nxt, nxt = t;
         grid.sync();
@@ -429,8 +584,14 @@ int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, 
     int sweeps = 0;
     {
         int per_sm = 0;
-        RTPP_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_worklist_kernel, 256, 0));
-        int blocks = ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm)); // few blocks: the barrier is the cost of a late round
+        RTPP_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_chase_kernel, 256, 0));
+        int cap_bps = 8, chase = 64;
+        // bucket width: 2.5 k-NN radii (r_k = sqrt(k / (pi * density)) for uniformly spread nodes); measured flat optimum 2-3.5 r_k at C4
+        float delta = 2.5f * sqrtf((float)k * (float)ctx->W * (float)ctx->H / (3.14159265f * (float)(s->n > 0 ? s->n : 1)));
+        if (const char *ev = getenv("RTPP_RELAX_BPS")) cap_bps = atoi(ev); // experiment hooks
+        if (const char *ev = getenv("RTPP_RELAX_CHASE")) chase = atoi(ev);
+        if (const char *ev = getenv("RTPP_RELAX_DELTA")) delta = (float)atof(ev);
+        int blocks = ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > cap_bps ? cap_bps : per_sm));
         const int need = (int)(((size_t)s->n * 32 + 255) / 256);
         if (blocks > need) blocks = need < 1 ? 1 : need;
         const int *knn = d_knn_idx;
@@ -438,8 +599,8 @@ int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, 
         cpword *cp = s->cp;
         int nn = s->n, kk = k, fo = free_only, mr = max_sweeps;
         int *fa = s->frontier, *fb = s->frontier + s->capacity, *st = s->children, *cn = s->counters;
-        void *args[] = {&knn, &ww, &nn, &kk, &fo, &cp, &fa, &fb, &st, &cn, &mr};
-        RTPP_CK(ctx, cudaLaunchCooperativeKernel((void *)relax_worklist_kernel, dim3(blocks), dim3(256), args, 0, ctx->stream));
+        void *args[] = {&knn, &ww, &nn, &kk, &fo, &cp, &fa, &fb, &st, &cn, &mr, &chase, &delta};
+        RTPP_CK(ctx, cudaLaunchCooperativeKernel((void *)relax_chase_kernel, dim3(blocks), dim3(256), args, 0, ctx->stream));
         ctx->launches++;
         RTPP_CK(ctx, cudaMemcpyAsync(&sweeps, s->counters + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
         RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
