@@ -199,9 +199,10 @@ RTPP_API int rtpp_tree_reroot(rtpp_ctx *ctx, int old_root, int new_root);
 RTPP_API int rtpp_tree_propagate(rtpp_ctx *ctx, int root, int divisor, int plane_mask, uint8_t *flags, int *reached);
 RTPP_API int rtpp_tree_propagate_dev(rtpp_ctx *ctx, int root, int divisor, int plane_mask, uint8_t *d_flags, int *reached);
 /* Rewire relaxations RTRRT.cpp:305-319,334-346 (AMRRT.cpp:497-510 with free_only = 1) over the
- * directed edges x -> knn[x][j] of a resident k-NN table (n*k ids, -1 = none), repeated as
- * Bellman-Ford sweeps until no cost word changes (at most max_sweeps).  The reference relaxes one
- * queue element at a time; both reach the same collision-free costs at quiescence. */
+ * directed edges x -> knn[x][j] of a resident k-NN table (n*k ids, -1 = none), drained as a work list ordered by cost
+ * bucket until no cost word changes (at most max_sweeps buckets; *sweeps_done = buckets drained).  The reference
+ * relaxes one queue element at a time; both reach the same collision-free costs at quiescence; among
+ * parents that give a node the same cost the smaller id is kept. */
 RTPP_API int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, int plane_mask, int free_only,
                             int max_sweeps, int *sweeps_done);
 

@@ -218,11 +218,15 @@ relax_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const int *__r
 // relaxes its share of the queued nodes with cost <= T and CHASES the nodes it improves — those with a new cost <= T go
 // to a queue in its shared memory and are relaxed in the next inner round after a __syncthreads (a hop costs the L2
 // latency chain of one node, not a barrier), everything else waits in the global list for a later bucket.
-// queued[x] = 1 while x sits in some list; the warp that takes x clears it BEFORE it reads cost[x], so an improvement
-// that lands later re-queues x (asynchronous work-list protocol).  The packed cost word is the bucket key: colliding
+// Whether a node sits in some list is bit 0 of its word WHILE THE KERNEL RUNS (cost | parent << 1 | idle): the
+// improving atomicMin carries idle = 0 and its return value says whether the node was idle before (then the improver
+// queues it), the warp that takes a node sets the bit and reads the cost with one atomicOr — one L2 round trip each,
+// no separate flag, no fence — so an improvement that lands after the take re-queues the node (asynchronous
+// work-list protocol).  Order of a word: cost, parent id, idle bit, so equal costs still resolve to the smaller parent.  The packed cost word is the bucket key: colliding
 // costs (bit 31) sort after every free cost and are drained last, in one bucket.
 // counters: [0..2] list sizes in rotation (current, next, being cleared), [3] outer rounds done, [4..6] smallest key of
 // the list, same rotation
+constexpr int kRelaxThreads = 512;
 constexpr int kRelaxQ = 1024;     // entries per shared-memory queue
 constexpr int kRelaxSpill = 2048; // block-local staging of the entries bound for the global list
 
@@ -234,6 +238,15 @@ struct RelaxBlock { // shared memory of one block
     uint32_t spill_min;
     int base;
 };
+
+// in-kernel word: cost(32) | parent(31) | idle(1); parent "none" (-1) = 0x7fffffff
+__device__ __forceinline__ cpword rq_make(uint32_t hi, int parent, uint32_t idle) {
+    return ((cpword)hi << 32) | (((uint32_t)parent & 0x7fffffffu) << 1) | idle;
+}
+__device__ __forceinline__ cpword rq_to_plain(cpword wq) {
+    const uint32_t p31 = ((uint32_t)wq) >> 1;
+    return cp_make(cp_hi(wq), p31 == 0x7fffffffu ? -1 : (int)p31);
+}
 
 __device__ __forceinline__ uint32_t relax_threshold(uint32_t min_key, float delta) {
     if (min_key >> 31) return 0xffffffffu; // only colliding costs are left: one last bucket
@@ -273,10 +286,10 @@ __device__ __forceinline__ void relax_flush(RelaxBlock &sm, int *nxt, int *nxt_c
     __syncthreads();
 }
 
-// warp-collective: relax the k edges out of x (its queued mark is already cleared and hx read after that); improved,
-// not yet queued neighbours go to the shared-memory queue qo when their new cost is in the bucket, else to the staging
+// warp-collective: relax the k edges out of x (already taken: hx is the cost relax_take returned); improved, idle
+// neighbours go to the shared-memory queue qo when their new cost is in the bucket, else to the staging
 __device__ __forceinline__ void relax_node(RelaxBlock &sm, int x, uint32_t hx, uint32_t T, const int *__restrict__ knn,
-                                           const uint32_t *__restrict__ w, int k, int free_only, cpword *cp, int *queued, int qo,
+                                           const uint32_t *__restrict__ w, int k, int free_only, cpword *cp, int qo,
                                            int *nxt, int *nxt_count, uint32_t *nxt_min) {
     const int lane = threadIdx.x & 31;
     for (int j0 = 0; j0 < k; j0 += 32) {
@@ -290,16 +303,13 @@ __device__ __forceinline__ void relax_node(RelaxBlock &sm, int x, uint32_t hx, u
             if (we != 0xffffffffu && !(free_only && (we >> 31))) {
                 sn = knn[e];
                 hn = cost_add(hx, we);
-                const cpword neww = cp_make(hn, x);
-                if (!(free_only && (hn >> 31)) && neww < ((volatile cpword *)cp)[sn]) {
+                const cpword neww = rq_make(hn, x, 0);
+                // the test before the atomic also keeps a re-relaxation at unchanged cost from re-queueing a whole subtree
+                if (!(free_only && (hn >> 31)) && neww < (((volatile cpword *)cp)[sn] & ~1ull)) {
                     const cpword prev = atomicMin(&cp[sn], neww);
-                    improved = cp_hi(prev) > hn; // a change of parent at equal cost moves no other cost
+                    improved = neww < prev && (prev & 1ull); // the word was replaced and the node was idle: queue it
                 }
             }
-        }
-        if (improved) {
-            __threadfence();
-            improved = atomicExch(&queued[sn], 1) == 0;
         }
         bool near = improved && hn <= T;
         const unsigned bal = __ballot_sync(0xffffffffu, near);
@@ -317,19 +327,16 @@ __device__ __forceinline__ void relax_node(RelaxBlock &sm, int x, uint32_t hx, u
     }
 }
 
-// warp-collective: take x off its list: clear the mark, then read the cost
-__device__ __forceinline__ uint32_t relax_take(int x, const cpword *cp, int *queued) {
-    if ((threadIdx.x & 31) == 0) {
-        ((volatile int *)queued)[x] = 0;
-        __threadfence();
-    }
-    __syncwarp();
-    return cp_hi(((const volatile cpword *)cp)[x]);
+// warp-collective: take x off its list: mark it idle and read its cost in one atomic
+__device__ __forceinline__ uint32_t relax_take(int x, cpword *cp) {
+    uint32_t h = 0;
+    if ((threadIdx.x & 31) == 0) h = cp_hi(atomicOr(&cp[x], 1ull));
+    return __shfl_sync(0xffffffffu, h, 0);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kRelaxThreads)
 relax_chase_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, int n, int k, int free_only, cpword *cp, int *fr_a, int *fr_b,
-                   int *queued, int *counters, int max_rounds, int chase, float delta) {
+                   int *counters, int max_rounds, int chase, float delta) {
     cg::grid_group grid = cg::this_grid();
     __shared__ RelaxBlock sm;
     const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
@@ -344,9 +351,10 @@ relax_chase_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, 
     for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < n; i0 += gridDim.x * blockDim.x) {
         const int i = i0 + lane;
         uint32_t h = 0xffffffffu;
-        if (i < n) h = cp_hi(cp[i]);
+        cpword wd = 0;
+        if (i < n) wd = cp[i], h = cp_hi(wd);
         const bool go = i < n && h != 0xffffffffu && !(free_only && (h >> 31));
-        if (i < n) queued[i] = go;
+        if (i < n) cp[i] = rq_make(h, cp_parent(wd), go ? 0u : 1u);
         relax_defer(sm, go, i, h, fr_a, &counters[0], &mins[0]);
     }
     relax_flush(sm, fr_a, &counters[0]);
@@ -409,8 +417,8 @@ relax_chase_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, 
             __syncthreads();
             for (int f = wib; f < cnt; f += wpb) {
                 const int x = sm.q[p][f];
-                const uint32_t hx = relax_take(x, cp, queued);
-                relax_node(sm, x, hx, T, knn, w, k, free_only, cp, queued, p ^ 1, nxt, nxt_count, nxt_min);
+                const uint32_t hx = relax_take(x, cp);
+                relax_node(sm, x, hx, T, knn, w, k, free_only, cp, p ^ 1, nxt, nxt_count, nxt_min);
             }
             p ^= 1;
         }
@@ -419,6 +427,8 @@ relax_chase_kernel(const int *__restrict__ knn, const uint32_t *__restrict__ w, 
         cur = nxt, nxt = t;
         grid.sync();
     }
+    // back to the resident layout (cost | parent)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cp[i] = rq_to_plain(cp[i]);
 }
 
 static int ensure_tree_scratch(rtpp_ctx *ctx, NodeStore *s) {
@@ -584,23 +594,23 @@ int rtpp_relax_dev(rtpp_ctx *ctx, const int32_t *d_knn_idx, int k, int divisor, 
     int sweeps = 0;
     {
         int per_sm = 0;
-        RTPP_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_chase_kernel, 256, 0));
-        int cap_bps = 8, chase = 64;
-        // bucket width: 2.5 k-NN radii (r_k = sqrt(k / (pi * density)) for uniformly spread nodes); measured flat optimum 2-3.5 r_k at C4
-        float delta = 2.5f * sqrtf((float)k * (float)ctx->W * (float)ctx->H / (3.14159265f * (float)(s->n > 0 ? s->n : 1)));
-        if (const char *ev = getenv("RTPP_RELAX_BPS")) cap_bps = atoi(ev); // experiment hooks
-        if (const char *ev = getenv("RTPP_RELAX_CHASE")) chase = atoi(ev);
-        if (const char *ev = getenv("RTPP_RELAX_DELTA")) delta = (float)atof(ev);
+        RTPP_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, relax_chase_kernel, kRelaxThreads, 0));
+        // all warp slots of an SM (4 blocks of 512): a hop is a chain of L2 round trips, more warps hide more of it
+        const int cap_bps = 4;
+        int chase = 64;
+        // bucket width: 3 k-NN radii (r_k = sqrt(k / (pi * density)) for uniformly spread nodes); the measured optimum
+        // at C4 is flat between 2 and 3.5 r_k (wider: provisional costs run ahead; narrower: more barriers)
+        float delta = 3.0f * sqrtf((float)k * (float)ctx->W * (float)ctx->H / (3.14159265f * (float)(s->n > 0 ? s->n : 1)));
         int blocks = ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > cap_bps ? cap_bps : per_sm));
-        const int need = (int)(((size_t)s->n * 32 + 255) / 256);
+        const int need = (int)(((size_t)s->n * 32 + kRelaxThreads - 1) / kRelaxThreads);
         if (blocks > need) blocks = need < 1 ? 1 : need;
         const int *knn = d_knn_idx;
         const uint32_t *ww = (const uint32_t *)dw;
         cpword *cp = s->cp;
         int nn = s->n, kk = k, fo = free_only, mr = max_sweeps;
-        int *fa = s->frontier, *fb = s->frontier + s->capacity, *st = s->children, *cn = s->counters;
-        void *args[] = {&knn, &ww, &nn, &kk, &fo, &cp, &fa, &fb, &st, &cn, &mr, &chase, &delta};
-        RTPP_CK(ctx, cudaLaunchCooperativeKernel((void *)relax_chase_kernel, dim3(blocks), dim3(256), args, 0, ctx->stream));
+        int *fa = s->frontier, *fb = s->frontier + s->capacity, *cn = s->counters;
+        void *args[] = {&knn, &ww, &nn, &kk, &fo, &cp, &fa, &fb, &cn, &mr, &chase, &delta};
+        RTPP_CK(ctx, cudaLaunchCooperativeKernel((void *)relax_chase_kernel, dim3(blocks), dim3(kRelaxThreads), args, 0, ctx->stream));
         ctx->launches++;
         RTPP_CK(ctx, cudaMemcpyAsync(&sweeps, s->counters + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
         RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));

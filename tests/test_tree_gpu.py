@@ -169,3 +169,46 @@ def test_propagate_fan_out_shapes(ctx, oracle):
     assert np.array_equal(gp, par)
     assert np.array_equal(gl, ol)
     assert np.array_equal(gc.view(np.uint32), oc.view(np.uint32))
+
+
+def test_relax_lattice_ties_schedule_independent(ctx, oracle):
+    """Integer lattice points: nearly every node has several parents of exactly equal cost.  The work-list schedule
+    (cost buckets, block-local chasing, asynchronous re-queueing) must still reach the oracle's costs and flags, and
+    the tie rule (smaller parent id) makes the parents reproducible from run to run."""
+    S = oracle.load_map("MESS6")
+    H, W = S.shape
+    ctx.map_set_plane(1, S)
+    ctx.map_clear_plane(2)
+    gx, gy = np.meshgrid(np.arange(8, W - 8, 6), np.arange(8, H - 8, 6))
+    pts = np.stack([gx.ravel(), gy.ravel()], 1).astype(np.float32)
+    pts = pts[S[pts[:, 1].astype(np.int32), pts[:, 0].astype(np.int32)] == 0]
+    rng = np.random.default_rng(5)
+    xy = np.ascontiguousarray(pts[rng.permutation(len(pts))])
+    n, k = len(xy), 9
+    assert n > 5000
+    ctx.nodes_reset(4, n, W, H)
+    ctx.nodes_append(xy)
+    d_idx, idx = _device_knn_table(ctx, n, k)
+    par = _random_tree(idx)
+    cost0 = np.full(n, 3.4e38, np.float32)
+    col0 = np.ones(n, np.uint8)
+    cost0[0], col0[0] = 0.0, 0
+    runs = []
+    for free_only in (True, False):
+        for _ in range(2):
+            ctx.tree_set(par, cost0, col0)
+            buckets = ctx.relax_dev(d_idx, k, 5, 1, free_only=free_only)
+            assert buckets >= 1
+            runs.append(ctx.tree_get())
+        (p1, c1, l1), (p2, c2, l2) = runs[-2:]
+        assert np.array_equal(p1, p2) and np.array_equal(c1.view(np.uint32), c2.view(np.uint32)) and np.array_equal(l1, l2)
+        fc, fl, _, _ = oracle.relax_fixpoint(S, None, xy, idx, 5, 1, cost0, col0, par, free_only=free_only)
+        assert np.array_equal(l1, fl)
+        free = fl == 0
+        assert free.sum() > n // 2
+        assert np.array_equal(c1[free].view(np.uint32), fc[free].view(np.uint32))
+        # every free node's parent realises its cost: cost[parent] + |parent - node| == cost[node] (binary32)
+        ch = np.nonzero(free & (np.arange(n) != 0))[0]
+        d = np.sqrt(((xy[ch] - xy[p1[ch]]) ** 2).sum(1, dtype=np.float32), dtype=np.float32)
+        assert np.array_equal((c1[p1[ch]] + d).astype(np.float32).view(np.uint32), c1[ch].view(np.uint32))
+    ctx.dev_free(d_idx)
