@@ -311,6 +311,13 @@ __device__ __forceinline__ void relax_node(RelaxBlock &sm, int x, uint32_t hx, u
                 }
             }
         }
+        if (improved) { // sn will be taken within a few inner rounds: start its two edge rows towards L2 now
+            const size_t r = (size_t)sn * k;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(w + r));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(w + r + k - 1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(knn + r));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(knn + r + k - 1));
+        }
         bool near = improved && hn <= T;
         const unsigned bal = __ballot_sync(0xffffffffu, near);
         if (bal) {
