@@ -439,7 +439,7 @@ def main():
         roofline["l2_form"] = {"achieved": l2_achieved, "peak": mp["l2_sector_gather_gbs"], "unit": "GB/s",
                                "frac": l2_achieved / mp["l2_sector_gather_gbs"],
                                "definition": "32 B x probes / launch time vs random 32-byte-sector loads (ld.global.cg) out of an "
-                                             "8 MiB L2-resident buffer; K1's probes hit L1 about half of the time, so this is an upper bound on its L2 use"}
+                                             "8 MiB L2-resident buffer; a value above 1 means the probes are served by L1 / merged inside the warp's request (tile layout), i.e. L2 is not the bound"}
         roofline["same_run_peaks"] = mp
     except Exception as exc:  # the bench line must survive a failed microbenchmark
         roofline["same_run_peaks"] = {"error": str(exc)}
