@@ -492,6 +492,7 @@ def measure_extras(wl, torch, sweep):
     out["knn_queries_per_s"] = n / (ms * 1e-3)
     out["knn_all_nodes_ms"] = ms
     out["knn_algorithmic_GBs"] = n * (16 + KNN * 20) / (ms * 1e-3) / 1e9  # 516 B per 25-NN query
+    out["edge_kernels"] = measure_edge_kernels(wl, torch, timed)
     cost0 = np.full(n, 3.4e38, np.float32)
     col0 = np.ones(n, np.uint8)
     cost0[0], col0[0] = 0.0, 0
@@ -508,6 +509,29 @@ def measure_extras(wl, torch, sweep):
     out.update(measure_fmt(ctx))
     out.update(measure_cdrt(ctx))
     out.update(measure_amrrt(ctx))
+    return out
+
+
+def measure_edge_kernels(wl, torch, timed):
+    """The other edge routines of SURVEY 8(a) on the same resident C4 edge list (device pointers, CUDA events): E1 (divisor 5, both
+    planes: RT-RRT*, RT-FMT), E2 (static plane only), E4 (first blocked point of a linear march, AM-RRT* Steer) and E5b (binary64
+    end points, divisor 10, dynamic plane: CDRT-RRT*) next to the timed E3 step."""
+    import ctypes as C
+
+    ctx, n = wl.ctx, wl.n_edges
+    bits = torch.zeros_like(wl.bits)
+    out = {}
+    for name, div, mask in (("E1_div5_SD", 5, 3), ("E2_div5_S", 5, 1)):
+        ms = timed(lambda: ctx.edges_check_dev(wl.edges.data_ptr(), n, div, mask, bits.data_ptr()), 10)
+        out[name] = {"edges": n, "ms": ms, "edges_per_s": n / (ms * 1e-3)}
+    m = 4_000_000  # first-hit also writes 8 B per edge; binary64 edges are 32 B each
+    sub = wl.edges[wl.n_edges - m:].contiguous()
+    pstart = torch.empty((m, 2), dtype=torch.float32, device=wl.dev)
+    ms = timed(lambda: ctx.call("edges_first_hit_dev", C.c_void_p(sub.data_ptr()), C.c_size_t(m), C.c_void_p(bits.data_ptr()), C.c_void_p(pstart.data_ptr())), 10)
+    out["E4_first_hit"] = {"edges": m, "ms": ms, "edges_per_s": m / (ms * 1e-3)}
+    sub64 = sub.double().contiguous()
+    ms = timed(lambda: ctx.call("edges_check_f64_dev", C.c_void_p(sub64.data_ptr()), C.c_size_t(m), 10, 2, C.c_void_p(bits.data_ptr())), 10)
+    out["E5b_f64_div10_D"] = {"edges": m, "ms": ms, "edges_per_s": m / (ms * 1e-3)}
     return out
 
 
