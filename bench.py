@@ -500,11 +500,17 @@ def measure_extras(wl, torch, sweep):
     ms = timed(lambda: ctx.tree_propagate_dev(0, DIVISOR, 3), 5)
     out["propagate_1e6_tree_edges_ms"] = ms
     out["propagate_edges_per_s"] = (n - 1) / (ms * 1e-3)
-    t0 = time.perf_counter()
-    sweeps = ctx.relax_dev(wl.knn_idx.data_ptr(), KNN, DIVISOR, 3, free_only=True)
-    torch.cuda.synchronize()
-    out["rewire_to_quiescence_ms"] = (time.perf_counter() - t0) * 1e3
+    best = None
+    for _ in range(3):  # the first call also allocates the 100 MB edge-weight scratch; same start state every time
+        ctx.tree_set(wl.parent, cost0, col0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sweeps = ctx.relax_dev(wl.knn_idx.data_ptr(), KNN, DIVISOR, 3, free_only=True)  # synchronous: returns the bucket count
+        ms = (time.perf_counter() - t0) * 1e3
+        best = ms if best is None else min(best, ms)
+    out["rewire_to_quiescence_ms"] = best
     out["rewire_sweeps"] = sweeps
+    out["rewire_schedule"] = "work list by cost bucket (near-far), blocks chase their improvements through shared-memory queues; wall time of the host call, best of 3"
     out.update(measure_replanning(ctx, sweep))
     out.update(measure_fmt(ctx))
     out.update(measure_cdrt(ctx))

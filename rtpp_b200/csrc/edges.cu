@@ -274,9 +274,11 @@ edge_check_f64_kernel(PlaneView pl, const double4 *__restrict__ edges, size_t n,
     }
 }
 
-// E4: linear march i = 1..M-1, t = (float)i/M weighting pe; needs the FIRST blocked index
-// (a min-reduction, not an OR).  One warp per edge: lanes take 32 consecutive i, the first chunk
-// with a hit gives f = base + ffs(ballot) - 1; pstart = point(f-1) (or ps when f == 1).
+// E4: linear march i = 1..M-1, t = (float)i/M weighting pe; needs the FIRST blocked index (a min-reduction, not an
+// OR) and the last free point before it.  A lane owns an edge and walks it in order until the first hit (Steer's
+// edges are short: M = len/2 + 2 is a handful of probes, and the walk stops early); edges with more than kFirstHitLane
+// interior probes are marched by the whole warp afterwards: lanes take 32 consecutive i, the first chunk with a hit
+// gives f = base + ffs(ballot) - 1.  pstart = point(f-1) (ps when f == 1, pe when nothing is hit).
 __device__ __forceinline__ float2 first_hit_point(float psx, float psy, float pex, float pey, int i, float Mf) {
     const float t = __fdiv_rn((float)i, Mf);
     const float omt = __fsub_rn(1.0f, t);
@@ -285,6 +287,8 @@ __device__ __forceinline__ float2 first_hit_point(float psx, float psy, float pe
     r.y = __fadd_rn(__fmul_rn(pey, t), __fmul_rn(omt, psy));
     return r;
 }
+
+constexpr int kFirstHitLane = 48;
 
 __global__ void __launch_bounds__(256)
 edge_first_hit_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, uint32_t *__restrict__ out_bits,
@@ -295,44 +299,64 @@ edge_first_hit_kernel(PlaneView pl, const float4 *__restrict__ edges, size_t n, 
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t nwords = (n + 31) >> 5;
     for (size_t w = warp0; w < nwords; w += nwarps) {
-        unsigned bits = 0;
-        const size_t base = w << 5;
-        const int cnt = (int)min((size_t)32, n - base);
-        // lane k preloads edge base+k; the warp then walks the 32 edges one at a time
+        const size_t e = (w << 5) + lane;
+        const bool have = e < n;
         float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < cnt) mine = ld_stream_f4(edges + base + lane);
-        for (int k = 0; k < cnt; k++) {
-            const float psx = __shfl_sync(full, mine.x, k), psy = __shfl_sync(full, mine.y, k);
-            const float pex = __shfl_sync(full, mine.z, k), pey = __shfl_sync(full, mine.w, k);
-            bool blocked = rt_probe(pl, __float2int_rz(psy), __float2int_rz(psx)) |
-                           rt_probe(pl, __float2int_rz(pey), __float2int_rz(pex));
-            float2 ps = make_float2(psx, psy);
+        if (have) mine = ld_stream_f4(edges + e);
+        const float psx = mine.x, psy = mine.y, pex = mine.z, pey = mine.w;
+        bool blocked = false, longer = false;
+        float2 ps = make_float2(psx, psy);
+        int M = 0;
+        if (have) {
+            blocked = rt_probe(pl, __float2int_rz(psy), __float2int_rz(psx)) | rt_probe(pl, __float2int_rz(pey), __float2int_rz(pex));
             if (!blocked) {
-                const int M = rt_march_M(rt_dist(psx, psy, pex, pey), 2.0f);
-                const float Mf = (float)M;
-                int f = 0; // first blocked index, 0 = none
-                for (int i0 = 1; i0 < M; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool hit = false;
-                    if (i < M) {
+                M = rt_march_M(rt_dist(psx, psy, pex, pey), 2.0f);
+                longer = M - 1 > kFirstHitLane;
+                if (!longer) {
+                    const float Mf = (float)M;
+                    float2 prev = ps; // the last free point so far
+                    for (int i = 1; i < M; i++) {
                         const float2 q = first_hit_point(psx, psy, pex, pey, i, Mf);
-                        hit = rt_probe(pl, __float2int_rz(q.y), __float2int_rz(q.x));
+                        if (rt_probe(pl, __float2int_rz(q.y), __float2int_rz(q.x))) {
+                            blocked = true;
+                            break;
+                        }
+                        prev = q;
                     }
-                    const unsigned hm = __ballot_sync(full, hit);
-                    if (hm) {
-                        f = i0 + __ffs(hm) - 1;
-                        break;
-                    }
+                    ps = blocked ? prev : make_float2(pex, pey);
                 }
-                if (f) {
-                    blocked = true;
-                    if (f > 1) ps = first_hit_point(psx, psy, pex, pey, f - 1, Mf);
-                } else
-                    ps = make_float2(pex, pey);
             }
-            if (blocked) bits |= 1u << k;
-            if (lane == 0) pstart[base + k] = ps;
         }
+        unsigned todo = __ballot_sync(full, longer);
+        while (todo) { // long edges: the whole warp marches one at a time
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float ax = __shfl_sync(full, psx, k), ay = __shfl_sync(full, psy, k);
+            const float bx = __shfl_sync(full, pex, k), by = __shfl_sync(full, pey, k);
+            const int Mk = __shfl_sync(full, M, k);
+            const float Mf = (float)Mk;
+            int f = 0; // first blocked index, 0 = none
+            for (int i0 = 1; i0 < Mk; i0 += 32) {
+                const int i = i0 + lane;
+                bool hit = false;
+                if (i < Mk) {
+                    const float2 q = first_hit_point(ax, ay, bx, by, i, Mf);
+                    hit = rt_probe(pl, __float2int_rz(q.y), __float2int_rz(q.x));
+                }
+                const unsigned hm = __ballot_sync(full, hit);
+                if (hm) {
+                    f = i0 + __ffs(hm) - 1;
+                    break;
+                }
+            }
+            if (lane == k) {
+                blocked = f != 0;
+                if (f > 1) ps = first_hit_point(ax, ay, bx, by, f - 1, Mf);
+                else if (f == 0) ps = make_float2(bx, by);
+            }
+        }
+        const unsigned bits = __ballot_sync(full, blocked);
+        if (have) pstart[e] = ps;
         if (lane == 0) out_bits[w] = bits;
     }
 }
