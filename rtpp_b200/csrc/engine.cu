@@ -182,10 +182,38 @@ __device__ __forceinline__ int knn_at_node(const EngView &ev, Inst &in, int x, K
         if (in.s.n == n0) return cnt;
         const int old_id = e.id;
         found = knn_warp_impl(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e, cnt, n0);
-        if (__all_sync(FULL, e.id == old_id)) { // no appended node entered the list: the cached edge verdicts stay valid
+        const unsigned diff = __ballot_sync(FULL, e.id != old_id);
+        if (diff == 0) { // no appended node entered the list: the cached edge verdicts stay valid
             if (lane == 0) in.nn_n[x] = in.s.n;
             __syncwarp();
             return found;
+        }
+        // ONE appended node entered a full list (the usual case: the root rewire pops every node between two accepted
+        // samples): the old entries moved down by one behind it, and the verdict of the new edge (x, nid) is already
+        // known if x sits in nid's own cached list — CrashDetection is symmetric in its end points (t and 1 - t are
+        // both exact dyadic fractions, RTRRT.cpp:214-217) — so the cached bits are shifted instead of marching 25 edges.
+        if (cnt == 25 && found == 25 && in.nn_blk_ep[x] == in.pl_epoch) {
+            const int pos = __ffs(diff) - 1;
+            const int prev_old = __shfl_up_sync(FULL, old_id, 1);
+            if (__all_sync(FULL, lane <= pos || lane >= 25 || e.id == prev_old)) {
+                const int nid = __shfl_sync(FULL, e.id, pos);
+                if (in.nn_blk_ep[nid] == in.pl_epoch) {
+                    const int cn = min(in.nn_n[nid], 25);
+                    int other = -1;
+                    if (lane < cn) other = in.nn_ids[(size_t)nid * 25 + lane];
+                    const unsigned m = __ballot_sync(FULL, other == x);
+                    if (m) {
+                        const unsigned v = ((unsigned)in.nn_blk[nid] >> (__ffs(m) - 1)) & 1u;
+                        const unsigned old = (unsigned)in.nn_blk[x];
+                        const unsigned nb = ((old & ((1u << pos) - 1u)) | (v << pos) | ((old >> pos) << (pos + 1))) & 0x1ffffffu;
+                        __syncwarp();
+                        if (lane < found) in.nn_ids[(size_t)x * 25 + lane] = e.id;
+                        if (lane == 0) in.nn_n[x] = in.s.n, in.nn_blk[x] = (int)nb;
+                        __syncwarp();
+                        return found;
+                    }
+                }
+            }
         }
     } else
         found = knn_warp(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e);
@@ -367,6 +395,17 @@ __device__ void expand_one(const EngView &ev, Inst &in, const MarchThresholds &m
             in.cp[id] = cp_make((uint32_t)(key >> 32), x_min);
         }
         in.s.n = id + 1;
+        // the new node's own neighbour list and edge verdicts are known already: itself (d2 = 0; the nearest other node is
+        // more than RnearR away), then the neighbours of the sample in the same (d2, id) order; the self edge is free (the
+        // sample's pixel was probed with every edge above) and CrashDetection(sample, x_near) = CrashDetection(x_near,
+        // sample).  Its first pop then needs neither a search nor a march, and its neighbours can take the verdict of
+        // their new edge from here (knn_at_node).
+        {
+            const unsigned bits = __ballot_sync(FULL, blk);
+            if (lane == 0) in.nn_ids[(size_t)id * 25] = id;
+            if (have && lane < 24) in.nn_ids[(size_t)id * 25 + lane + 1] = e.id;
+            if (lane == 0) in.nn_n[id] = id + 1, in.nn_blk[id] = (int)((bits << 1) & 0x1ffffffu), in.nn_blk_ep[id] = in.pl_epoch;
+        }
         __syncwarp();
         qr_push(ev, in, lane == 0, id);
         maybe_rebuild(ev, in);
