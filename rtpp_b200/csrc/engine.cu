@@ -174,12 +174,12 @@ __device__ __forceinline__ int knn_at_node(const EngView &ev, Inst &in, int x, K
     if (n0 > 0 && in.s.n - n0 <= 512) {
         const int cnt = min(n0, 25);
         e.d2 = CUDART_INF, e.id = 0x7fffffff;
+        if (lane < cnt) e.id = in.nn_ids[(size_t)x * 25 + lane];
+        if (in.s.n == n0) return cnt; // nothing appended since: the callers use the ids only
         if (lane < cnt) {
-            e.id = in.nn_ids[(size_t)x * 25 + lane];
             const float2 q = in.xy[e.id];
             e.d2 = knn_d2((double)px.x, (double)px.y, q.x, q.y);
         }
-        if (in.s.n == n0) return cnt;
         const int old_id = e.id;
         found = knn_warp_impl(inst_grid(ev, in), (double)px.x, (double)px.y, 25, e, cnt, n0);
         const unsigned diff = __ballot_sync(FULL, e.id != old_id);
