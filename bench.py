@@ -9,9 +9,14 @@ Workload (BASELINE.json configs[3], the largest single-GPU configuration): AM-RR
 tick: the 999 999 tree edges (R3 re-cost, AMRRT.cpp:185-199) + the 25e6 rewire edges node ->
 25-NN (AMRRT.cpp:496-500), divisor 2, both planes; 26.0e6 edges, 416 MB of end points (> L2).
 metric = edge collision checks / s.  `value`: edge list resident in HBM, K launches timed with
-CUDA events on the launching stream.  `e2e`: the same batch through the host-buffer C-ABI call
-(rtpp_edges_check) from pinned host memory, H2D + kernel + D2H of the verdict words every step.
-Extras (k-NN queries/s, tick latencies, replan iterations/s) are measured outside the timed region.
+CUDA events on the launching stream.  `e2e`: one replanning tick over the same 26.0e6 edges through the
+host-buffer C-ABI calls a planner class makes (rtpp_map_draw_dynamic + rtpp_tick_edges_check): the
+obstacle poses go in, the verdict words come back to pinned host memory, the tree stays resident;
+the same batch as an explicit end-point list from the host (rtpp_edges_check, 416 MB H2D per step)
+is reported beside it.  `roofline`: algorithmic bytes of the step / launch time against the measured
+HBM peak, plus the L2 form against denominators measured in the same run (rtpp_measure_peaks).
+Extras (the other edge kernels, k-NN queries/s, propagate / relax latency, the four planners'
+replan iterations/s and tick latencies against the CPU port) are measured outside the timed region.
 
 --impl reference: the reference's own AMRRTplanner::CrashDetection (compiled in place into
 oracle/_ref; the oracle port if that library is absent) over the same edges on all host threads.
