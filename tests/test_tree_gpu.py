@@ -212,3 +212,64 @@ def test_relax_lattice_ties_schedule_independent(ctx, oracle):
         d = np.sqrt(((xy[ch] - xy[p1[ch]]) ** 2).sum(1, dtype=np.float32), dtype=np.float32)
         assert np.array_equal((c1[p1[ch]] + d).astype(np.float32).view(np.uint32), c1[ch].view(np.uint32))
     ctx.dev_free(d_idx)
+
+
+@pytest.mark.parametrize("free_only", [False, True])
+def test_relax_ragged_tables_and_tiny_graphs(ctx, oracle, free_only):
+    """Ragged inputs of the bulk relax: a single node, rows with missing neighbours (-1), self loops, nodes nobody
+    points at, a graph cut in two by a wall (the far side keeps its colliding start cost under the AM-RRT* rule and
+    gets a colliding cost through the wall under the RT-RRT* rule), and costs that are already a fixpoint."""
+    H = W = 256
+    S = np.zeros((H, W), np.uint8)
+    S[:, 120:136] = 255  # a wall from top to bottom
+    ctx.map_set_plane(1, S)
+    ctx.map_clear_plane(2)
+    rng = np.random.default_rng(11)
+
+    def run(xy, idx, par, cost0, col0):
+        n, k = idx.shape
+        ctx.nodes_reset(4, max(n, 1), W, H)
+        ctx.nodes_append(xy)
+        d_idx = ctx.dev_alloc(max(idx.nbytes, 4))
+        ctx.h2d(d_idx, np.ascontiguousarray(idx))
+        ctx.tree_set(par, cost0, col0)
+        ctx.sync()
+        buckets = ctx.relax_dev(d_idx, k, 5, 1, free_only=free_only)
+        got = ctx.tree_get()
+        fc, fl, _, _ = oracle.relax_fixpoint(S, None, xy, idx, 5, 1, cost0, col0, par, free_only=free_only)
+        assert np.array_equal(got[2], fl)
+        free = fl == 0
+        assert np.array_equal(got[1][free].view(np.uint32), fc[free].view(np.uint32))
+        # a second call from the fixpoint changes nothing
+        ctx.relax_dev(d_idx, k, 5, 1, free_only=free_only)
+        again = ctx.tree_get()
+        assert all(np.array_equal(a, b) for a, b in zip(got, again))
+        ctx.dev_free(d_idx)
+        return got, buckets
+
+    # one node, no neighbours
+    got, _ = run(np.array([[10.5, 10.5]], np.float32), np.full((1, 3), -1, np.int32), np.array([-1], np.int32),
+                 np.zeros(1, np.float32), np.zeros(1, np.uint8))
+    assert got[0][0] == -1 and got[1][0] == 0 and got[2][0] == 0
+    # two sides of the wall, ragged rows
+    n, k = 400, 6
+    xy = np.concatenate([rng.random((n // 2, 2)) * [100, 250] + [5, 3], rng.random((n // 2, 2)) * [100, 250] + [145, 3]]).astype(np.float32)
+    d = ((xy[:, None, :].astype(np.float64) - xy[None, :, :]) ** 2).sum(2)
+    idx = np.argsort(d, axis=1, kind="stable")[:, :k].astype(np.int32)   # column 0 = the node itself (self loop)
+    idx[rng.random((n, k)) < 0.25] = -1                                     # missing entries anywhere in a row
+    idx[7] = -1                                                             # a node without any out-edge
+    idx[idx == 9] = -1                                                      # a node nobody points at
+    # bridges through the wall (blocked edges)
+    idx[3, 1], idx[5, 2] = n // 2 + 4, n // 2 + 8
+    par = np.full(n, 0, np.int32)
+    par[0] = -1
+    cost0 = np.full(n, 3.4e38, np.float32)
+    col0 = np.ones(n, np.uint8)
+    cost0[0], col0[0] = 0.0, 0
+    got, buckets = run(xy, idx, par, cost0, col0)
+    assert buckets >= 1
+    left_free = got[2][: n // 2] == 0
+    assert left_free.sum() > n // 4
+    assert (got[2][n // 2 :] == 1).all()  # nothing on the far side is reachable without crossing the wall
+    if free_only:
+        assert np.array_equal(got[1][n // 2 :].view(np.uint32), cost0[n // 2 :].view(np.uint32))
