@@ -43,27 +43,70 @@ __global__ void __launch_bounds__(256) tree_unpack_kernel(const cpword *__restri
     }
 }
 
-// (A) + child counting.  w[i] = {E(parent,i), |parent - i|} packed like a cost.
+// (A) + child counting.  w[i] = {E(parent,i), |parent - i|} packed like a cost.  A lane owns a tree edge; edges of 32
+// march steps or more (a node that found no near parent hangs far away) are marched by the whole warp afterwards, and
+// the children of the ROOT — the one hub a tree may have: thousands of nodes in the synthetic C4 tree — are counted per
+// block, so that neither a lane-serial 2000-probe march nor 40 k atomics on one address sit on the critical path
+// (270 -> 33 us at C4).
 __global__ void __launch_bounds__(256)
 tree_edge_weights_kernel(PlaneView pl, const float2 *__restrict__ xy, const cpword *__restrict__ cp, int n, int root,
                          MarchThresholds divisor, uint32_t *__restrict__ w, int *__restrict__ child_count) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int p = cp_parent(cp[i]);
-        uint32_t wi = 0;
-        if (i != root && p >= 0 && p < n) {
-            const float2 a = xy[p], b = xy[i];
-            wi = cost_pack(rt_edge_blocked(pl, a.x, a.y, b.x, b.y, divisor), rt_dist(a.x, a.y, b.x, b.y));
-            atomicAdd(&child_count[p], 1);
+    __shared__ int root_children;
+    if (threadIdx.x == 0) root_children = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + lane;
+        int p = -1;
+        if (i < n) p = cp_parent(cp[i]);
+        const bool edge = i < n && i != root && p >= 0 && p < n;
+        float2 a = make_float2(0.f, 0.f), b = a;
+        bool blk = false, longer = false;
+        if (edge) {
+            a = xy[p], b = xy[i];
+            longer = rt_march_P(divisor, rt_sqlen(a.x, a.y, b.x, b.y)) >= 32;
+            if (!longer) blk = rt_edge_blocked(pl, a.x, a.y, b.x, b.y, divisor);
         }
-        w[i] = wi;
+        unsigned todo = __ballot_sync(0xffffffffu, longer);
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const bool bk = rt_edge_blocked_warp(pl, __shfl_sync(0xffffffffu, a.x, k), __shfl_sync(0xffffffffu, a.y, k),
+                                                 __shfl_sync(0xffffffffu, b.x, k), __shfl_sync(0xffffffffu, b.y, k), divisor);
+            if (lane == k) blk = bk;
+        }
+        if (i < n) w[i] = edge ? cost_pack(blk, rt_dist(a.x, a.y, b.x, b.y)) : 0u;
+        const unsigned to_root = __ballot_sync(0xffffffffu, edge && p == root);
+        if (lane == 0 && to_root) atomicAdd(&root_children, __popc(to_root));
+        if (edge && p != root) atomicAdd(&child_count[p], 1);
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && root_children) atomicAdd(&child_count[root], root_children);
 }
 
+// (B) children lists by parent (counting sort: cursor = exclusive scan of the counts).  The root's children take their
+// slots block by block (one atomic per 256 nodes) for the same reason as above.
 __global__ void __launch_bounds__(256) tree_children_kernel(const cpword *__restrict__ cp, int n, int root,
                                                            int *__restrict__ cursor, int *__restrict__ children) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int p = cp_parent(cp[i]);
-        if (i != root && p >= 0 && p < n) children[atomicAdd(&cursor[p], 1)] = i;
+    __shared__ int blk_cnt, blk_base;
+    const int lane = threadIdx.x & 31;
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        if (threadIdx.x == 0) blk_cnt = 0;
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+        int p = -1;
+        if (i < n) p = cp_parent(cp[i]);
+        const bool edge = i < n && i != root && p >= 0 && p < n;
+        const bool to_root = edge && p == root;
+        const unsigned m = __ballot_sync(0xffffffffu, to_root);
+        int warp_base = 0;
+        if (lane == 0 && m) warp_base = atomicAdd(&blk_cnt, __popc(m));
+        warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+        __syncthreads();
+        if (threadIdx.x == 0 && blk_cnt) blk_base = atomicAdd(&cursor[root], blk_cnt);
+        __syncthreads();
+        if (to_root) children[blk_base + warp_base + __popc(m & ((1u << lane) - 1u))] = i;
+        else if (edge) children[atomicAdd(&cursor[p], 1)] = i;
     }
 }
 
@@ -75,20 +118,88 @@ __global__ void __launch_bounds__(256) tree_children_kernel(const cpword *__rest
 // children are spread over the lanes), or — a root that thousands of nodes hang from — the whole grid after the
 // level's barrier (counters[4 + (L&1)] = how many such nodes level L met, listed behind the counters).
 static constexpr int kTreeBig = 2048;
-__device__ __forceinline__ void tree_visit(int c, int p, uint32_t hp, const uint32_t *__restrict__ w, cpword *__restrict__ cp,
-                                           uint8_t *__restrict__ flags) {
+__device__ __forceinline__ uint32_t tree_visit(int c, int p, uint32_t hp, const uint32_t *__restrict__ w, cpword *__restrict__ cp,
+                                               uint8_t *__restrict__ flags) {
     const uint32_t hn = cost_add(hp, w[c]);
     if (flags) {
         const uint32_t ho = cp_hi(cp[c]);
         flags[c] = (uint8_t)(((hn >> 31) & ~(ho >> 31) & 1u) | ((hn > ho) ? 2u : 0u) | ((hn < ho) ? 4u : 0u));
     }
     cp[c] = cp_make(hn, p);
+    return hn;
 }
+// One warp step of the walk: lane l expands parent p (cost word hp, children [s, e)); the warp reserves the slots of
+// all its children at once — in the block's shared-memory queue `qo` when they fit (the block then keeps walking
+// down these subtrees without a grid barrier), else in the global next frontier.
+constexpr int kTreeQ = 2048; // entries per shared-memory queue (node, cost word)
+struct TreeBlock {
+    int2 q[2][kTreeQ];
+    int qn[2];
+};
+__device__ __forceinline__ void tree_expand(TreeBlock &sm, int qo, int p, uint32_t hp, int s, int e, const int *__restrict__ children,
+                                            const uint32_t *__restrict__ w, cpword *__restrict__ cp, uint8_t *__restrict__ flags, int *nxt,
+                                            int *cnt_next, int *reached, int *big, int *big_count, int big_cap) {
+    const int lane = threadIdx.x & 31;
+    int cnt = e - s;
+    if (cnt > kTreeBig) { // expanded by the grid after the barrier
+        const int k = atomicAdd(big_count, 1);
+        if (k < big_cap) big[k] = p;
+        cnt = 0;
+    }
+    int x = cnt;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, x, 31);
+    if (total == 0) return;
+    int base = -1; // >= 0: slot in the shared-memory queue
+    if (lane == 31) {
+        int old = sm.qn[qo], assumed;
+        do {
+            assumed = old;
+            if (assumed + total > kTreeQ) break;
+            old = atomicCAS(&sm.qn[qo], assumed, assumed + total);
+        } while (old != assumed);
+        if (assumed + total <= kTreeQ) base = assumed;
+        atomicAdd(reached, total);
+    }
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const bool local = base >= 0;
+    if (!local) {
+        if (lane == 31) base = atomicAdd(cnt_next, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+    }
+    base += x - cnt;
+    if (cnt <= 8)
+        for (int j = 0; j < cnt; j++) {
+            const int c = children[s + j];
+            const uint32_t hn = tree_visit(c, p, hp, w, cp, flags);
+            if (local) sm.q[qo][base + j] = make_int2(c, (int)hn);
+            else nxt[base + j] = c;
+        }
+    unsigned wide = __ballot_sync(0xffffffffu, cnt > 8);
+    while (wide) {
+        const int o = __ffs(wide) - 1;
+        wide &= wide - 1;
+        const int po = __shfl_sync(0xffffffffu, p, o), so = __shfl_sync(0xffffffffu, s, o), co = __shfl_sync(0xffffffffu, cnt, o);
+        const int bo = __shfl_sync(0xffffffffu, base, o);
+        const uint32_t ho = __shfl_sync(0xffffffffu, hp, o);
+        for (int j = lane; j < co; j += 32) {
+            const int c = children[so + j];
+            const uint32_t hn = tree_visit(c, po, ho, w, cp, flags);
+            if (local) sm.q[qo][bo + j] = make_int2(c, (int)hn);
+            else nxt[bo + j] = c;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int *__restrict__ children,
                 const uint32_t *__restrict__ w, cpword *__restrict__ cp, int *__restrict__ frontier, int capacity,
                 int *__restrict__ counters, uint8_t *__restrict__ flags, int big_cap) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ TreeBlock sm;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, lane = tid & 31;
     int *big_list = counters + 8; // [2][big_cap]
     if (tid == 0) {
@@ -103,8 +214,11 @@ tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int 
         const int *cur = frontier + (size_t)(level & 1) * capacity;
         int *nxt = frontier + (size_t)((level + 1) & 1) * capacity;
         int *big = big_list + (size_t)(level & 1) * big_cap;
+        int *big_count = &counters[4 + (level & 1)];
         if (tid == 0) counters[(level + 2) % 3] = 0;
-        // one frontier node per thread; the warp reserves its children's slots with ONE atomicAdd
+        if (threadIdx.x < 2) sm.qn[threadIdx.x] = 0;
+        __syncthreads();
+        // this block's share of the global frontier, one node per thread
         for (int f0 = (tid & ~31); f0 < cur_n; f0 += nth) {
             const int f = f0 + lane;
             int p = -1, s = 0, e = 0;
@@ -114,41 +228,27 @@ tree_bfs_kernel(int n, int root, const int *__restrict__ child_start, const int 
                 hp = cp_hi(cp[p]);
                 s = child_start[p], e = child_start[p + 1];
             }
-            int cnt = e - s;
-            if (cnt > kTreeBig) { // expanded by the grid after the barrier
-                const int k = atomicAdd(&counters[4 + (level & 1)], 1);
-                if (k < big_cap) big[k] = p;
-                cnt = 0;
-            }
-            int x = cnt;
-            for (int off = 1; off < 32; off <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, x, off);
-                if (lane >= off) x += y;
-            }
-            const int total = __shfl_sync(0xffffffffu, x, 31);
-            int base = 0;
-            if (lane == 31 && total) base = atomicAdd(cnt_next, total);
-            base = __shfl_sync(0xffffffffu, base, 31) + x - cnt;
-            if (cnt <= 8)
-                for (int j = 0; j < cnt; j++) {
-                    const int c = children[s + j];
-                    tree_visit(c, p, hp, w, cp, flags);
-                    nxt[base + j] = c;
+            tree_expand(sm, 0, p, hp, s, e, children, w, cp, flags, nxt, cnt_next, &counters[3], big, big_count, big_cap);
+        }
+        // ... then down the subtrees it holds, level by level inside the block (a __syncthreads per level instead of a
+        // grid barrier; the cost word travels with the node, so a step is children -> weight -> store)
+        for (int pq = 0;; pq ^= 1) {
+            __syncthreads();
+            const int m = sm.qn[pq];
+            if (m == 0) break;
+            if (threadIdx.x == 0) sm.qn[pq ^ 1] = 0; // (nobody reads the drained queue's count again)
+            __syncthreads();
+            for (int f0 = (threadIdx.x & ~31); f0 < m; f0 += blockDim.x) {
+                const int f = f0 + lane;
+                int p = -1, s = 0, e = 0;
+                uint32_t hp = 0;
+                if (f < m) {
+                    const int2 ent = sm.q[pq][f];
+                    p = ent.x, hp = (uint32_t)ent.y;
+                    s = child_start[p], e = child_start[p + 1];
                 }
-            unsigned wide = __ballot_sync(0xffffffffu, cnt > 8);
-            while (wide) {
-                const int o = __ffs(wide) - 1;
-                wide &= wide - 1;
-                const int po = __shfl_sync(0xffffffffu, p, o), so = __shfl_sync(0xffffffffu, s, o), co = __shfl_sync(0xffffffffu, cnt, o);
-                const int bo = __shfl_sync(0xffffffffu, base, o);
-                const uint32_t ho = __shfl_sync(0xffffffffu, hp, o);
-                for (int j = lane; j < co; j += 32) {
-                    const int c = children[so + j];
-                    tree_visit(c, po, ho, w, cp, flags);
-                    nxt[bo + j] = c;
-                }
+                tree_expand(sm, pq ^ 1, p, hp, s, e, children, w, cp, flags, nxt, cnt_next, &counters[3], big, big_count, big_cap);
             }
-            if (lane == 31 && total) atomicAdd(&counters[3], total);
         }
         grid.sync();
         const int nb = min(counters[4 + (level & 1)], big_cap);
