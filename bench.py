@@ -517,9 +517,62 @@ def measure_extras(wl, torch, sweep):
     out["rewire_sweeps"] = sweeps
     out["rewire_schedule"] = "work list by cost bucket (near-far), blocks chase their improvements through shared-memory queues; wall time of the host call, best of 3"
     out.update(measure_replanning(ctx, sweep))
+    try:
+        out["dropin_rtrrt_class"] = measure_dropin_class()
+    except Exception as exc:  # an extra must not cost the bench line
+        out["dropin_rtrrt_class"] = {"error": repr(exc)}
     out.update(measure_fmt(ctx))
     out.update(measure_cdrt(ctx))
     out.update(measure_amrrt(ctx))
+    return out
+
+
+def measure_dropin_class(ticks=24, dt=5000):
+    """BASELINE configs[0] through the drop-in boundary itself: the C++ RTRRTplanner class of rtpp_b200/planners (same method
+    names as the reference's, GPU engine underneath) against the reference's OWN class compiled in place (oracle/_ref: RTRRT.cpp
+    unmodified; its two absent third-party libraries are stand-ins — cv::Mat shim, brute-force exact k-NN for CGAL), both driven
+    through DrawDObsmap + UpdateTree + ExpandRewiring(50 ms of virtual time = 1e4 clock reads) + GetPath on bundled GAME0 with the
+    scripted obstacle set of RTRRT/test/testD.cpp, same rand() stream; trees compared bit for bit at the end."""
+    from oracle import loader as orc
+    from rtpp_b200 import capi
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import TESTD_OUTLINES
+
+    S = orc.load_map("GAME0")
+    rand = orc.rand31(5, 3_000_000)
+    obs = [(0, 370, 388, 0.0, 57, [(0, 0)]), (0, 2370, 630, 0.0, 114, [(0, 0)]),
+           (1, 1364, 1364, 0.78539816, 0, TESTD_OUTLINES[3]), (1, 1340, 2520, 0.0, 0, TESTD_OUTLINES[4])]
+    out = {"map": "GAME0", "ticks": ticks, "virtual_dt_ns": dt}
+    trees = []
+    for name in ("gpu_class", "reference_class"):
+        try:
+            pl = capi.PlannerRTRRT(S) if name == "gpu_class" else orc.RefRTRRT(S)
+        except FileNotFoundError:
+            out[name] = "unavailable (oracle/_ref not built)"
+            continue
+        pl.set_clock(dt)
+        pl.set_rand(rand)
+        pl.set_agent(350.0, 2350.0)
+        pl.set_goal(1400.0, 2050.0)
+        for num, (typ, x, y, ang, rad, outline) in enumerate(obs):
+            pl.add_obstacle(num, typ, x, y, ang, rad, outline)
+        lat = []
+        for _ in range(ticks):
+            t0 = time.perf_counter()
+            if name == "gpu_class":
+                pl.main_task()
+            else:
+                pl.draw_dobs(), pl.update_tree(), pl.expand_rewiring(50)
+            path = pl.get_path()
+            lat.append(time.perf_counter() - t0)
+        trees.append(pl.dump())
+        out[name + "_tick_ms_p50"] = float(np.median(lat)) * 1e3
+        out[name + "_nodes"] = int(len(trees[-1][0]))
+        out[name + "_path_len"] = int(len(path[0]))
+        pl.close()
+    if len(trees) == 2:
+        out["trees_match"] = bool(all(np.array_equal(a.view(np.uint8), b.view(np.uint8)) for a, b in zip(trees[0], trees[1])))
     return out
 
 
