@@ -225,6 +225,10 @@ RTPP_API int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances
 RTPP_API int rtpp_engine_destroy(rtpp_engine *e);
 /* plane 1 = static (Obsmap), 2 = dynamic (DObsmap; src NULL = all free) of map slot 0..15 */
 RTPP_API int rtpp_engine_set_map(rtpp_engine *e, int slot, int plane, const uint8_t *rowmajor, int W, int H);
+/* DrawDObsmap (RTRRT.cpp:138-169, AMRRT.cpp:202-233) of a map slot on the device, arguments as rtpp_map_draw_dynamic: the
+ * slot's dynamic plane is cleared, the circles and polygons are drawn into its bit tiles, S|D is refreshed; stream-ordered. */
+RTPP_API int rtpp_engine_draw_dynamic(rtpp_engine *e, int slot, const int32_t *circles, int n_circles, const int32_t *poly_xy,
+                                      const int32_t *poly_sizes, int n_polys);
 RTPP_API int rtpp_engine_init_instances(rtpp_engine *e, const int32_t *map_slot, const float *agent_xy, const float *goal_xy);
 RTPP_API int rtpp_engine_set_inputs(rtpp_engine *e, const float *agent_xy, const float *goal_xy, const float *samples_xy,
                                     const int32_t *n_samples);

@@ -23,6 +23,9 @@
 
 #include "nodes.cuh"
 
+int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t *circles, int n_circles, const int32_t *poly_xy,
+                     const int32_t *poly_sizes, int n_polys); // raster.cu
+
 #define FULL 0xffffffffu
 
 struct EngInst {
@@ -1126,6 +1129,25 @@ int rtpp_engine_set_map(rtpp_engine *e, int slot, int plane, const uint8_t *src,
     e->v.plane_epoch[slot]++; // cached edge verdicts of this slot's instances are stale now
     e->v.planes[slot].w = e->plane_sd[slot];
     e->v.planes[slot].W = W, e->v.planes[slot].H = H, e->v.planes[slot].tilesX = tilesX;
+    return RTPP_OK;
+}
+
+// DrawDObsmap of a map slot on the device (RTRRT.cpp:138-169, AMRRT.cpp:202-233): clears the slot's dynamic plane, draws the
+// circles ((cx, cy, r) int triples) and polygons straight into its bit tiles and refreshes S|D — a tick ships the obstacle
+// poses instead of an H*W byte plane.  Stream-ordered, no synchronisation.
+int rtpp_engine_draw_dynamic(rtpp_engine *e, int slot, const int32_t *circles, int n_circles, const int32_t *poly_xy,
+                             const int32_t *poly_sizes, int n_polys) {
+    if (!e || slot < 0 || slot >= 16 || n_circles < 0 || n_polys < 0 || (n_circles && !circles) || (n_polys && (!poly_xy || !poly_sizes)))
+        return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    if (!e->plane_s[slot]) RTPP_FAIL(ctx, RTPP_ERR_STATE, "set the static plane of the slot first");
+    const int W = e->W[slot], H = e->H[slot];
+    const size_t words = e->plane_words[slot];
+    int rc = rtpp_raster_into(ctx, e->plane_d[slot], W, H, circles, n_circles, poly_xy, poly_sizes, n_polys); // clears first
+    if (rc) return rc;
+    engine_merge_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
+    RTPP_LAUNCHED(ctx);
+    e->v.plane_epoch[slot]++; // cached edge verdicts of this slot's instances are stale now
     return RTPP_OK;
 }
 

@@ -14,6 +14,12 @@ void AMRRTplanner::OnStaticPlane() {
     if (eng_) rtpp_engine_destroy(eng_), eng_ = nullptr;
     started_ = false;
 }
+bool AMRRTplanner::OnDynamicShapes(const int32_t *circles, int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, int n_polys) {
+    if (!EnsureEngine()) return true; // no engine yet: nothing to refresh
+    const int rc = rtpp_engine_draw_dynamic(eng_, 0, circles, n_circles, poly_xy, poly_sizes, n_polys);
+    if (rc) Fail("AMRRTplanner", "rtpp_engine_draw_dynamic", rc);
+    return rc == 0;
+}
 void AMRRTplanner::OnDynamicPlane() {
     if (EnsureEngine()) rtpp_engine_set_map(eng_, 0, 2, DObsmap.data.data(), shapeX, shapeY);
 }

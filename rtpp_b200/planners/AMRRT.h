@@ -30,6 +30,7 @@ class AMRRTplanner : public rtppPlannerBase {
     void UploadDiffusion();
     void OnStaticPlane() override;
     void OnDynamicPlane() override;
+    bool OnDynamicShapes(const int32_t *circles, int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, int n_polys) override;
 
   public:
     std::map<RTpoint, RTrrt_NodeAttribute> Node_Map; // filled by SyncNodeMap()

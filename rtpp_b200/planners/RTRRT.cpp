@@ -141,6 +141,7 @@ void RTRRTplanner::SetDObsmap(const uint8_t *plane) {
 void RTRRTplanner::DrawDObsmap(void) {
     if (DObsmap.empty()) return;
     DObsmap.zero();
+    std::vector<int32_t> circles, poly_xy, poly_sizes;
     for (const auto &kv : DObstacles) {
         const RTrrt_DynamicObstacle &obs = kv.second;
         const float sinangle = sinf(obs.angle), cosangle = cosf(obs.angle);
@@ -150,11 +151,28 @@ void RTRRTplanner::DrawDObsmap(void) {
             pts.push_back({(int)((a - b) + obs.x), (int)((c + d) + obs.y)});
         }
         if (obs.DObsType == 0)
-            for (const auto &q : pts) rtpp::fill_circle(DObsmap, q.first, q.second, (int)obs.radius, 127);
-        else if (obs.DObsType == 1)
+            for (const auto &q : pts) {
+                rtpp::fill_circle(DObsmap, q.first, q.second, (int)obs.radius, 127);
+                circles.push_back(q.first), circles.push_back(q.second), circles.push_back((int)obs.radius);
+            }
+        else if (obs.DObsType == 1) {
             rtpp::fill_polygon(DObsmap, pts, 127);
+            for (const auto &q : pts) poly_xy.push_back(q.first), poly_xy.push_back(q.second);
+            poly_sizes.push_back((int32_t)pts.size());
+        }
     }
-    SetDObsmap(DObsmap.data.data());
+    // The public DObsmap member above stays what the reference's is (callers draw it); the device planes are drawn from
+    // the same integer shapes by the library (pixel-identical rasteriser), so a tick uploads poses, not two byte planes.
+    if (!ctx_) return;
+    bool device_ok = true;
+    for (int32_t v : poly_sizes) device_ok &= v <= 64; // the device rasteriser's vertex limit; beyond it the byte plane is uploaded
+    if (device_ok) {
+        const int nc = (int)circles.size() / 3, np = (int)poly_sizes.size();
+        int rc = rtpp_map_draw_dynamic(ctx_, circles.data(), nc, poly_xy.data(), poly_sizes.data(), np);
+        if (!rc && EnsureEngine()) rc = rtpp_engine_draw_dynamic(eng_, 0, circles.data(), nc, poly_xy.data(), poly_sizes.data(), np);
+        if (rc) Fail("rtpp_*_draw_dynamic", rc), device_ok = false;
+    }
+    if (!device_ok) SetDObsmap(DObsmap.data.data());
 }
 
 void RTRRTplanner::UploadAgentGoal() {

@@ -86,6 +86,8 @@ void rtppPlannerBase::SetDObsmap(const uint8_t *plane) {
 void rtppPlannerBase::DrawDObsmap(void) {
     if (DObsmap.empty()) return;
     DObsmap.zero();
+    std::vector<int32_t> circles, poly_xy, poly_sizes;
+    bool device_ok = true;
     for (const auto &kv : DObstacles) {
         const RTrrt_DynamicObstacle &obs = kv.second;
         const float sinangle = sinf(obs.angle), cosangle = cosf(obs.angle);
@@ -95,11 +97,27 @@ void rtppPlannerBase::DrawDObsmap(void) {
             pts.push_back({(int)((a - b) + obs.x), (int)((c + d) + obs.y)});
         }
         if (obs.DObsType == 0)
-            for (const auto &q : pts) rtpp::fill_circle(DObsmap, q.first, q.second, (int)obs.radius, 127);
-        else if (obs.DObsType == 1)
+            for (const auto &q : pts) {
+                rtpp::fill_circle(DObsmap, q.first, q.second, (int)obs.radius, 127);
+                circles.push_back(q.first), circles.push_back(q.second), circles.push_back((int)obs.radius);
+            }
+        else if (obs.DObsType == 1) {
             rtpp::fill_polygon(DObsmap, pts, 127);
+            for (const auto &q : pts) poly_xy.push_back(q.first), poly_xy.push_back(q.second);
+            poly_sizes.push_back((int32_t)pts.size());
+            device_ok &= pts.size() <= 64; // the device rasteriser's vertex limit; beyond it the byte plane is uploaded
+        }
     }
-    UploadDObsmap();
+    // The public DObsmap member stays what the reference's is; the device planes are drawn from the same integer shapes by
+    // the library's pixel-identical rasteriser, so a tick ships poses instead of byte planes.
+    if (!ctx_) return;
+    if (device_ok) {
+        const int nc = (int)circles.size() / 3, np = (int)poly_sizes.size();
+        int rc = rtpp_map_draw_dynamic(ctx_, circles.data(), nc, poly_xy.data(), poly_sizes.data(), np);
+        if (rc) Fail("DrawDObsmap", "rtpp_map_draw_dynamic", rc), device_ok = false;
+        else if (!OnDynamicShapes(circles.data(), nc, poly_xy.data(), poly_sizes.data(), np)) OnDynamicPlane();
+    }
+    if (!device_ok) UploadDObsmap();
 }
 bool rtppPlannerBase::EdgeBlocked(const RTpoint &ps, const RTpoint &pe, int divisor, int mask) {
     if (!ctx_) return true;

@@ -67,6 +67,8 @@ class rtppPlannerBase {
     bool Fail(const char *who, const char *what, int rc);
     virtual void OnStaticPlane() {}               // a new Obsmap was loaded
     virtual void OnDynamicPlane() {}              // DObsmap changed (upload to the engine)
+    // the same change as integer shapes (DrawDObsmap): return true when the engine drew them itself on the device
+    virtual bool OnDynamicShapes(const int32_t *, int, const int32_t *, const int32_t *, int) { return false; }
     void LoadGray(const uint8_t *gray, int rows, int cols, int th);
     bool LoadPGM(const char *path, int th);
     bool EdgeBlocked(const RTpoint &ps, const RTpoint &pe, int divisor, int mask);

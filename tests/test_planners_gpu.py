@@ -181,3 +181,39 @@ def test_cpp_bimap_reproduces_reference_golden(oracle):
             for i, a in enumerate(pl.dump()):  # Node_Map with parents, costs, invM and subs sizes
                 assert np.array_equal(a.view(np.uint8), z[f"t{k}_dump{i}"].view(np.uint8)), f"tick {k} dump {i}"
     pl.close()
+
+
+def test_cpp_planner_device_drawn_plane_equals_uploaded_plane(oracle):
+    """DrawDObsmap() ships the obstacle shapes and the library draws the ctx and engine planes on the device; a second
+    planner gets the SAME plane as uploaded bytes (SetDObsmap of the first one's public DObsmap member).  Both must
+    grow identical trees over moving obstacles — the device rasteriser, the host rasteriser and the upload path agree
+    wherever an edge probes them."""
+    from rtpp_b200 import capi
+
+    S = oracle.load_map("GAME0")
+    rand = oracle.rand31(17, 1_500_000)
+    pls = [capi.PlannerRTRRT(S), capi.PlannerRTRRT(S)]
+    obs = [(0, 700, 2300, 0.0, 90, [(0, 0), (40, 10)]), (1, 1000, 2200, 0.3, 0, TESTD_OUTLINES[1]), (1, 1364, 1364, 0.78539816, 0, TESTD_OUTLINES[3])]
+    for pl in pls:
+        pl.set_clock(20000)
+        pl.set_rand(rand)
+        pl.set_agent(350.0, 2350.0)
+        pl.set_goal(1400.0, 2050.0)
+    for num, (typ, x, y, ang, rad, outline) in enumerate(obs):
+        pls[0].add_obstacle(num, typ, x, y, ang, rad, outline)
+    for tick in range(6):
+        for num, (typ, x, y, ang, rad, outline) in enumerate(obs):  # the obstacles move and turn
+            pls[0].add_obstacle(num, typ, x + 15 * tick, y - 10 * tick, ang + 0.2 * tick, rad, outline)
+        pls[0].main_task()
+        plane = pls[0].get_dobs()
+        assert plane.any()
+        pls[1].set_dobs(plane)
+        pls[1].update_tree()
+        pls[1].expand_rewiring(50)
+        a, b = pls[0].dump(), pls[1].dump()
+        assert all(np.array_equal(u.view(np.uint8), v.view(np.uint8)) for u, v in zip(a, b)), tick
+        assert pls[0].rand_pos() == pls[1].rand_pos()
+        assert pls[0].get_path()[2] == pls[1].get_path()[2]
+    assert len(a[0]) > 50 and a[3].any()  # some nodes are currently behind an obstacle
+    for pl in pls:
+        pl.close()
