@@ -22,25 +22,35 @@ def single(ctx, orc, name="GAME0", goal=2, seed=7, dt=2000, ticks=60):
     r = orc.rand31(seed, 2_000_000)
     o = orc.CdrtCpu(fx, "oracle")
     g = rtpp_b200.CdrtPlanner(ctx, fx)
-    for p in (o, g):
+    try:  # the reference's own BImap (CDRT.cpp compiled in place; cv::Mat and CGAL k-NN are stand-ins), when it was built
+        ref = orc.CdrtCpu(fx, "ref")
+    except (FileNotFoundError, OSError):
+        ref = None
+    everyone = [p for p in (o, g, ref) if p is not None]
+    for p in everyone:
         sc.setup(p, name, goal, r, dt_ns=dt)
-    tc, tg = [], []
-    same = True
+    tc, tg, tr = [], [], []
+    same = same_ref = True
     for k in range(ticks):
-        for p, acc in ((o, tc), (g, tg)):
+        for p, acc in ((o, tc), (g, tg), (ref, tr)):
+            if p is None:
+                continue
             t0 = time.perf_counter()
             p.task()
             acc.append(time.perf_counter() - t0)
         pa, pb = o.get_path(), g.get_path()
         same &= bool(np.array_equal(pa[0], pb[0]) and pa[2] == pb[2])
+        if ref is not None:
+            pr = ref.get_path()
+            same_ref &= bool(np.array_equal(pr[0], pb[0]) and pr[2] == pb[2])
         t = (k + 1) * sc.TICK_S
         for i, wp in enumerate(sc.OBS_PATHS[name]):
             q = sc.along(wp, sc.OBS_SPEED * t)
-            for p in (o, g):
+            for p in everyone:
                 p.move_obstacle(i, float(q[0]), float(q[1]), float(sc.OBSTACLES[name][i][3]))
         if len(pa[0]) >= 2:
             a = sc.along(pa[0], sc.SPEED * sc.TICK_S)
-            for p in (o, g):
+            for p in everyone:
                 p.set_agent(float(a[0]), float(a[1]))
     da, db = o.dump(), g.dump()
     same &= all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(da, db))
@@ -48,6 +58,13 @@ def single(ctx, orc, name="GAME0", goal=2, seed=7, dt=2000, ticks=60):
     out = {"map": name, "ticks": ticks, "virtual_dt_ns": dt, "pops_per_tick": st["pops"] / ticks, "pushes_per_tick": st["pushes"] / ticks,
            "nodes": len(da[0]), "gpu_tick_ms_p50": float(np.median(tg) * 1e3), "cpu_tick_ms_p50": float(np.median(tc) * 1e3),
            "cpu_kind": "port (oracle/cdrt_oracle.hpp), 1 thread", "state_matches_cpu": bool(same), "gpu_status": st["status"]}
+    if ref is not None:
+        dr = ref.dump()
+        same_ref &= all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(dr, db))
+        out["reference_tick_ms_p50"] = float(np.median(tr) * 1e3)
+        out["reference_kind"] = "BImap::RTRT_task of the reference's CDRT.cpp compiled in place (oracle/_ref), 1 thread"
+        out["state_matches_reference"] = bool(same_ref)
+        ref.close()
     o.close()
     g.close()
     return out
