@@ -60,19 +60,21 @@ __device__ __forceinline__ int isqrt_floor(int v) {
     while ((s + 1) * (s + 1) <= v) s++;
     return s;
 }
-__global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t0, const int4 *__restrict__ circles, const int2 *__restrict__ step_of,
-                                                            int n_steps) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_steps) return;
-    const int4 c = circles[step_of[j].x]; // cx, cy, r, plane
-    const int dy = step_of[j].y;
-    const int dx = isqrt_floor(c.z * c.z - dy * dy);
-    if (dx < dy) return;
+__global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t0, const int4 *__restrict__ circles, int n_circles) {
+    // one block per circle, threads over the steps dy = 0, 1, ... of the first octant (the step list used to be built on
+    // the host: with one plane per planner instance that was hundreds of thousands of entries per tick)
+    if ((int)blockIdx.x >= n_circles) return;
+    const int4 c = circles[blockIdx.x]; // cx, cy, r, plane
+    if (c.z < 0 || c.z > 23000) return; // r^2 must fit the exact integer arithmetic below
     const TileTarget t = tile_plane(t0, c.w);
-    tile_span(t, c.y - dy, c.x - dx, c.x + dx);
-    tile_span(t, c.y + dy, c.x - dx, c.x + dx);
-    tile_span(t, c.y - dx, c.x - dy, c.x + dy);
-    tile_span(t, c.y + dx, c.x - dy, c.x + dy);
+    for (int dy = threadIdx.x; dy <= c.z; dy += blockDim.x) {
+        const int dx = isqrt_floor(c.z * c.z - dy * dy);
+        if (dx < dy) break; // past the octant's end (dx - dy only falls from here on)
+        tile_span(t, c.y - dy, c.x - dx, c.x + dx);
+        tile_span(t, c.y + dy, c.x - dx, c.x + dx);
+        tile_span(t, c.y - dx, c.x - dy, c.x + dy);
+        tile_span(t, c.y + dx, c.x - dy, c.x + dy);
+    }
 }
 
 // polygon vertices: pts[first .. first+count) ; edge k joins vertex k-1 (cyclic) to vertex k
@@ -80,40 +82,34 @@ struct PolyDesc {
     int first, count, ymin, ymax, inst;
 };
 
-// outline: one warp per polygon edge, lanes stride over the Bresenham points
+// outline: one block per polygon, its warps take the edges in turn, lanes stride over the Bresenham points
 __global__ void __launch_bounds__(128) raster_poly_outline_kernel(TileTarget t0, const int2 *__restrict__ pts, const PolyDesc *__restrict__ polys,
-                                                                 const int2 *__restrict__ edge_of, int n_edges) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n_edges) return;
-    const PolyDesc pd = polys[edge_of[w].x];
+                                                                 int n_polys) {
+    if ((int)blockIdx.x >= n_polys) return;
+    const int lane = threadIdx.x & 31;
+    const PolyDesc pd = polys[blockIdx.x];
     const TileTarget t = tile_plane(t0, pd.inst);
-    const int k = edge_of[w].y;
-    int2 a = pts[pd.first + (k + pd.count - 1) % pd.count], b = pts[pd.first + k];
-    if (b.x < a.x) {
-        const int2 s = a;
-        a = b, b = s;
-    }
-    const int ddx = b.x - a.x, sgn = b.y < a.y ? -1 : 1, ddy = (b.y - a.y) * sgn;
-    const bool steep = ddy > ddx;
-    const long long big = steep ? ddy : ddx, small = steep ? ddx : ddy;
-    for (long long i = lane; i <= big; i += 32) {
-        const long long off = big ? (2 * small * i + big - 1) / (2 * big) : 0; // minor-axis offset of point i
-        const int x = steep ? a.x + (int)off : a.x + (int)i;
-        const int y = steep ? a.y + sgn * (int)i : a.y + sgn * (int)off;
-        tile_put(t, x, y);
+    for (int k = threadIdx.x >> 5; k < pd.count; k += blockDim.x >> 5) {
+        int2 a = pts[pd.first + (k + pd.count - 1) % pd.count], b = pts[pd.first + k];
+        if (b.x < a.x) {
+            const int2 s = a;
+            a = b, b = s;
+        }
+        const int ddx = b.x - a.x, sgn = b.y < a.y ? -1 : 1, ddy = (b.y - a.y) * sgn;
+        const bool steep = ddy > ddx;
+        const long long big = steep ? ddy : ddx, small = steep ? ddx : ddy;
+        for (long long i = lane; i <= big; i += 32) {
+            const long long off = big ? (2 * small * i + big - 1) / (2 * big) : 0; // minor-axis offset of point i
+            const int x = steep ? a.x + (int)off : a.x + (int)i;
+            const int y = steep ? a.y + sgn * (int)i : a.y + sgn * (int)off;
+            tile_put(t, x, y);
+        }
     }
 }
 
 // fill: one thread per (polygon, row); at most kMaxPolyEdges edges per polygon
 static constexpr int kMaxPolyEdges = 64;
-__global__ void __launch_bounds__(128) raster_poly_fill_kernel(TileTarget t0, const int2 *__restrict__ pts, const PolyDesc *__restrict__ polys,
-                                                              const int2 *__restrict__ row_of, int n_rows) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    const PolyDesc pd = polys[row_of[r].x];
-    const TileTarget t = tile_plane(t0, pd.inst);
-    const int y = row_of[r].y;
-    if (y < 0 || y >= t.H) return;
+__device__ __forceinline__ void raster_poly_fill_row(const TileTarget &t, const int2 *__restrict__ pts, const PolyDesc &pd, int y) {
     long long xs[kMaxPolyEdges], sl[kMaxPolyEdges];
     int m = 0;
     for (int k = 0; k < pd.count && m < kMaxPolyEdges; k++) {
@@ -132,6 +128,14 @@ __global__ void __launch_bounds__(128) raster_poly_fill_kernel(TileTarget t0, co
         const int xa = (int)((xs[k] + 32768) >> 16), xb = (int)(xs[k + 1] >> 16);
         if (xa < t.W && xb >= 0) tile_span(t, y, xa, xb);
     }
+}
+__global__ void __launch_bounds__(128) raster_poly_fill_kernel(TileTarget t0, const int2 *__restrict__ pts, const PolyDesc *__restrict__ polys,
+                                                              int n_polys) {
+    // one block per polygon, one thread per row of its clipped bounding box
+    if ((int)blockIdx.x >= n_polys) return;
+    const PolyDesc pd = polys[blockIdx.x];
+    const TileTarget t = tile_plane(t0, pd.inst);
+    for (int y = max(pd.ymin, 0) + (int)threadIdx.x; y < pd.ymax && y < t.H; y += blockDim.x) raster_poly_fill_row(t, pts, pd, y);
 }
 
 __global__ void __launch_bounds__(256) raster_merge_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ out, size_t n4) {
@@ -155,15 +159,9 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
         for (int i = 0; i < n_planes; i++) RTPP_CK(ctx, cudaMemsetAsync(planes + (size_t)i * stride_words, 0, words * 4, ctx->stream));
     }
     TileTarget t{planes, W, H, tilesX, stride_words};
-    // host-side job lists (a handful of shapes with a handful of vertices each), packed into ONE upload:
-    // [circles | circle steps | polygon vertices | polygon descriptors | polygon edges | polygon rows]
-    std::vector<int2> steps, edges, rows;
+    // host side: the shapes themselves in ONE upload — [circles | polygon vertices | polygon descriptors]; steps, edges and
+    // rows are enumerated by the kernels (one block per shape)
     std::vector<PolyDesc> polys((size_t)(n_polys > 0 ? n_polys : 0));
-    for (int c = 0; c < n_circles; c++) { // every dy with dx(dy) >= dy lies in [0, r*0.7072]
-        const int r = circles4[4 * c + 2];
-        if (r < 0 || r > 23000) continue; // r^2 must fit the exact integer arithmetic of the kernel
-        for (int dy = 0; dy <= (int)(r * 0.70711) + 1; dy++) steps.push_back(make_int2(c, dy));
-    }
     size_t npts = 0;
     for (int p = 0; p < n_polys; p++) {
         const int cnt = poly_sizes[p];
@@ -172,42 +170,34 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
         for (int k = 0; k < cnt; k++) {
             const int y = poly_xy[2 * (npts + k) + 1];
             ymin = y < ymin ? y : ymin, ymax = y > ymax ? y : ymax;
-            edges.push_back(make_int2(p, k));
         }
         polys[p] = PolyDesc{(int)npts, cnt, ymin, ymax, poly_inst ? poly_inst[p] : 0};
-        for (int y = (ymin < 0 ? 0 : ymin); y < ymax && y < H; y++) rows.push_back(make_int2(p, y));
         npts += cnt;
     }
+    if (n_circles <= 0 && n_polys <= 0) return RTPP_OK;
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const size_t o_cir = 0, o_stp = up16((size_t)n_circles * 16), o_pts = up16(o_stp + steps.size() * 8), o_pol = up16(o_pts + npts * 8),
-                 o_edg = up16(o_pol + polys.size() * sizeof(PolyDesc)), o_row = up16(o_edg + edges.size() * 8), total = up16(o_row + rows.size() * 8);
-    if (steps.empty() && edges.empty() && rows.empty()) return RTPP_OK;
+    const size_t o_cir = 0, o_pts = up16((size_t)(n_circles > 0 ? n_circles : 0) * 16), o_pol = up16(o_pts + npts * 8),
+                 total = up16(o_pol + polys.size() * sizeof(PolyDesc)) + 16;
     std::vector<char> stage(total, 0);
     if (n_circles > 0) memcpy(stage.data() + o_cir, circles4, (size_t)n_circles * 16);
-    if (!steps.empty()) memcpy(stage.data() + o_stp, steps.data(), steps.size() * 8);
     if (npts) memcpy(stage.data() + o_pts, poly_xy, npts * 8);
     if (!polys.empty()) memcpy(stage.data() + o_pol, polys.data(), polys.size() * sizeof(PolyDesc));
-    if (!edges.empty()) memcpy(stage.data() + o_edg, edges.data(), edges.size() * 8);
-    if (!rows.empty()) memcpy(stage.data() + o_row, rows.data(), rows.size() * 8);
     void *d = nullptr;
     int rc = rtpp_scratch(ctx, 2, total, &d);
     if (rc) return rc;
     // (a pageable source is staged by cudaMemcpyAsync before it returns, so `stage` may go out of scope; no synchronisation)
     RTPP_CK(ctx, cudaMemcpyAsync(d, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     const char *base = (const char *)d;
-    if (!steps.empty()) {
-        raster_circles_kernel<<<((int)steps.size() + 127) / 128, 128, 0, ctx->stream>>>(t, (const int4 *)(base + o_cir), (const int2 *)(base + o_stp),
-                                                                                       (int)steps.size());
+    if (n_circles > 0) {
+        raster_circles_kernel<<<n_circles, 128, 0, ctx->stream>>>(t, (const int4 *)(base + o_cir), n_circles);
         RTPP_LAUNCHED(ctx);
     }
-    const int2 *dp = (const int2 *)(base + o_pts);
-    const PolyDesc *dpo = (const PolyDesc *)(base + o_pol);
-    if (!edges.empty()) {
-        raster_poly_outline_kernel<<<((int)edges.size() + 3) / 4, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_edg), (int)edges.size());
+    if (n_polys > 0) {
+        const int2 *dp = (const int2 *)(base + o_pts);
+        const PolyDesc *dpo = (const PolyDesc *)(base + o_pol);
+        raster_poly_outline_kernel<<<n_polys, 128, 0, ctx->stream>>>(t, dp, dpo, n_polys);
         RTPP_LAUNCHED(ctx);
-    }
-    if (!rows.empty()) {
-        raster_poly_fill_kernel<<<((int)rows.size() + 127) / 128, 128, 0, ctx->stream>>>(t, dp, dpo, (const int2 *)(base + o_row), (int)rows.size());
+        raster_poly_fill_kernel<<<n_polys, 128, 0, ctx->stream>>>(t, dp, dpo, n_polys);
         RTPP_LAUNCHED(ctx);
     }
     return RTPP_OK;
