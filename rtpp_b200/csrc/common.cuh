@@ -72,6 +72,14 @@ struct rtpp_ctx {
     } while (0)
 
 int rtpp_scratch(rtpp_ctx *ctx, int slot, size_t bytes, void **out);
+// raster.cu: the shapes a batch of dynamic planes was drawn from (kept by a caller that wants them erased, not memset)
+#include <vector>
+struct RasterShapes {
+    std::vector<int32_t> circles4, poly_xy, poly_sizes, poly_inst;
+};
+int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int n_planes, int W, int H, const int32_t *circles4,
+                      int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, const int32_t *poly_inst, int n_polys,
+                      const RasterShapes *prev);
 int rtpp_select_plane(rtpp_ctx *ctx, int plane_mask, PlaneView *pv);
 struct MarchThresholds;
 void rtpp_march_thresholds(int divisor, MarchThresholds *out);

@@ -40,9 +40,6 @@
 #define FULL 0xffffffffu
 typedef unsigned long long u64;
 
-int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int n_planes, int W, int H, const int32_t *circles4,
-                      int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, const int32_t *poly_inst, int n_polys);
-
 static constexpr int kOrigin = 0x40000000;        // originIndexFun, CDRT.h:226
 static constexpr double kDoubleMax = 1.79769e+307; // CDRT.h:359
 enum { F_ALIVE = 1, F_LARGER = 2, F_SMALLER = 4 };
@@ -1006,6 +1003,8 @@ struct rtpp_cdrt_engine {
     std::vector<double> h_pose, h_chk;
     std::vector<int> h_chk_obs;
     bool chk_dirty = true;
+    RasterShapes drawn;       // what the instances' dynamic planes hold (erased, not memset, at the next tick)
+    bool drawn_valid = false; // false until the first tick has cleared every plane
 };
 
 #define CD_CK(e, call) RTPP_CK((e)->ctx, call)
@@ -1403,8 +1402,13 @@ int rtpp_cdrt_tick(rtpp_cdrt_engine *e, long long dt_ns, int do_get_path) {
         if (hi.check_dirty) e->chk_dirty = true, hi.check_dirty = false;
     }
     int rc = rtpp_raster_batch(ctx, v.dplane, v.plane_words, v.n_inst, v.W, v.H, circles.data(), (int)circles.size() / 4, poly_xy.data(),
-                               poly_sizes.data(), poly_inst.data(), (int)poly_sizes.size());
-    if (rc) return rc;
+                               poly_sizes.data(), poly_inst.data(), (int)poly_sizes.size(), e->drawn_valid ? &e->drawn : nullptr);
+    if (rc) {
+        e->drawn_valid = false;
+        return rc;
+    }
+    e->drawn.circles4.swap(circles), e->drawn.poly_xy.swap(poly_xy), e->drawn.poly_sizes.swap(poly_sizes), e->drawn.poly_inst.swap(poly_inst);
+    e->drawn_valid = true;
     CD_CK(e, cudaMemcpyAsync((void *)v.hdr, hdr.data(), hdr.size() * sizeof(CdHdr), cudaMemcpyHostToDevice, ctx->stream));
     CD_CK(e, cudaMemcpyAsync(v.pose, pose.data(), pose.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (e->chk_dirty) { // the check points only change with RTRT_AddDynamicObstacle

@@ -26,6 +26,7 @@ struct TileTarget {
     uint32_t *w;
     int W, H, tilesX;
     size_t stride; // words between the planes of a batch (primitive p draws into plane inst(p))
+    int erase;     // 1: clear the pixels of the shapes instead of setting them (undo of the previous tick's drawing)
 };
 __device__ __forceinline__ TileTarget tile_plane(const TileTarget &t, int inst) {
     TileTarget r = t;
@@ -42,12 +43,15 @@ __device__ __forceinline__ void tile_span(const TileTarget &t, int y, int xa, in
     for (int wx = xa >> 5; wx <= (xb >> 5); wx++) {
         const int lo = max(xa, wx << 5) & 31, hi = min(xb, (wx << 5) + 31) & 31;
         const uint32_t mask = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-        atomicOr(&t.w[row_base + ((size_t)wx << 5)], mask);
+        if (t.erase) atomicAnd(&t.w[row_base + ((size_t)wx << 5)], ~mask);
+        else atomicOr(&t.w[row_base + ((size_t)wx << 5)], mask);
     }
 }
 __device__ __forceinline__ void tile_put(const TileTarget &t, int x, int y) {
     if ((unsigned)x >= (unsigned)t.W || (unsigned)y >= (unsigned)t.H) return;
-    atomicOr(&t.w[((((size_t)(y >> 5) * t.tilesX + (x >> 5)) << 5) + (y & 31))], 1u << (x & 31));
+    uint32_t *wd = &t.w[((((size_t)(y >> 5) * t.tilesX + (x >> 5)) << 5) + (y & 31))];
+    if (t.erase) atomicAnd(wd, ~(1u << (x & 31)));
+    else atomicOr(wd, 1u << (x & 31));
 }
 
 // Filled circle = cv::circle(FILLED): the midpoint recurrence (err += 2*dy+1; if err > 0: err -= 2*dx-1, dx--)
@@ -145,22 +149,11 @@ __global__ void __launch_bounds__(256) raster_merge_kernel(const uint4 *__restri
     }
 }
 
-// Draw a batch of planes (n_planes tile planes `stride_words` apart): every plane is cleared
-// (DObsmap = cv::Mat::zeros, RTRRT.cpp:140), then circle c = (cx, cy, r, plane) and polygon p (poly_inst[p])
-// are drawn into their planes with one launch per primitive kind.  Used by the ctx planes, the engines'
-// map slots (one plane) and the CDRT engine (one dynamic plane per planner instance).
-int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int n_planes, int W, int H, const int32_t *circles4,
-                      int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, const int32_t *poly_inst, int n_polys) {
-    const int tilesX = (W + 31) >> 5, tilesY = (H + 31) >> 5;
-    const size_t words = (size_t)tilesX * tilesY * 32;
-    if (n_planes > 1 && stride_words == words) {
-        RTPP_CK(ctx, cudaMemsetAsync(planes, 0, words * 4 * (size_t)n_planes, ctx->stream));
-    } else {
-        for (int i = 0; i < n_planes; i++) RTPP_CK(ctx, cudaMemsetAsync(planes + (size_t)i * stride_words, 0, words * 4, ctx->stream));
-    }
-    TileTarget t{planes, W, H, tilesX, stride_words};
-    // host side: the shapes themselves in ONE upload — [circles | polygon vertices | polygon descriptors]; steps, edges and
-    // rows are enumerated by the kernels (one block per shape)
+// One pass over a set of shapes: circle c = (cx, cy, r, plane), polygon p into plane poly_inst[p]; erase = 1 clears their
+// pixels.  The shapes go up in ONE copy — [circles | polygon vertices | polygon descriptors]; steps, edges and rows are
+// enumerated by the kernels (one block per shape).
+static int raster_shapes(rtpp_ctx *ctx, TileTarget t, const int32_t *circles4, int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes,
+                         const int32_t *poly_inst, int n_polys) {
     std::vector<PolyDesc> polys((size_t)(n_polys > 0 ? n_polys : 0));
     size_t npts = 0;
     for (int p = 0; p < n_polys; p++) {
@@ -185,7 +178,8 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
     void *d = nullptr;
     int rc = rtpp_scratch(ctx, 2, total, &d);
     if (rc) return rc;
-    // (a pageable source is staged by cudaMemcpyAsync before it returns, so `stage` may go out of scope; no synchronisation)
+    // (a pageable source is staged by cudaMemcpyAsync before it returns, so `stage` may go out of scope; the copy is ordered
+    // on the stream behind the kernels of an earlier pass that read the same scratch)
     RTPP_CK(ctx, cudaMemcpyAsync(d, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     const char *base = (const char *)d;
     if (n_circles > 0) {
@@ -203,12 +197,38 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
     return RTPP_OK;
 }
 
+// Draw a batch of planes (n_planes tile planes `stride_words` apart): every plane is cleared
+// (DObsmap = cv::Mat::zeros, RTRRT.cpp:140), then circle c = (cx, cy, r, plane) and polygon p (poly_inst[p])
+// are drawn into their planes with one launch per primitive kind.  Used by the ctx planes, the engines'
+// map slots (one plane) and the CDRT engine (one dynamic plane per planner instance).
+// prev_* (optional): the shapes these planes hold from the previous call and nothing else — they are then cleared by
+// erasing exactly those shapes instead of a memset of every plane (1024 planners x 0.95 MB = 1 GB per tick on GAME0).
+int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int n_planes, int W, int H, const int32_t *circles4,
+                      int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, const int32_t *poly_inst, int n_polys,
+                      const RasterShapes *prev) {
+    const int tilesX = (W + 31) >> 5, tilesY = (H + 31) >> 5;
+    const size_t words = (size_t)tilesX * tilesY * 32;
+    TileTarget t{planes, W, H, tilesX, stride_words, 0};
+    if (prev) {
+        t.erase = 1;
+        int rc = raster_shapes(ctx, t, prev->circles4.data(), (int)prev->circles4.size() / 4, prev->poly_xy.data(), prev->poly_sizes.data(),
+                               prev->poly_inst.data(), (int)prev->poly_sizes.size());
+        if (rc) return rc;
+        t.erase = 0;
+    } else if (n_planes > 1 && stride_words == words) {
+        RTPP_CK(ctx, cudaMemsetAsync(planes, 0, words * 4 * (size_t)n_planes, ctx->stream));
+    } else {
+        for (int i = 0; i < n_planes; i++) RTPP_CK(ctx, cudaMemsetAsync(planes + (size_t)i * stride_words, 0, words * 4, ctx->stream));
+    }
+    return raster_shapes(ctx, t, circles4, n_circles, poly_xy, poly_sizes, poly_inst, n_polys);
+}
+
 // one plane; circles as (cx, cy, r) triples
 int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t *circles, int n_circles, const int32_t *poly_xy,
                      const int32_t *poly_sizes, int n_polys) {
     std::vector<int32_t> c4((size_t)n_circles * 4);
     for (int i = 0; i < n_circles; i++) c4[4 * i] = circles[3 * i], c4[4 * i + 1] = circles[3 * i + 1], c4[4 * i + 2] = circles[3 * i + 2], c4[4 * i + 3] = 0;
-    return rtpp_raster_batch(ctx, plane, 0, 1, W, H, c4.data(), n_circles, poly_xy, poly_sizes, nullptr, n_polys);
+    return rtpp_raster_batch(ctx, plane, 0, 1, W, H, c4.data(), n_circles, poly_xy, poly_sizes, nullptr, n_polys, nullptr);
 }
 
 extern "C" {
