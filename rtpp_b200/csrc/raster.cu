@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) raster_circles_kernel(TileTarget t0, cons
     const int4 c = circles[blockIdx.x]; // cx, cy, r, plane
     if (c.z < 0 || c.z > 23000) return; // r^2 must fit the exact integer arithmetic below
     const TileTarget t = tile_plane(t0, c.w);
-    for (int dy = threadIdx.x; dy <= c.z; dy += blockDim.x) {
+    for (int dy = blockIdx.y * blockDim.x + threadIdx.x; dy <= c.z; dy += gridDim.y * blockDim.x) {
         const int dx = isqrt_floor(c.z * c.z - dy * dy);
         if (dx < dy) break; // past the octant's end (dx - dy only falls from here on)
         tile_span(t, c.y - dy, c.x - dx, c.x + dx);
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) raster_poly_outline_kernel(TileTarget t0,
     const int lane = threadIdx.x & 31;
     const PolyDesc pd = polys[blockIdx.x];
     const TileTarget t = tile_plane(t0, pd.inst);
-    for (int k = threadIdx.x >> 5; k < pd.count; k += blockDim.x >> 5) {
+    for (int k = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); k < pd.count; k += gridDim.y * (blockDim.x >> 5)) {
         int2 a = pts[pd.first + (k + pd.count - 1) % pd.count], b = pts[pd.first + k];
         if (b.x < a.x) {
             const int2 s = a;
@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(128) raster_poly_fill_kernel(TileTarget t0, co
     if ((int)blockIdx.x >= n_polys) return;
     const PolyDesc pd = polys[blockIdx.x];
     const TileTarget t = tile_plane(t0, pd.inst);
-    for (int y = max(pd.ymin, 0) + (int)threadIdx.x; y < pd.ymax && y < t.H; y += blockDim.x) raster_poly_fill_row(t, pts, pd, y);
+    for (int y = max(pd.ymin, 0) + (int)(blockIdx.y * blockDim.x + threadIdx.x); y < pd.ymax && y < t.H; y += gridDim.y * blockDim.x)
+        raster_poly_fill_row(t, pts, pd, y);
 }
 
 __global__ void __launch_bounds__(256) raster_merge_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ out, size_t n4) {
@@ -156,6 +157,7 @@ static int raster_shapes(rtpp_ctx *ctx, TileTarget t, const int32_t *circles4, i
                          const int32_t *poly_inst, int n_polys) {
     std::vector<PolyDesc> polys((size_t)(n_polys > 0 ? n_polys : 0));
     size_t npts = 0;
+    int max_rows = 1, max_cnt = 1, max_r = 0; // the second grid dimension spreads a big shape over several blocks
     for (int p = 0; p < n_polys; p++) {
         const int cnt = poly_sizes[p];
         if (cnt > kMaxPolyEdges) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "polygon has too many vertices");
@@ -166,7 +168,10 @@ static int raster_shapes(rtpp_ctx *ctx, TileTarget t, const int32_t *circles4, i
         }
         polys[p] = PolyDesc{(int)npts, cnt, ymin, ymax, poly_inst ? poly_inst[p] : 0};
         npts += cnt;
+        const int rows = (ymax < t.H ? ymax : t.H) - (ymin > 0 ? ymin : 0);
+        max_rows = rows > max_rows ? rows : max_rows, max_cnt = cnt > max_cnt ? cnt : max_cnt;
     }
+    for (int c = 0; c < n_circles; c++) max_r = circles4[4 * c + 2] > max_r && circles4[4 * c + 2] <= 23000 ? circles4[4 * c + 2] : max_r;
     if (n_circles <= 0 && n_polys <= 0) return RTPP_OK;
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t o_cir = 0, o_pts = up16((size_t)(n_circles > 0 ? n_circles : 0) * 16), o_pol = up16(o_pts + npts * 8),
@@ -183,15 +188,15 @@ static int raster_shapes(rtpp_ctx *ctx, TileTarget t, const int32_t *circles4, i
     RTPP_CK(ctx, cudaMemcpyAsync(d, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     const char *base = (const char *)d;
     if (n_circles > 0) {
-        raster_circles_kernel<<<n_circles, 128, 0, ctx->stream>>>(t, (const int4 *)(base + o_cir), n_circles);
+        raster_circles_kernel<<<dim3(n_circles, (max_r * 3 / 4 + 2 + 127) / 128), 128, 0, ctx->stream>>>(t, (const int4 *)(base + o_cir), n_circles);
         RTPP_LAUNCHED(ctx);
     }
     if (n_polys > 0) {
         const int2 *dp = (const int2 *)(base + o_pts);
         const PolyDesc *dpo = (const PolyDesc *)(base + o_pol);
-        raster_poly_outline_kernel<<<n_polys, 128, 0, ctx->stream>>>(t, dp, dpo, n_polys);
+        raster_poly_outline_kernel<<<dim3(n_polys, (max_cnt + 3) / 4), 128, 0, ctx->stream>>>(t, dp, dpo, n_polys);
         RTPP_LAUNCHED(ctx);
-        raster_poly_fill_kernel<<<n_polys, 128, 0, ctx->stream>>>(t, dp, dpo, n_polys);
+        raster_poly_fill_kernel<<<dim3(n_polys, (max_rows + 127) / 128), 128, 0, ctx->stream>>>(t, dp, dpo, n_polys);
         RTPP_LAUNCHED(ctx);
     }
     return RTPP_OK;
