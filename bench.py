@@ -497,6 +497,20 @@ def measure_extras(wl, torch, sweep):
     out["knn_queries_per_s"] = n / (ms * 1e-3)
     out["knn_all_nodes_ms"] = ms
     out["knn_algorithmic_GBs"] = n * (16 + KNN * 20) / (ms * 1e-3) / 1e9  # 516 B per 25-NN query
+    # the same store queried at 1e6 uniform random points (binary64, as a planner's samples are: no shared cell between
+    # consecutive queries), ids + squared distances out; device buffers
+    import ctypes as C
+
+    nq = 1_000_000
+    q = torch.rand((nq, 2), dtype=torch.float64, device=wl.dev) * MAP_SIZE
+    qi = torch.empty((nq, KNN), dtype=torch.int32, device=wl.dev)
+    qd = torch.empty((nq, KNN), dtype=torch.float64, device=wl.dev)
+    qc = torch.empty(nq, dtype=torch.int32, device=wl.dev)
+    ms = timed(lambda: ctx.call("knn_dev", C.c_void_p(q.data_ptr()), C.c_size_t(nq), KNN, C.c_void_p(qi.data_ptr()), C.c_void_p(qd.data_ptr()),
+                                C.c_void_p(qc.data_ptr())), 5)
+    out["knn_random_queries_per_s"] = nq / (ms * 1e-3)
+    out["knn_random_queries_ms"] = ms
+    del q, qi, qd, qc
     out["edge_kernels"] = measure_edge_kernels(wl, torch, timed)
     cost0 = np.full(n, 3.4e38, np.float32)
     col0 = np.ones(n, np.uint8)

@@ -143,11 +143,7 @@ __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, doubl
         const int cx = grid_cell_of(qx, g.shift, g.gw - 1), cy = grid_cell_of(qy, g.shift, g.gh - 1);
         const int want = min(k, g.n);
         const int rmax = max(max(cx, g.gw - 1 - cx), max(cy, g.gh - 1 - cy));
-        auto scan_row = [&](int y, int x0, int x1) {
-            if (y < 0 || y >= g.gh) return;
-            x0 = max(x0, 0), x1 = min(x1, g.gw - 1);
-            if (x0 > x1) return;
-            const int s = g.cell_start[y * g.gw + x0], e = g.cell_start[y * g.gw + x1 + 1];
+        auto scan_range = [&](int s, int e) { // positions [s, e) of the cell-sorted arrays
             for (int i0 = s; i0 < e; i0 += 32) {
                 const int i = i0 + lane;
                 const bool v = i < e;
@@ -160,15 +156,35 @@ __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, doubl
                 offer(v, knn_d2(qx, qy, p.x, p.y), id);
             }
         };
+        auto scan_row = [&](int y, int x0, int x1) {
+            if (y < 0 || y >= g.gh) return;
+            x0 = max(x0, 0), x1 = min(x1, g.gw - 1);
+            if (x0 > x1) return;
+            scan_range(g.cell_start[y * g.gw + x0], g.cell_start[y * g.gw + x1 + 1]);
+        };
         for (int r = 0; r <= rmax; r++) {
             if (r == 0)
                 scan_row(cy, cx, cx);
             else {
                 scan_row(cy - r, cx - r, cx + r);
                 scan_row(cy + r, cx - r, cx + r);
-                for (int y = cy - r + 1; y <= cy + r - 1; y++) {
-                    scan_row(y, cx - r, cx - r);
-                    scan_row(y, cx + r, cx + r);
+                // the 2(2r - 1) side cells of the ring: one lane looks up one cell, only the non-empty ones are scanned (a
+                // query far from every node — a sample inside an obstacle — walks many rings of empty cells; the result does
+                // not depend on the order in which candidates are offered)
+                const int nside = 2 * (2 * r - 1);
+                for (int c0 = 0; c0 < nside; c0 += 32) {
+                    const int c = c0 + lane;
+                    int cs = 0, ce = 0;
+                    if (c < nside) {
+                        const int y = cy - r + 1 + (c >> 1), x = (c & 1) ? cx + r : cx - r;
+                        if (y >= 0 && y < g.gh && x >= 0 && x < g.gw) cs = g.cell_start[y * g.gw + x], ce = g.cell_start[y * g.gw + x + 1];
+                    }
+                    unsigned ne = __ballot_sync(full, ce > cs);
+                    while (ne) {
+                        const int src = __ffs(ne) - 1;
+                        ne &= ne - 1;
+                        scan_range(__shfl_sync(full, cs, src), __shfl_sync(full, ce, src));
+                    }
                 }
             }
             if (found >= want) {
