@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(32 * KNN_NODES_WARPS) knn_nodes_kernel(GridVie
 void rtpp_nodes_destroy(rtpp_ctx *ctx) {
     NodeStore *s = ctx->nodes;
     if (!s) return;
-    cudaFree(s->xy), cudaFree(s->sxy), cudaFree(s->sid), cudaFree(s->cell_of), cudaFree(s->cell_start), cudaFree(s->cursor);
+    cudaFree(s->xy), cudaFree(s->sxy), cudaFree(s->sid), cudaFree(s->cell_of), cudaFree(s->cell_start), cudaFree(s->cursor), cudaFree(s->gap);
     cudaFree(s->knn_table), cudaFree(s->knn_pos), cudaFree(s->pos_of), cudaFree(s->edge_list), cudaFree(s->scan_totals), cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
     delete s;
     ctx->nodes = nullptr;
@@ -118,6 +118,28 @@ static int grid_for(rtpp_ctx *ctx, size_t n) {
 }
 
 // (re)sort the hash so that it covers every node appended so far
+// gap[c] = the first ring around cell c that holds a sorted node (0: the cell itself), saturating at 255: the ring walk of
+// a query starts there.  Ring r = rows cy-r and cy+r (each ONE range of the cell-sorted array) + 2(2r-1) side cells.
+__global__ void __launch_bounds__(256) grid_gap_kernel(const int *__restrict__ cell_start, int gw, int gh, unsigned char *__restrict__ gap) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= gw * gh) return;
+    const int cx = c % gw, cy = c / gw;
+    const int rmax = min(255, max(max(cx, gw - 1 - cx), max(cy, gh - 1 - cy)));
+    int r = 0;
+    for (; r < rmax; r++) {
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, gw - 1);
+        bool any = false;
+        if (cy - r >= 0) any |= cell_start[(cy - r) * gw + x1 + 1] > cell_start[(cy - r) * gw + x0];
+        if (r > 0 && cy + r < gh) any |= cell_start[(cy + r) * gw + x1 + 1] > cell_start[(cy + r) * gw + x0];
+        for (int y = max(cy - r + 1, 0); y <= min(cy + r - 1, gh - 1) && !any; y++) {
+            if (cx - r >= 0) any |= cell_start[y * gw + cx - r + 1] > cell_start[y * gw + cx - r];
+            if (cx + r < gw) any |= cell_start[y * gw + cx + r + 1] > cell_start[y * gw + cx + r];
+        }
+        if (any) break;
+    }
+    gap[c] = (unsigned char)r;
+}
+
 int rtpp_nodes_build_internal(rtpp_ctx *ctx) {
     NodeStore *s = ctx->nodes;
     if (!s) RTPP_FAIL(ctx, RTPP_ERR_STATE, "rtpp_nodes_reset has not been called");
@@ -133,6 +155,8 @@ int rtpp_nodes_build_internal(rtpp_ctx *ctx) {
     }
     grid_scatter_kernel<<<grid_for(ctx, s->n), 256, 0, ctx->stream>>>(s->xy, s->cell_of, s->n, s->cursor, s->sxy, s->sid);
     RTPP_LAUNCHED(ctx);
+    grid_gap_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(s->cell_start, s->gw, s->gh, s->gap);
+    RTPP_LAUNCHED(ctx);
     s->n_sorted = s->n;
     return RTPP_OK;
 }
@@ -146,6 +170,7 @@ int rtpp_grid_view(rtpp_ctx *ctx, GridView *g) {
     }
     g->sxy = s->sxy, g->sid = s->sid, g->cell_start = s->cell_start, g->xy = s->xy;
     g->gw = s->gw, g->gh = s->gh, g->shift = s->shift, g->n_sorted = s->n_sorted, g->n = s->n;
+    g->gap = s->n_sorted > 0 ? s->gap : nullptr;
     return RTPP_OK;
 }
 
@@ -174,6 +199,7 @@ int rtpp_nodes_reset(rtpp_ctx *ctx, int cell_log2, size_t capacity, int domain_w
     RTPP_CK(ctx, cudaMalloc(&s->cell_of, capacity * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cell_start, m * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cursor, m * sizeof(int)));
+    RTPP_CK(ctx, cudaMalloc(&s->gap, m));
     RTPP_CK(ctx, cudaMalloc(&s->scan_totals, ((m > capacity ? m : capacity) / 2048 + 4) * sizeof(int)));
     RTPP_CK(ctx, cudaMalloc(&s->cp, capacity * sizeof(unsigned long long)));
     RTPP_CK(ctx, cudaMemsetAsync(s->cp, 0xff, capacity * sizeof(unsigned long long), ctx->stream));

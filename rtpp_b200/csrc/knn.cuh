@@ -29,6 +29,7 @@ struct GridView {
     const float2 *xy;                     // coordinates by node id             [n]
     int gw, gh, shift;                    // grid of (1<<shift)-pixel cells
     int n_sorted, n;                      // ids >= n_sorted are the unsorted tail
+    const unsigned char *gap = nullptr;   // optional [gw*gh]: rings 0 .. gap-1 around the cell hold no sorted node (saturates at 255)
 };
 
 struct KnnEntry {
@@ -162,7 +163,8 @@ __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, doubl
             if (x0 > x1) return;
             scan_range(g.cell_start[y * g.gw + x0], g.cell_start[y * g.gw + x1 + 1]);
         };
-        for (int r = 0; r <= rmax; r++) {
+        // rings known to be empty (a query deep inside an obstacle) are skipped: exact, the table describes the sorted part
+        for (int r = g.gap ? min((int)g.gap[cy * g.gw + cx], rmax) : 0; r <= rmax; r++) {
             if (r == 0)
                 scan_row(cy, cx, cx);
             else {

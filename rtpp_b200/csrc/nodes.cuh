@@ -34,6 +34,7 @@ struct NodeStore {
     int *cell_start = nullptr;  // [gw*gh + 1]
     int *cursor = nullptr;      // [gw*gh + 1]
     int *scan_totals = nullptr; // scratch of the prefix sums
+    unsigned char *gap = nullptr; // [gw*gh] Chebyshev distance in cells to the nearest non-empty cell (ring-walk start)
     cpword *cp = nullptr;       // [capacity] cost|parent words
     // tree.cu scratch (allocated on first use)
     uint32_t *edge_w = nullptr; // per node: weight of the edge (parent -> node)
