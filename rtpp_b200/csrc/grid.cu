@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) knn_query_kernel(GridView g, const double
         const double2 qq = q[w];
         KnnEntry e;
         int found = knn_warp_block3(g, qq.x, qq.y, k, e, scratch[threadIdx.x >> 5]);
-        if (found < 0) found = knn_warp(g, qq.x, qq.y, k, e);
+        if (found < 0) found = knn_warp_wide(g, qq.x, qq.y, k, e);
         if (lane < k) {
             idx[w * k + lane] = lane < found ? e.id : -1;
             if (d2) d2[w * k + lane] = lane < found ? e.d2 : CUDART_INF;

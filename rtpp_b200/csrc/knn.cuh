@@ -56,6 +56,11 @@ __device__ __forceinline__ int grid_cell_of(double v, int shift, int gmax) {
 // found0 < 0: a fresh query.  found0 >= 0: `mine` already holds the exact result over the node ids [0, scan_from)
 // (lanes >= found0 hold +inf) and only the ids [scan_from, n) are scanned, linearly — the planner engines cache the
 // neighbour list of a tree node and extend it by the nodes appended since (nodes never move or disappear).
+// kWide: the variant for queries that may lie far from every node (bulk queries at arbitrary points: a third of uniform
+// samples fall inside obstacles at C4): a ring's side cells are looked up one per lane and the walk starts at the first
+// non-empty ring (GridView::gap).  The engines and the all-nodes table keep the plain walk: their queries sit among the
+// nodes, and the extra code costs the all-nodes kernel registers (0.72 -> 0.77 ms when it was shared).
+template <bool kWide = false>
 __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, double qy, int k, KnnEntry &mine, int found0, int scan_from) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -164,7 +169,7 @@ __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, doubl
             scan_range(g.cell_start[y * g.gw + x0], g.cell_start[y * g.gw + x1 + 1]);
         };
         // rings known to be empty (a query deep inside an obstacle) are skipped: exact, the table describes the sorted part
-        for (int r = g.gap ? min((int)g.gap[cy * g.gw + cx], rmax) : 0; r <= rmax; r++) {
+        for (int r = (kWide && g.gap) ? min((int)g.gap[cy * g.gw + cx], rmax) : 0; r <= rmax; r++) {
             if (r == 0)
                 scan_row(cy, cx, cx);
             else {
@@ -173,7 +178,12 @@ __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, doubl
                 // the 2(2r - 1) side cells of the ring: one lane looks up one cell, only the non-empty ones are scanned (a
                 // query far from every node — a sample inside an obstacle — walks many rings of empty cells; the result does
                 // not depend on the order in which candidates are offered)
-                const int nside = 2 * (2 * r - 1);
+                const int nside = kWide ? 2 * (2 * r - 1) : 0;
+                if (!kWide)
+                    for (int y = cy - r + 1; y <= cy + r - 1; y++) {
+                        scan_row(y, cx - r, cx - r);
+                        scan_row(y, cx + r, cx + r);
+                    }
                 for (int c0 = 0; c0 < nside; c0 += 32) {
                     const int c = c0 + lane;
                     int cs = 0, ce = 0;
@@ -206,6 +216,9 @@ __device__ __forceinline__ int knn_warp_impl(const GridView &g, double qx, doubl
 }
 __device__ __forceinline__ int knn_warp(const GridView &g, double qx, double qy, int k, KnnEntry &mine) {
     return knn_warp_impl(g, qx, qy, k, mine, -1, 0);
+}
+__device__ __forceinline__ int knn_warp_wide(const GridView &g, double qx, double qy, int k, KnnEntry &mine) {
+    return knn_warp_impl<true>(g, qx, qy, k, mine, -1, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
