@@ -536,6 +536,10 @@ def measure_extras(wl, torch, sweep):
     except Exception as exc:  # an extra must not cost the bench line
         out["dropin_rtrrt_class"] = {"error": repr(exc)}
     out.update(measure_fmt(ctx))
+    try:
+        out.update(measure_fmt_sweep(ctx))
+    except Exception as exc:  # an extra must not cost the bench line
+        out["rtfmt_sweep"] = {"error": repr(exc)}
     out.update(measure_cdrt(ctx))
     out.update(measure_amrrt(ctx))
     return out
@@ -740,6 +744,61 @@ def measure_fmt(ctx, samples=100_000, iters=20_000):
     return {"rtfmt_1e5": {"samples": samples, "rounds": iters, "gpu_start_ms": gpu_start * 1e3, "gpu_rounds_per_s": iters / gpu_s,
                           "cpu_start_ms": cpu_start * 1e3, "cpu_rounds_per_s": iters / cpu_s, "cpu_kind": "port, 1 thread",
                           "state_matches_cpu": same}}
+
+
+def measure_fmt_sweep(ctx, n_inst=512, samples=2000, iters=2000, cpu_inst=16):
+    """RT-FMT as shipped (2000 samples per planner, RTFMT/test/test.cpp) over many planners: n_inst instances on GAME0 with their
+    own sample sets (rand() seeds) and goals run `iters` rounds of ExpandFMT + both rewires + GetPath on the engine (one warp
+    each); the CPU port runs cpu_inst of them on the host threads; the trees of those are compared bit for bit."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import rtpp_b200
+    from oracle import loader as orc
+
+    S = orc.load_map("GAME0")
+    H, W = S.shape
+    goals = [(2000.0, 400.0), (1400.0, 2050.0), (888.0, 800.0), (2500.0, 1500.0)]
+    threads = os.cpu_count() or 1
+
+    def make(i):
+        o = orc.OrcRTFMT(S)
+        o.set_agent(360.0, 540.0)
+        o.set_goal(*goals[i % 4])
+        o.start(orc.rand31(100 + i, 3 * samples + 1000), samples)
+        return o
+
+    with ThreadPoolExecutor(threads) as ex:
+        planners = list(ex.map(make, range(n_inst)))
+    nodes = [o.dump()[0] for o in planners]
+    eng = rtpp_b200.FmtEngine(ctx, n_inst, max(len(a) for a in nodes) + 32, 5, W, H)
+    eng.set_map(0, 1, S)
+    eng.start(np.zeros(n_inst, np.int32), nodes, np.array([goals[i % 4] for i in range(n_inst)], np.float32))
+    ctx.sync()
+    t0 = time.perf_counter()
+    eng.tick(update_tree=True, iters=iters, with_rewire=True, get_path=True)
+    ctx.sync()
+    gpu_s = time.perf_counter() - t0
+
+    def run_cpu(o):
+        o.update_tree()
+        o.expand(iters, True)
+        return o.dump()
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        cpu = list(ex.map(run_cpu, planners[:cpu_inst]))
+    cpu_s = time.perf_counter() - t0
+    same = True
+    for i, (oxy, opar, oc, ocl, ost) in enumerate(cpu):
+        par, c, cl, st = eng.read_tree(i)
+        same &= bool(np.array_equal(par, opar) and np.array_equal(st, ost) and np.array_equal(c.view(np.uint32), oc.view(np.uint32)))
+    status = int(eng.stats()[:, 12].max())
+    eng.close()
+    for o in planners:
+        o.close()
+    return {"rtfmt_sweep": {"map": "GAME0", "instances": n_inst, "samples": samples, "rounds": iters, "gpu_status_max": status,
+                            "gpu_tick_ms": gpu_s * 1e3, "gpu_rounds_per_s": n_inst * iters / gpu_s, "cpu_instances": cpu_inst, "cpu_threads": threads,
+                            "cpu_rounds_per_s": cpu_inst * iters / cpu_s, "cpu_kind": "port (oracle loops)", "trees_match_cpu": same}}
 
 
 def measure_sharded_batch(wl, rank, world, torch, dist, reps=20):
