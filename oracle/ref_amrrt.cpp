@@ -7,6 +7,7 @@
 #undef private
 #include "ref_common.hpp"
 #include "raster.hpp"
+#include "pool.hpp"
 
 struct RefAMRRT {
     AMRRTplanner p;
@@ -84,23 +85,16 @@ REF_EXPORT void ref_amrrt_crash(void *h, const float *xyxy, long long n, uint8_t
         out[i] = p.CrashDetection(a, b);
     }
 }
-// the same routine fanned out over host threads (CrashDetection only reads the two planes)
+// the same routine fanned out over host threads (CrashDetection only reads the two planes): persistent pool, chunks of
+// 8192 edges dealt through an atomic cursor (pool.hpp)
 REF_EXPORT void ref_amrrt_crash_mt(void *h, const float *xyxy, long long n, uint8_t *out, int nthreads) {
     AMRRTplanner *p = &((RefAMRRT *)h)->p;
-    if (nthreads < 1) nthreads = 1;
-    std::vector<std::thread> th;
-    long long chunk = (n + nthreads - 1) / nthreads;
-    for (int t = 0; t < nthreads; t++) {
-        long long a = t * chunk, b = std::min(n, a + chunk);
-        if (a >= b) break;
-        th.emplace_back([=] {
-            for (long long i = a; i < b; i++) {
-                RTpoint s{xyxy[4 * i], xyxy[4 * i + 1]}, e{xyxy[4 * i + 2], xyxy[4 * i + 3]};
-                out[i] = p->CrashDetection(s, e);
-            }
-        });
-    }
-    for (auto &t : th) t.join();
+    orc_pool(nthreads).run(n, 8192, [=](long long a, long long b) {
+        for (long long i = a; i < b; i++) {
+            RTpoint s{xyxy[4 * i], xyxy[4 * i + 1]}, e{xyxy[4 * i + 2], xyxy[4 * i + 3]};
+            out[i] = p->CrashDetection(s, e);
+        }
+    });
 }
 REF_EXPORT void ref_amrrt_crash_start(void *h, const float *xyxy, long long n, uint8_t *out, float *pstart) {
     AMRRTplanner &p = ((RefAMRRT *)h)->p;

@@ -3,6 +3,7 @@
 // cpu_baseline / --impl reference legs; never by the product path.
 #include "rtpp_oracle.hpp"
 #include "raster.hpp"
+#include "pool.hpp"
 #include <cstring>
 #include <thread>
 
@@ -16,19 +17,13 @@ static Map mk_map(const uint8_t *S, const uint8_t *D, int W, int H) {
     return m;
 }
 
+// batches are dealt in chunks to a persistent pool (pool.hpp): no thread start-up inside a timed call
 template <class F> static void par_for(long long n, int nthreads, F f) {
     if (nthreads <= 1 || n < 4096) {
         f(0, n);
         return;
     }
-    std::vector<std::thread> th;
-    long long chunk = (n + nthreads - 1) / nthreads;
-    for (int t = 0; t < nthreads; t++) {
-        long long a = t * chunk, b = std::min(n, a + chunk);
-        if (a >= b) break;
-        th.emplace_back([=] { f(a, b); });
-    }
-    for (auto &t : th) t.join();
+    orc_pool(nthreads).run(n, 8192, f);
 }
 
 ORC_EXPORT void orc_edges_check_f32(const uint8_t *S, const uint8_t *D, int W, int H, const float *xyxy, long long n,
