@@ -145,6 +145,33 @@ RTPP_API int rtpp_edges_first_hit_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t
 RTPP_API int rtpp_tick_edges_check(rtpp_ctx *ctx, const uint8_t *dynamic_plane, int divisor, int plane_mask,
                                    uint32_t *blocked_bits, size_t *n_edges);
 RTPP_API int rtpp_tick_edges_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_blocked_bits, size_t *n_edges);
+
+/* The same tick with the verdicts in the layout the windowed kernel produces (csrc/tick.cu; north star: bit-packed tiles with
+ * TMA / shared-memory staging of the per-block map window).  The nodes are ordered by 64x64-pixel supercell into SLOTS (groups
+ * of 32, padded per supercell); the order is fixed by rtpp_knn_table_build and read with rtpp_tick_plan_info:
+ *   d_slot_id[slot]     node id held by a slot (-1 = padding),   d_slot_of_id[id]  the slot of a node,
+ *   usable              0 when the plan does not apply (hash cells larger than 64 pixels, or more than a quarter of the edges
+ *                       leave the 32-pixel halo): rtpp_tick_check* then fail with RTPP_ERR_STATE and rtpp_tick_edges_check uses
+ *                       its gathering kernels,   far_fraction  share of the edges (for `divisor`: a march finer than 16 steps
+ *                       counts) that the same launch checks with the general routine instead of the window.
+ * rtpp_tick_check[_dev]: tree_bits[(n-1+31)/32]: bit e = CrashDetection(parent(e+1), e+1) (UpdateTree, AMRRT.cpp:185-199;
+ * RTRRT.cpp:128-134); row_bits[n_slots]: bit j of word slot = CrashDetection(node, knn[node][j]) (RewireRoot, AMRRT.cpp:496-500;
+ * RTRRT.cpp:304-320), 0 where the node has fewer than k neighbours.  Host variant: page-locked buffers are written by the kernel. */
+RTPP_API int rtpp_tick_plan_info(rtpp_ctx *ctx, int divisor, size_t *n_slots, const int32_t **d_slot_id, const int32_t **d_slot_of_id,
+                                 int *usable, double *far_fraction);
+RTPP_API int rtpp_tick_check_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_tree_bits, uint32_t *d_row_bits);
+RTPP_API int rtpp_tick_check(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *tree_bits, uint32_t *row_bits);
+/* ONE tick over the GPUs of a node (SURVEY 8(e) grain 2; tree, table and planes replicated): the launch's blocks are dealt
+ * round-robin over the ranks, every block stores its verdict words into EVERY rank's buffers (tree_all[r], row_all[r]: rank r's
+ * buffers as mapped in this process, rtpp_peer_alloc / rtpp_peer_open), and the last block to retire signals the peers and waits
+ * for theirs (flags_all[r]: RTPP_PEER_FLAG_INTS zero-initialised ints per rank; `epoch` must increase by one per call; alternate
+ * two result buffers by epoch parity).  The wait is bounded (RTPP_PEER_TIMEOUT_MS, default 1000): when a peer never arrives this
+ * rank's buffers are filled with 1-bits (every edge reads BLOCKED: fail closed) and rtpp_peer_status reports the timeout. */
+#define RTPP_PEER_FLAG_INTS 16
+RTPP_API int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *const *tree_all, uint32_t *const *row_all,
+                                           int32_t *const *flags_all, int rank, int world, int epoch);
+/* Synchronises the ctx stream; *timeouts = fused exchanges that timed out on this rank's flag array since the last call. */
+RTPP_API int rtpp_peer_status(rtpp_ctx *ctx, int32_t *d_flags, int *timeouts);
 /* C2 RTpoint::operator% RTRRT.h:47-52 on n point pairs (exposed for parity tests). */
 RTPP_API int rtpp_dist(rtpp_ctx *ctx, const float *xyxy, size_t n, float *out);
 

@@ -227,6 +227,32 @@ class Ctx:
         self.call("tick_edges_check", _p(d), int(divisor), int(mask), _p(bits), C.byref(ne))
         return self.unpack_bits(bits, ne.value)
 
+    def tick_plan_info(self, divisor=2, want_ids=True):
+        """The slot order of the windowed tick (rtpp_tick_plan_info): dict(n_slots, usable, far_fraction, slot_id, slot_of_id)."""
+        ns, p_id, p_of = C.c_size_t(), C.c_void_p(), C.c_void_p()
+        usable, far = C.c_int(), C.c_double()
+        self.call("tick_plan_info", int(divisor), C.byref(ns), C.byref(p_id), C.byref(p_of), C.byref(usable), C.byref(far))
+        out = {"n_slots": ns.value, "usable": bool(usable.value), "far_fraction": far.value, "d_slot_id": p_id.value, "d_slot_of_id": p_of.value}
+        if want_ids and ns.value:
+            out["slot_id"] = np.zeros(ns.value, np.int32)
+            self.d2h(out["slot_id"], p_id.value)
+            out["slot_of_id"] = np.zeros(self.nodes_count(), np.int32)
+            self.d2h(out["slot_of_id"], p_of.value)
+            self.sync()
+        return out
+
+    def tick_check(self, divisor, mask):
+        """One tick through host buffers in the windowed kernel's layout -> (tree_bits [n-1 verdicts], row_words [n_slots])."""
+        n = self.nodes_count()
+        info = self.tick_plan_info(divisor, want_ids=False)
+        tree = np.zeros(max(1, (max(n - 1, 0) + 31) // 32), np.uint32)
+        rows = np.zeros(max(1, info["n_slots"]), np.uint32)
+        self.call("tick_check", int(divisor), int(mask), _p(tree), _p(rows))
+        return self.unpack_bits(tree, max(n - 1, 0)), rows[: info["n_slots"]]
+
+    def tick_check_dev(self, divisor, mask, d_tree_bits, d_row_bits):
+        self.call("tick_check_dev", int(divisor), int(mask), C.c_void_p(d_tree_bits), C.c_void_p(d_row_bits))
+
     # ---- tree costs
     def tree_set(self, parent, cost, col):
         p, c, l = _c(parent, np.int32), _c(cost, np.float32), _c(col, np.uint8)

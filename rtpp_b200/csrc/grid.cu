@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(32 * KNN_NODES_WARPS) knn_nodes_kernel(GridVie
 void rtpp_nodes_destroy(rtpp_ctx *ctx) {
     NodeStore *s = ctx->nodes;
     if (!s) return;
+    rtpp_tick_plan_free(s);
     cudaFree(s->xy), cudaFree(s->sxy), cudaFree(s->sid), cudaFree(s->cell_of), cudaFree(s->cell_start), cudaFree(s->cursor), cudaFree(s->gap);
     cudaFree(s->knn_table), cudaFree(s->knn_pos), cudaFree(s->pos_of), cudaFree(s->edge_list), cudaFree(s->scan_totals), cudaFree(s->cp), cudaFree(s->edge_w), cudaFree(s->child_start), cudaFree(s->children), cudaFree(s->frontier), cudaFree(s->counters);
     delete s;
@@ -317,6 +318,7 @@ int rtpp_knn_table_build(rtpp_ctx *ctx, int k) {
     }
     s->knn_n = s->n;
     s->edge_list_n = -1;
+    rtpp_tick_plan_invalidate(s);
     int rc = rtpp_knn_nodes_dev(ctx, k, s->knn_table, nullptr); // also re-sorts the hash: sid covers every node
     if (rc) return rc;
     // the same table in cell-sorted positions: neighbours of a node are neighbours in sxy[], so the

@@ -49,7 +49,13 @@ struct NodeStore {
     float4 *edge_list = nullptr; // materialised tick edge list (tree edges, then node -> k-NN edges), NaN = no edge
     size_t edge_list_cap = 0;
     int edge_list_n = -1;       // node count the node -> k-NN part was built for (-1 = stale)
+    struct TickPlan *plan = nullptr; // tick.cu: supercell-ordered plan of the windowed tick check
 };
 
 int rtpp_nodes_build_internal(rtpp_ctx *ctx);
+void rtpp_tick_plan_free(NodeStore *s);       // tick.cu
+void rtpp_tick_plan_invalidate(NodeStore *s); // tick.cu
+// tick.cu: the windowed tick; *ran = false when the plan does not apply (the caller takes the gathering kernels)
+int rtpp_tick_window_run(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_tree_bits, uint32_t *d_row_bits, bool *ran);
+int rtpp_tick_window_run_packed(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d_bits, bool *ran);
 int rtpp_grid_view(rtpp_ctx *ctx, GridView *g);
