@@ -7,21 +7,24 @@ Workload (BASELINE.json configs[3], the largest single-GPU configuration): AM-RR
 4096x4096 occupancy map (PCG64 seed 42: 400 rectangles + 200 discs, plus 6 dynamic obstacles) with
 1e6 tree nodes.  One STEP = one batched collision pass over every candidate edge of one rewire
 tick: the 999 999 tree edges (R3 re-cost, AMRRT.cpp:185-199) + the 25e6 rewire edges node ->
-25-NN (AMRRT.cpp:496-500), divisor 2, both planes; 26.0e6 edges, 416 MB of end points (> L2).
-metric = edge collision checks / s.  `value`: edge list resident in HBM, K launches timed with
-CUDA events on the launching stream.  `e2e`: one replanning tick over the same 26.0e6 edges through the
-host-buffer C-ABI calls a planner class makes (rtpp_map_draw_dynamic + rtpp_tick_edges_check): the
-obstacle poses go in, the verdict words come back to pinned host memory, the tree stays resident;
-the same batch as an explicit end-point list from the host (rtpp_edges_check, 416 MB H2D per step)
-is reported beside it.  `roofline`: algorithmic bytes of the step / launch time against the measured
-HBM peak, plus the L2 form against denominators measured in the same run (rtpp_measure_peaks).
-Extras (the other edge kernels, k-NN queries/s, propagate / relax latency, the four planners'
+25-NN (AMRRT.cpp:496-500), divisor 2, both planes: 25 999 999 edges.
+metric = edge collision checks / s.
+`value`: the tick over the RESIDENT tree (rtpp_tick_check_dev: windowed kernel, csrc/tick.cu), K launches timed with CUDA
+events on the launching stream; the launch reads ~250 MB of plan + tree (> L2) and no edge list.
+N > 1 (torchrun): ONE tick — the same 25 999 999 edges — split over the ranks (strong scaling): the tree is replicated,
+the tick's work items go round-robin over the ranks and every rank ends with ALL verdict words
+(rtpp_tick_check_allgather_dev: the all-gather is peer stores over NVLink inside the launch); time = max over ranks.
+`e2e`: one replanning tick through the host-buffer C-ABI calls a planner class makes
+(rtpp_map_draw_dynamic + rtpp_tick_check): the obstacle poses go in, the verdict words come back to page-locked host
+memory, the tree stays resident.  The same edges as an explicit end-point list from the host (rtpp_edges_check, 416 MB H2D per
+step) are reported beside it.
+`roofline`: algorithmic bytes of the step (16 + 4 * probes + 1/8 per edge) / launch time against the measured
+HBM peak, with the physically moved bytes (ncu) and the instruction-issue form next to it.
+Extras (the explicit-list kernel, the other edge kernels, k-NN queries/s, propagate / relax latency, the four planners'
 replan iterations/s and tick latencies against the CPU port) are measured outside the timed region.
 
---impl reference: the reference's own AMRRTplanner::CrashDetection (compiled in place into
-oracle/_ref; the oracle port if that library is absent) over the same edges on all host threads.
-N > 1 (torchrun): every rank owns its own copy of the same workload (fixed work per GPU), no
-data-path collective; weak scaling; time = max over ranks.
+--impl reference: the reference's own AMRRTplanner::CrashDetection (compiled in place into oracle/_ref; the oracle port if
+that library is absent) over the SAME 25 999 999 edges per step on all host threads (rank 0 only).
 """
 import argparse
 import json
@@ -134,10 +137,29 @@ class Workload:
         cost0[0], col0[0] = 0.0, 0
         self.ctx.tree_set(self.parent, cost0, col0)
         self.ctx.knn_table_build(KNN)
+        # the tick's result buffers in the windowed kernel's layout: packed tree bits + one verdict word per plan slot
+        self.plan = self.ctx.tick_plan_info(DIVISOR)
+        if not self.plan["usable"]:
+            raise SystemExit("the windowed tick plan does not apply to the C4 workload")
+        self.tree_bits = torch.zeros((n - 1 + 31) // 32, dtype=torch.int32, device=self.dev)
+        self.row_bits = torch.zeros(self.plan["n_slots"], dtype=torch.int32, device=self.dev)
         torch.cuda.synchronize()
 
     def step(self):
+        """The timed step: one tick's collision pass over the resident tree (windowed kernel)."""
+        self.ctx.tick_check_dev(DIVISOR, 3, self.tree_bits.data_ptr(), self.row_bits.data_ptr())
+
+    def explicit_step(self):
+        """The same 25 999 999 edges as an explicit end-point list (streaming kernel K1)."""
         self.ctx.edges_check_dev(self.edges.data_ptr(), self.n_edges, DIVISOR, 3, self.bits.data_ptr())
+
+    def tick_verdicts(self, tree_words, row_words):
+        """(tree words, slot row words) as numpy uint32 -> one verdict per edge in the explicit list's order."""
+        n = len(self.xy)
+        tb = np.unpackbits(np.ascontiguousarray(tree_words).view(np.uint8), bitorder="little")[: n - 1]
+        r = np.ascontiguousarray(row_words).view(np.uint32)[self.plan["slot_of_id"]]
+        rb = ((r[:, None] >> np.arange(KNN, dtype=np.uint32)[None, :]) & 1).astype(np.uint8).reshape(-1)
+        return np.concatenate([tb, rb])
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -206,15 +228,15 @@ def cpu_edge_fn(S, D, threads):
 
 
 def cpu_edge_rate(S, D, edges, threads, reps=5):
-    """-> (edges/s, kind, sample, fn): the WHOLE step's edge list, `reps` times after one warm-up pass, best."""
+    """-> (edges/s, kind, sample, verdicts): the WHOLE step's edge list, `reps` times after one warm-up pass, best."""
     fn, kind = cpu_edge_fn(S, D, threads)
     fn(edges[: min(len(edges), 2_000_000)])
-    best = 0.0
+    best, verdicts = 0.0, None
     for _ in range(reps):
         t = time.perf_counter()
-        fn(edges)
+        verdicts = fn(edges)
         best = max(best, len(edges) / (time.perf_counter() - t))
-    return best, kind, f"all {len(edges)} step edges x{reps}, best (persistent thread pool)", fn
+    return best, kind, f"all {len(edges)} step edges x{reps}, best (persistent thread pool)", verdicts
 
 
 def c4_edges_host(xy, idx):
@@ -273,7 +295,7 @@ def workload_config(n_edges):
     return {"workload": "C4: AM-RRT* on synthetic 4096x4096 map, 1e6 tree nodes; step = collision pass over "
                         "999999 tree edges + 25e6 rewire (node -> 25-NN) edges, divisor 2, planes S|D",
             "map": "4096x4096 seed 42", "nodes": N_NODES, "k": KNN, "divisor": DIVISOR, "edges_per_step": int(n_edges),
-            "l2_policy": "inputs larger than L2 (416 MB edge list per step)"}
+            "l2_policy": "inputs larger than L2 (about 250 MB of plan + tree read per step; the explicit-list extra reads 416 MB)"}
 
 
 # ------------------------------------------------------------------------------------ main
@@ -313,6 +335,8 @@ def main():
         run_reference(args, rank, world)
         return 0
 
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
@@ -321,19 +345,30 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # weak scaling = the SAME work on every GPU: all ranks build the identical workload (seed 0).  (Per-rank seeds gave per-rank
-    # step times between 0.167 and 0.191 ms on ONE GPU — the node sample decides how many long tree edges there are — and the
-    # max over ranks then measured the heaviest sample instead of scaling.)
+    # every rank builds the identical workload (seed 0): for N > 1 the tree is REPLICATED and one tick is split over the ranks
     wl = Workload(local_rank, seed=0)
     ctx = wl.ctx
+    peer = None
+    if world > 1:
+        from rtpp_b200 import shard
+
+        peer = shard.PeerTick(ctx, DIVISOR)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = [None]
+
+    def step():
+        if peer is None:
+            wl.step()
+        else:
+            last[0] = peer.check(3)  # this rank's share; the verdict words of the WHOLE tick land in every rank's buffers
+
     for _ in range(args.warmup):
-        wl.step()
+        step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -342,41 +377,48 @@ def main():
     t_host0 = time.perf_counter()
     ev0.record(wl.stream)
     for _ in range(args.steps):
-        wl.step()
+        step()
     ev1.record(wl.stream)
     barrier()
     t_host1 = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.kernel_launches() - launches0
+    if peer is not None:
+        peer.status()  # raises if an exchange timed out (the buffers would read "blocked")
     # keep the GPU busy a little longer if the timed region was too short for NVML's sampling period
     if t_host1 - t_host0 < 0.25:
         t_b0 = time.perf_counter()
         while time.perf_counter() - t_b0 < 0.3:
             for _ in range(50):
-                wl.step()
-            torch.cuda.synchronize()
+                step()
+            barrier()
         t_host0, t_host1 = t_b0, time.perf_counter()
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     clocks = sampler.summary(t_host0, t_host1)
 
-    # max over ranks
+    # max over ranks; for N > 1 the ranks together did ONE step per iteration
     t = torch.tensor([ms_total], dtype=torch.float64, device=wl.dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = wl.n_edges * world / (ms_step * 1e-3)
+    value = wl.n_edges / (ms_step * 1e-3)
 
-    # ---- e2e: one replanning tick through the host-buffer C-ABI calls.  What changes per tick crosses
-    # the boundary inside the timed region: the obstacle poses go in (DrawDObsmap runs on the device), the
-    # verdict words come back to pinned host memory; the tree itself (nodes, parents, k-NN table) is
-    # resident, exactly as the planner classes keep it.  Same 26.0 M edges, same verdicts as `value`.
-    import ctypes as C
+    # the timed path's verdicts, for the parity checks below (every rank holds the whole tick)
+    if peer is None:
+        torch.cuda.synchronize()
+        gpu_tree, gpu_rows = wl.tree_bits.cpu().numpy(), wl.row_bits.cpu().numpy()
+    else:
+        gpu_tree, gpu_rows = peer.read(last[0])
+    gpu_verdicts = wl.tick_verdicts(gpu_tree, gpu_rows)
 
+    # ---- e2e: one replanning tick through the host-buffer C-ABI calls.  What changes per tick crosses the boundary inside
+    # the timed region: the obstacle poses go in (DrawDObsmap runs on the device), the verdict words come back to page-locked
+    # host memory; the tree itself (nodes, parents, k-NN table, plan) is resident, exactly as the planner classes keep it.
     e2e_steps = max(3, min(args.steps, 20))
-    h_bits = torch.empty((wl.n_edges + 31) // 32, dtype=torch.int32, pin_memory=True)
-    ne = C.c_size_t()
+    h_tree = torch.empty(wl.tree_bits.numel(), dtype=torch.int32, pin_memory=True)
+    h_rows = torch.empty(wl.row_bits.numel(), dtype=torch.int32, pin_memory=True)
     circ = np.ascontiguousarray(np.array(wl.obstacles[0], np.int32))
     pxy = np.ascontiguousarray(np.concatenate(wl.obstacles[1]).astype(np.int32))
     psz = np.ascontiguousarray(np.array([len(p) for p in wl.obstacles[1]], np.int32))
@@ -384,35 +426,45 @@ def main():
     def e2e_step():
         # MainTask's DrawDObsmap (obstacle poses in) + the tick's collision pass (verdict words out)
         ctx.call("map_draw_dynamic", C.c_void_p(circ.ctypes.data), len(circ), C.c_void_p(pxy.ctypes.data), C.c_void_p(psz.ctypes.data), len(psz))
-        ctx.call("tick_edges_check", None, DIVISOR, 3, C.c_void_p(h_bits.data_ptr()), C.byref(ne))
+        if peer is None:
+            ctx.call("tick_check", DIVISOR, 3, C.c_void_p(h_tree.data_ptr()), C.c_void_p(h_rows.data_ptr()))  # synchronous
+        else:
+            d_tree, d_rows = peer.check(3)
+            ctx.call("d2h", C.c_void_p(h_tree.data_ptr()), C.c_void_p(d_tree), C.c_size_t(h_tree.numel() * 4))
+            ctx.call("d2h", C.c_void_p(h_rows.data_ptr()), C.c_void_p(d_rows), C.c_size_t(h_rows.numel() * 4))
+            ctx.sync()
 
     for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()  # synchronous: returns after the verdict words are back on the host
+        e2e_step()  # returns after the verdict words are back on the host
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device=wl.dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        peer.status()
     e2e_s = float(t.item())
-    same = bool(ne.value == wl.n_edges and (h_bits.to(wl.dev) == wl.bits).all().item())
-    e2e = {"value": wl.n_edges * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(circ.nbytes + pxy.nbytes + psz.nbytes),
-           "d2h_bytes_per_step": int(h_bits.numel() * 4), "steps": e2e_steps, "matches_resident_run": same,
-           "api": "rtpp_map_draw_dynamic + rtpp_tick_edges_check (host buffers): obstacle poses in, verdict words out (pinned), tree resident"}
-    # the same batch as an explicit end-point list from the host (rtpp_edges_check): PCIe-bound by 16 B/edge
+    same = bool(np.array_equal(h_tree.numpy(), gpu_tree.view(np.int32)) and np.array_equal(h_rows.numpy(), gpu_rows.view(np.int32)))
+    e2e = {"value": wl.n_edges / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(circ.nbytes + pxy.nbytes + psz.nbytes),
+           "d2h_bytes_per_step": int((h_tree.numel() + h_rows.numel()) * 4), "steps": e2e_steps, "matches_resident_run": same,
+           "api": ("rtpp_map_draw_dynamic + rtpp_tick_check (host buffers): obstacle poses in, verdict words out (page-locked, written by the kernel), tree resident"
+                   if peer is None else
+                   "per rank: rtpp_map_draw_dynamic + rtpp_tick_check_allgather_dev + D2H of the whole tick's verdict words (page-locked); max over ranks")}
+    # the same edges as an explicit end-point list from the host (rtpp_edges_check): PCIe-bound by 16 B/edge
     h_edges = torch.empty((wl.n_edges, 4), dtype=torch.float32, pin_memory=True)
     h_edges.copy_(wl.edges)
-    h_bits2 = torch.empty_like(h_bits)
-    for _ in range(2):
-        ctx.call("edges_check", C.c_void_p(h_edges.data_ptr()), C.c_size_t(wl.n_edges), DIVISOR, 3, C.c_void_p(h_bits2.data_ptr()))
-    t0 = time.perf_counter()
-    for _ in range(5):
-        ctx.call("edges_check", C.c_void_p(h_edges.data_ptr()), C.c_size_t(wl.n_edges), DIVISOR, 3, C.c_void_p(h_bits2.data_ptr()))
-    e2e["explicit_edge_list"] = {"value": wl.n_edges / ((time.perf_counter() - t0) / 5), "h2d_bytes_per_step": wl.n_edges * 16,
-                                 "api": "rtpp_edges_check (host buffers, pinned)", "per_rank": True}
+    if rank == 0:
+        h_bits2 = torch.empty(wl.bits.numel(), dtype=torch.int32, pin_memory=True)
+        for _ in range(2):
+            ctx.call("edges_check", C.c_void_p(h_edges.data_ptr()), C.c_size_t(wl.n_edges), DIVISOR, 3, C.c_void_p(h_bits2.data_ptr()))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.call("edges_check", C.c_void_p(h_edges.data_ptr()), C.c_size_t(wl.n_edges), DIVISOR, 3, C.c_void_p(h_bits2.data_ptr()))
+        e2e["explicit_edge_list"] = {"value": wl.n_edges / ((time.perf_counter() - t0) / 5), "h2d_bytes_per_step": wl.n_edges * 16,
+                                     "d2h_bytes_per_step": int(h_bits2.numel() * 4), "api": "rtpp_edges_check (host buffers, page-locked), one GPU"}
 
     # ---- BASELINE configs[4]: the scenario sweep, sharded by instance id over the ranks (all ranks take part)
     sweep = None
@@ -425,6 +477,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            peer.close()
             dist.destroy_process_group()
         return 0
 
@@ -442,56 +495,64 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
-    traffic = None
+    prof = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_dram_traffic.json")))["dram_bytes_per_launch"]
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_k1w_ncu_summary.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "edge_check_f32_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    traffic = prof.get("dram_bytes_per_launch")
+    # what the launch has to read: neighbour coordinates (8 B/edge slot), slot tables, node table + parents, plan masks
+    n_slots = wl.plan["n_slots"]
+    moved_model = n_slots * KNN * 8 + n_slots * (8 + 4 + 4 + 4) + N_NODES * (8 + 8) + n_slots * 4 + (N_NODES // 8)
+    roofline = {"bound": "hbm", "kernel": "tick_check_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, burst)" if peaks else "fallback 6650",
                 "algorithmic_bytes_per_edge": 16 + 4 * probes_per_edge + 0.125, "mean_probes_per_edge": probes_per_edge,
-                "stream_only_GBs": wl.n_edges * 16.125 / (ms_step * 1e-3) / 1e9}
-    # the L2 form of the same launch (one 32-byte sector per probe) against the L2 gather rate measured in
-    # this run, and the other same-run denominators (L2 line stream, FP32 FFMA issue, HBM copy) next to MEASURED_PEAKS
+                "note": "the algorithmic formula (SURVEY 8(d)) charges 16 B of end points per edge and one 4-byte plane word per probe to HBM; "
+                        "the windowed kernel streams 8 B of neighbour coordinates per edge and probes a shared-memory copy of the map window, "
+                        "so it moves fewer bytes than the formula counts and frac can exceed 1: physical_frac and issue_frac say what bounds it",
+                "moved_bytes_model": int(moved_model), "physical_GBs": (traffic or moved_model) / (ms_step * 1e-3) / 1e9,
+                "physical_frac": (traffic or moved_model) / (ms_step * 1e-3) / 1e9 / peak}
+    if prof.get("warp_instructions_per_launch"):
+        # instruction-issue form: warp instructions of one launch (ncu) / launch time vs 148 SMs x 4 schedulers x SM clock
+        issue_peak = ctx.sm_count() * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6
+        roofline["issue_frac"] = prof["warp_instructions_per_launch"] / (ms_step * 1e-3) / issue_peak
+        roofline["warp_instructions_per_32_edges"] = prof["warp_instructions_per_launch"] / (wl.n_edges / 32)
+        roofline["profile"] = prof.get("source")
     try:
         mp = ctx.measure_peaks(8 << 20, 5)
-        l2_achieved = wl.n_edges * probes_per_edge * 32 / (ms_step * 1e-3) / 1e9
-        roofline["l2_form"] = {"achieved": l2_achieved, "peak": mp["l2_sector_gather_gbs"], "unit": "GB/s",
-                               "frac": l2_achieved / mp["l2_sector_gather_gbs"],
-                               "definition": "32 B x probes / launch time vs random 32-byte-sector loads (ld.global.cg) out of an "
-                                             "8 MiB L2-resident buffer; a value above 1 means the probes are served by L1 / merged inside the warp's request (tile layout), i.e. L2 is not the bound"}
         roofline["same_run_peaks"] = mp
     except Exception as exc:  # the bench line must survive a failed microbenchmark
         roofline["same_run_peaks"] = {"error": str(exc)}
 
-    # ---- CPU baseline on this box's host cores (bounded sample of the same edges)
+    # ---- CPU baseline on this box's host cores: the WHOLE step, and full parity of the timed GPU path against it
     threads = os.cpu_count() or 1
-    cpu_rate, kind, sample_desc, fn = cpu_edge_rate(wl.S, wl.D, edges_host, threads)
-    # parity spot check of the timed path against the same CPU routine
-    chk = edges_host[:1_000_000]
-    got = np.unpackbits(wl.bits[: len(chk) // 32 + 1].cpu().numpy().view(np.uint8), bitorder="little")[: len(chk)]
-    parity_ok = bool(np.array_equal(got, fn(chk)))
+    cpu_rate, kind, sample_desc, cpu_verdicts = cpu_edge_rate(wl.S, wl.D, edges_host, threads)
+    parity_ok = bool(np.array_equal(gpu_verdicts, cpu_verdicts))
     cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample_desc,
-                    "verdicts_match_gpu": parity_ok}
+                    "verdicts_match_gpu": parity_ok, "verdicts_compared": int(len(cpu_verdicts))}
 
     extras = {}
     if not args.no_extras:
-        extras = measure_extras(wl, torch, sweep)
+        extras = measure_extras(wl, torch, sweep, roofline_formula=(16 + 4 * probes_per_edge + 0.125), peak=peak, cpu_verdicts=cpu_verdicts)
         if sharded_batch:
             extras["sharded_edge_batch"] = sharded_batch
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(wl.n_edges), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras}
+    if world > 1:
+        line["config"]["sharding"] = ("one tick split over the ranks: tree replicated, work items round-robin, verdict words stored into every rank's "
+                                      "buffers over NVLink by the kernel (rtpp_tick_check_allgather_dev)")
     emit(line)
     if world > 1:
         dist.barrier()
+        peer.close()
         dist.destroy_process_group()
     return 0
 
 
-def measure_extras(wl, torch, sweep):
+def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdicts=None):
     """Neighbour queries/s and tick latencies on the resident C4 state (outside the timed region)."""
     ctx = wl.ctx
     out = {}
@@ -508,6 +569,13 @@ def measure_extras(wl, torch, sweep):
         return e0.elapsed_time(e1) / reps
 
     n = len(wl.xy)
+    # the same step as an explicit end-point list (K1 of csrc/edges.cu: streams 16 B per edge, probes the plane through L1/L2)
+    ms = timed(wl.explicit_step, 20)
+    got = np.unpackbits(wl.bits.cpu().numpy().view(np.uint8), bitorder="little")[: wl.n_edges]
+    out["explicit_list_kernel"] = {"kernel": "edge_check_f32_kernel", "ms_per_step": ms, "edges_per_s": wl.n_edges / (ms * 1e-3),
+                                   "verdicts_match_cpu": None if cpu_verdicts is None else bool(np.array_equal(got, cpu_verdicts))}
+    if roofline_formula and peak:
+        out["explicit_list_kernel"]["roofline_frac"] = wl.n_edges * roofline_formula / (ms * 1e-3) / 1e9 / peak
     ms = timed(lambda: ctx.knn_nodes_dev(KNN, wl.knn_idx.data_ptr()), 5)
     out["knn_queries_per_s"] = n / (ms * 1e-3)
     out["knn_all_nodes_ms"] = ms
@@ -858,7 +926,7 @@ def measure_sharded_batch(wl, rank, world, torch, dist, reps=20):
     fused_words = peer.read(d_words)
     same = same_fused = None
     if rank == 0:
-        wl.step()  # rank 0's own single-GPU verdicts of the same edges
+        wl.explicit_step()  # rank 0's own single-GPU verdicts of the same edges
         torch.cuda.synchronize()
         same = bool((full == wl.bits).all().item())
         same_fused = bool(np.array_equal(fused_words, wl.bits.cpu().numpy()))

@@ -113,9 +113,12 @@ RTPP_API int rtpp_edges_check(rtpp_ctx *ctx, const float *xyxy, size_t n, int di
  * share — the 2048-edge blocks g with g mod world == rank, round-robin because an edge's cost varies with its length by
  * two orders of magnitude — and every block stores its verdict words into the same word range of every rank's result
  * buffer (bits_all[r], as mapped in this process; plain stores over NVLink), then the rank signals its peers and waits
- * for theirs (flags_all[r]: world int32 per rank, `epoch` must grow by one per call): when the stream reaches the end of
- * the call, bits_all[rank] holds the verdict words of the whole batch, as rtpp_edges_check_dev on one GPU writes them.
- * Alternate two result buffers (epoch parity) so that a fast peer never overwrites words still being read. */
+ * for theirs (flags_all[r]: RTPP_PEER_FLAG_INTS zero-initialised int32 per rank, `epoch` must grow by one per call): when the
+ * stream reaches the end of the call, bits_all[rank] holds the verdict words of the whole batch, as rtpp_edges_check_dev on one
+ * GPU writes them.  Alternate two result buffers (epoch parity) so that a fast peer never overwrites words still being read.
+ * The wait for the peers is BOUNDED (rtpp_peer_set_timeout_ms, default 1000 ms).  A rank whose peer never arrives fails closed: its
+ * result buffer is filled with 1-bits (every edge reads blocked) and rtpp_peer_status reports the timeout; callers must check it
+ * before trusting a batch.  d_xyxy must be 16-byte aligned and n must not exceed 2^32 - 1 (RTPP_ERR_INVALID otherwise). */
 #define RTPP_MAX_PEERS 8
 RTPP_API int rtpp_peer_alloc(rtpp_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64]);
 RTPP_API int rtpp_peer_open(rtpp_ctx *ctx, const unsigned char handle[64], void **peer_ptr);
@@ -165,13 +168,14 @@ RTPP_API int rtpp_tick_check(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_
  * round-robin over the ranks, every block stores its verdict words into EVERY rank's buffers (tree_all[r], row_all[r]: rank r's
  * buffers as mapped in this process, rtpp_peer_alloc / rtpp_peer_open), and the last block to retire signals the peers and waits
  * for theirs (flags_all[r]: RTPP_PEER_FLAG_INTS zero-initialised ints per rank; `epoch` must increase by one per call; alternate
- * two result buffers by epoch parity).  The wait is bounded (RTPP_PEER_TIMEOUT_MS, default 1000): when a peer never arrives this
- * rank's buffers are filled with 1-bits (every edge reads BLOCKED: fail closed) and rtpp_peer_status reports the timeout. */
+ * two result buffers by epoch parity).  The wait is bounded (rtpp_peer_set_timeout_ms, default 1000 ms): when a peer never arrives
+ * this rank's buffers are filled with 1-bits (every edge reads BLOCKED: fail closed) and rtpp_peer_status reports the timeout. */
 #define RTPP_PEER_FLAG_INTS 16
 RTPP_API int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *const *tree_all, uint32_t *const *row_all,
                                            int32_t *const *flags_all, int rank, int world, int epoch);
 /* Synchronises the ctx stream; *timeouts = fused exchanges that timed out on this rank's flag array since the last call. */
 RTPP_API int rtpp_peer_status(rtpp_ctx *ctx, int32_t *d_flags, int *timeouts);
+RTPP_API int rtpp_peer_set_timeout_ms(rtpp_ctx *ctx, double ms);
 /* C2 RTpoint::operator% RTRRT.h:47-52 on n point pairs (exposed for parity tests). */
 RTPP_API int rtpp_dist(rtpp_ctx *ctx, const float *xyxy, size_t n, float *out);
 

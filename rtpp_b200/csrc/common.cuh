@@ -47,6 +47,7 @@ struct rtpp_ctx {
     size_t scratch_bytes[4] = {0, 0, 0, 0};
 
     NodeStore *nodes = nullptr;
+    double peer_timeout_ms = 1000.0; // bound of the fused multi-GPU exchanges' flag wait (rtpp_peer_set_timeout_ms)
 };
 
 #define RTPP_CK(ctx, call)                                                                          \

@@ -119,23 +119,39 @@ edge_deferred_kernel(PlaneView pl, const float4 *__restrict__ edges, MarchThresh
 
 // After a rank's fused check has finished (stream order), tell every peer (its flag slot `rank` := epoch, system scope)
 // and wait until every peer has told us: from then on this rank's result buffer holds the whole batch's verdict words.
+// The wait is bounded (rtpp_peer_set_timeout_ms): when a peer never arrives the rank's result buffer is filled with 1-bits —
+// every edge reads BLOCKED, fail closed — and the sticky timeout counter of its flag array is raised (rtpp_peer_status).
 struct PeerFlags {
     int *p[RTPP_MAX_PEERS];
 };
-__global__ void peer_signal_wait_kernel(PeerFlags flags_all, int rank, int world, int epoch) {
+static constexpr int kPeerFlagTimeouts = RTPP_MAX_PEERS; // same slot as tick.cu's kFlagTimeouts
+__global__ void __launch_bounds__(256) peer_signal_wait_kernel(PeerFlags flags_all, int rank, int world, int epoch, uint32_t *own_bits, size_t n_words,
+                                                              long long spin_limit) {
     const int r = threadIdx.x;
-    int *theirs = nullptr, *mine = nullptr;
+    int *theirs = nullptr, *mine = nullptr, *own = nullptr;
 #pragma unroll
     for (int k = 0; k < RTPP_MAX_PEERS; k++) {
         if (k == r) theirs = flags_all.p[k] + rank;
-        if (k == rank) mine = flags_all.p[k] + r;
+        if (k == rank) mine = flags_all.p[k] + r, own = flags_all.p[k];
     }
     const bool peer = r < world && r != rank;
+    bool timed_out = false;
     if (peer) *(volatile int *)theirs = epoch;
     __threadfence_system();
-    if (peer) // bounded (about a second): a peer that never arrives must not hang the GPU; the caller's result check fails instead
-        for (int it = 0; *(volatile int *)mine < epoch && it < (1 << 23); it++) __nanosleep(100);
+    if (peer) {
+        long long it = 0;
+        while (*(volatile int *)mine < epoch && it < spin_limit) {
+            __nanosleep(64);
+            it++;
+        }
+        timed_out = *(volatile int *)mine < epoch;
+    }
+    const int any_timeout = __syncthreads_or(timed_out);
     __threadfence_system();
+    if (any_timeout) {
+        for (size_t i = threadIdx.x; i < n_words; i += blockDim.x) own_bits[i] = 0xffffffffu;
+        if (threadIdx.x == 0) atomicAdd(own + kPeerFlagTimeouts, 1);
+    }
 }
 
 // E5b: binary64 end points, binary32 interpolation parameter (CDRT.cpp:586-600).
@@ -414,6 +430,7 @@ extern "C" {
 int rtpp_edges_check_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, int divisor, int plane_mask, uint32_t *d_bits) {
     if (!ctx || (n && (!d_xyxy || !d_bits))) return RTPP_ERR_INVALID;
     if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    if (((uintptr_t)d_xyxy & 15) != 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "the edge list must be 16-byte aligned (float4 loads)");
     PlaneView pv;
     int rc = rtpp_select_plane(ctx, plane_mask, &pv);
     if (rc) return rc;
@@ -435,6 +452,8 @@ int rtpp_edges_check_allgather_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n,
     if (!ctx || !bits_all || !flags_all || (n && !d_xyxy)) return RTPP_ERR_INVALID;
     if (world < 1 || world > RTPP_MAX_PEERS || rank < 0 || rank >= world) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad rank / world size");
     if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    if (((uintptr_t)d_xyxy & 15) != 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "the edge list must be 16-byte aligned");
+    if (n > 0xffffffffull) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "at most 2^32 - 1 edges per fused batch");
     PlaneView pv;
     int rc = rtpp_select_plane(ctx, plane_mask, &pv);
     if (rc) return rc;
@@ -463,7 +482,8 @@ int rtpp_edges_check_allgather_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n,
     if (world > 1) {
         PeerFlags pf;
         for (int r = 0; r < RTPP_MAX_PEERS; r++) pf.p[r] = r < world ? flags_all[r] : nullptr;
-        peer_signal_wait_kernel<<<1, 32, 0, ctx->stream>>>(pf, rank, world, epoch);
+        const long long spin_limit = (long long)(ctx->peer_timeout_ms * 1e6 / 100.0) + 1; // one poll is ~100 ns
+        peer_signal_wait_kernel<<<1, 256, 0, ctx->stream>>>(pf, rank, world, epoch, bits_all[rank], (n + 31) / 32, spin_limit);
         RTPP_LAUNCHED(ctx);
     }
     return RTPP_OK;
@@ -531,9 +551,12 @@ static int tick_edges_run(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *
         }
         s->edge_list = nullptr, s->edge_list_cap = 0, s->edge_list_n = -1;
         const size_t want = (size_t)(s->capacity - 1) + s->capacity * s->knn_k;
+        // a tick list that does not fit is not an error — the gathering kernel checks the same edges from the node table — but it
+        // is recorded in the ctx so that a caller who expects the streaming rate can see why it did not get it
         if (cudaMalloc(&s->edge_list, want * sizeof(float4)) == cudaSuccess) s->edge_list_cap = want;
         else {
             (void)cudaGetLastError();
+            ctx->err = "tick edge list (" + std::to_string(want * sizeof(float4)) + " bytes) could not be allocated: using the gathering kernel";
             use_list = false;
         }
     }
@@ -600,6 +623,7 @@ int rtpp_tick_edges_check(rtpp_ctx *ctx, const uint8_t *dynamic_plane, int divis
 int rtpp_edges_check_f64_dev(rtpp_ctx *ctx, const double *d_xyxy, size_t n, int divisor, int plane_mask, uint32_t *d_bits) {
     if (!ctx || (n && (!d_xyxy || !d_bits))) return RTPP_ERR_INVALID;
     if (divisor <= 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "divisor must be positive");
+    if (((uintptr_t)d_xyxy & 31) != 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "the binary64 edge list must be 32-byte aligned (double4 loads)");
     PlaneView pv;
     int rc = rtpp_select_plane(ctx, plane_mask, &pv);
     if (rc) return rc;
@@ -611,6 +635,7 @@ int rtpp_edges_check_f64_dev(rtpp_ctx *ctx, const double *d_xyxy, size_t n, int 
 
 int rtpp_edges_first_hit_dev(rtpp_ctx *ctx, const float *d_xyxy, size_t n, uint32_t *d_bits, float *d_pstart) {
     if (!ctx || (n && (!d_xyxy || !d_bits || !d_pstart))) return RTPP_ERR_INVALID;
+    if (((uintptr_t)d_xyxy & 15) != 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "the edge list must be 16-byte aligned (float4 loads)");
     PlaneView pv;
     int rc = rtpp_select_plane(ctx, 3, &pv);
     if (rc) return rc;

@@ -10,7 +10,7 @@
 //   * the 4x4 bit tiles around the supercell (supercell + 32-pixel halo) are staged in shared memory per warp, column-major
 //     by tile column, so a probe is one 32-bit shared load whose bank is the pixel row: the 32 lanes of a step probe around
 //     32 nearby nodes and mostly hit distinct banks.  Staging is either one coalesced 128-byte load + conflict-free store
-//     per tile or (RTPP_TICK_BULK=1) one cp.async.bulk per tile completing on the warp's mbarrier;
+//     per tile (RTPP_TICK_BULK=0) or, by default, one cp.async.bulk per tile completing on the warp's mbarrier;
 //   * the interpolation ps*t + (1-t)*pe of both coordinates is one packed binary32x2 sequence (FMUL2, FMUL2, FFMA2 by a
 //     run-time 1.0 so that ptxas cannot contract the product into the sum, FADD2.RZ for the truncation): the same roundings
 //     as the reference's scalar code, half the instructions;
@@ -18,14 +18,16 @@
 //     (bit j = edge node -> knn[node][j] blocked).
 // Edges the window cannot serve — neighbour outside the halo, an end point on the map's last row / column or outside it, a
 // march finer than 16 steps for the plan's divisor — are known when the plan is built: they form a static FAR list (explicit
-// end points) that the first blocks of the same launch check with the general warp routine of edges.cu; a window warp picks
-// their verdict bits up when it writes its rows (the far blocks have the lowest block indices and wait for nobody).  The
-// tree edges (parent -> child, any length) take the same general routine in the launch's next blocks.
+// end points) checked with the general warp routine of edges.cu by the same launch; a window warp picks their verdict bits
+// up when it writes its rows.  The tree edges (parent -> child, any length) take the same general routine.
+// The launch is ONE resident wave of persistent warps drawing work items from a queue (one atomicAdd per item): the far
+// list's 32-edge words first (so nobody waits for them), then the tree's words (a hub's thousand-pixel edges sit at its
+// head and are marched warp-wide), then the window groups — no block-sized tail and no warp idling inside a block.
 //
-// Multi-GPU (SURVEY 8(e) grain 2): with kPeers the tree and window blocks of ONE tick are dealt round-robin over the ranks
-// (the small far list is checked by every rank); a block stores its verdict words into every rank's result buffers over
-// NVLink (CUDA IPC mappings), and the LAST block of the launch to retire signals the peers and waits for their signals —
-// the exchange is part of the launch: no collective call, no second kernel.
+// Multi-GPU (SURVEY 8(e) grain 2): with kPeers the tree words and window groups of ONE tick are dealt round-robin over the
+// ranks (the small far list is checked by every rank); a warp stores its verdict words into every rank's result buffers
+// over NVLink (CUDA IPC mappings), and the LAST block of the launch to retire signals the peers and waits for their signals
+// — the exchange is part of the launch: no collective call, no second kernel.
 #include <stdlib.h>
 
 #include "edge_march.cuh"
@@ -91,8 +93,6 @@ static constexpr int kSCT = 2;            // supercell = kSCT x kSCT bit tiles (
 static constexpr int kWT = kSCT + 2;      // window = supercell + one tile of halo on every side (128 x 128 pixels)
 static constexpr int kWinWords = kWT * kWT * 32;
 static constexpr int kTickWarps = 8;
-static constexpr int kListChunk = 1;      // 32-edge words per warp of a far / tree block (small blocks: a run of long edges — a hub's
-                                          // children, thousands of pixels each — spreads over many SMs instead of one block)
 
 struct TickPlan {
     // slot order (a function of the node set alone)
@@ -114,7 +114,7 @@ struct TickPlan {
     float2 *ent = nullptr;     // [n_groups * k * 32] neighbour coordinates of (group, j, lane); the source itself where the edge is far / absent
     float4 *far_list = nullptr; // [far_edges] explicit end points
     uint32_t *far_bits = nullptr; // [far_edges / 32 + 1] their verdicts, rewritten by every launch
-    unsigned *far_done = nullptr; // far blocks retired so far (monotonic; a launch waits for its own target)
+    unsigned *far_done = nullptr; // far words finished so far (monotonic across launches; a launch waits for its own target)
     unsigned far_target = 0;
     unsigned long long *stats = nullptr; // [3] far edges, valid edges, cells too large to rank
     uint32_t *row_scratch = nullptr, *tree_scratch = nullptr; // for the legacy packed-bit entry points / pageable host buffers
@@ -263,24 +263,27 @@ struct TickArgs {
     PlaneView pl;
     MarchThresholds mt;
     float one; // 1.0f at run time (see fma2 above)
-    // far list (blocks [0, n_far_blocks))
+    // work items: [0, n_far_words) = 32-edge words of the far list, then this rank's share of the tick's tree words and window
+    // groups (shared item s: s < n_tree_words tree word s, else group s - n_tree_words), dealt round-robin to the launch's warps
+    unsigned n_items;
+    // far list
     const float4 *far_list;
     uint32_t *far_bits;
-    unsigned *far_done;
+    unsigned *far_done;      // far words finished so far (monotonic; this launch's window warps wait for far_target)
     unsigned far_target;
-    int n_far, n_far_blocks;
-    // tree edges (next n_tree_blocks blocks)
+    int n_far, n_far_words;
+    // tree edges
     const float2 *xy;
     const cpword *cp;
-    int n, n_tree_blocks;
+    int n, n_tree_words;
     uint32_t *tree_bits;
     // rewire edges (the rest)
-    int n_groups, k, groups_per_warp, scw;
+    int n_groups, k, scw;
     const int *group_sc, *far_off;
     const float2 *slot_xy, *ent;
     const uint32_t *far_mask, *valid_mask;
     uint32_t *row_bits;
-    int blk_stride, blk_first; // multi-GPU: this launch's tree / window block b is block b * blk_stride + blk_first of the tick
+    int stride, first;         // multi-GPU: this launch's shared item i is item i * stride + first of the tick
     int parts;                 // bit 0: tree edges, bit 1: rewire edges (RTPP_TICK_PARTS, profiling only; default 3)
 };
 
@@ -300,81 +303,87 @@ __device__ __forceinline__ uint32_t win_probe(u64 p, unsigned cblk) {
 }
 static_assert(kWT == 4, "win_probe's shift assumes a 4-tile-wide window");
 
-// 32 consecutive edges of an explicit list (far list) or of the tree (child e+1 and its parent) per warp and step
+// 32 consecutive edges of an explicit list (far list) or of the tree (child e+1 and its parent): one warp, one word
 template <bool kPeers, bool kTree>
-__device__ __forceinline__ void tick_list_block(const TickArgs &a, const TickPeers &peers, size_t blk) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t n_edges = kTree ? (size_t)(a.n - 1) : (size_t)a.n_far, words = (n_edges + 31) >> 5;
-    const size_t base = blk * kTickWarps * kListChunk;
-    for (int it = 0; it < kListChunk; it++) {
-        const size_t w = base + (size_t)it * kTickWarps + warp;
-        if (w >= words) break;
-        const size_t e = (w << 5) + lane;
-        bool valid = e < n_edges;
-        float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            if (kTree) {
-                const int b = (int)e + 1, p = cp_parent(a.cp[b]);
-                valid = p >= 0;
-                if (valid) {
-                    const float2 pa = a.xy[p], pb = a.xy[b];
-                    ed = make_float4(pa.x, pa.y, pb.x, pb.y);
-                }
-            } else {
-                ed = a.far_list[e];
+__device__ __forceinline__ void tick_list_word(const TickArgs &a, const TickPeers &peers, size_t w) {
+    const int lane = threadIdx.x & 31;
+    const size_t n_edges = kTree ? (size_t)(a.n - 1) : (size_t)a.n_far;
+    const size_t e = (w << 5) + lane;
+    bool valid = e < n_edges;
+    float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        if (kTree) {
+            const int b = (int)e + 1, p = cp_parent(a.cp[b]);
+            valid = p >= 0;
+            if (valid) {
+                const float2 pa = a.xy[p], pb = a.xy[b];
+                ed = make_float4(pa.x, pa.y, pb.x, pb.y);
             }
+        } else {
+            ed = a.far_list[e];
         }
-        const unsigned bits = warp_edges_verdict(a.pl, ed, valid, a.mt);
-        if (lane == 0) {
-            if (kTree) {
-                a.tree_bits[w] = bits;
-                if (kPeers) {
+    }
+    // tree words: the warp routine of edges.cu (a hub's thousand-pixel edges are marched by the whole warp).  Far words: every lane
+    // marches its own edge — far edges are tens of pixels long (32 to 64 steps), all of a word's edges are like that, and marching
+    // them one after the other warp-wide made these few words the launch's critical path
+    const unsigned bits = kTree ? warp_edges_verdict(a.pl, ed, valid, a.mt)
+                                : __ballot_sync(0xffffffffu, valid && rt_edge_blocked(a.pl, ed.x, ed.y, ed.z, ed.w, a.mt));
+    if (lane == 0) {
+        if (kTree) {
+            a.tree_bits[w] = bits;
+            if (kPeers) {
 #pragma unroll
-                    for (int r = 0; r < RTPP_MAX_PEERS - 1; r++)
-                        if (r < peers.n) peers.tree[r][w] = bits;
-                }
-            } else {
-                a.far_bits[w] = bits;
+                for (int r = 0; r < RTPP_MAX_PEERS - 1; r++)
+                    if (r < peers.n) peers.tree[r][w] = bits;
             }
+        } else {
+            a.far_bits[w] = bits;
         }
     }
 }
 
-template <bool kPeers, bool kBulk>
-__global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const TickArgs a, const TickPeers peers) {
+template <bool kPeers, bool kBulk, int kMinBlocks = 4>
+__global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel(const TickArgs a, const TickPeers peers) {
     __shared__ __align__(128) uint32_t win[kTickWarps][kWinWords];
     __shared__ __align__(8) unsigned long long bars[kTickWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
-    if ((int)blockIdx.x < a.n_far_blocks) {
-        // far list: every rank checks all of it; the launch's window warps wait for these blocks (lowest indices, no waiting here)
-        tick_list_block<false, false>(a, peers, blockIdx.x);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(a.far_done, 1u);
-    } else {
-        const size_t rel = (size_t)blockIdx.x - a.n_far_blocks;
-        const size_t blk = kPeers ? rel * a.blk_stride + a.blk_first : rel;
-        if (blk < (size_t)a.n_tree_blocks) {
-            if (a.parts & 1) tick_list_block<kPeers, true>(a, peers, blk);
-        } else if (a.parts & 2) {
-            const unsigned wbase = (unsigned)__cvta_generic_to_shared(&win[warp][0]);
-            const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[warp]);
-            unsigned parity = 0;
-            if (kBulk) {
-                if (lane == 0) {
-                    mbar_init(bar, 1);
-                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                }
-                __syncwarp();
-            }
-            int cur_sc = -1;
-            unsigned cblk = 0;
-            const u64 one2 = pk2(a.one, a.one);
-            const size_t g0 = ((blk - a.n_tree_blocks) * kTickWarps + warp) * (size_t)a.groups_per_warp;
-            for (int gi = 0; gi < a.groups_per_warp; gi++) {
-                const size_t grp = g0 + gi;
-                if (grp >= (size_t)a.n_groups) break;
+    const unsigned wbase = (unsigned)__cvta_generic_to_shared(&win[warp][0]);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[warp]);
+    unsigned parity = 0;
+    if (kBulk) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    int cur_sc = -1;
+    unsigned cblk = 0;
+    const u64 one2 = pk2(a.one, a.one);
+    // persistent warps: one resident wave; warp w takes items w, w + W, w + 2W, ... (far words first, then the tree — whose long
+    // edges sit at its head and so spread over all warps — then the window groups: no block-sized tail, no warp idling inside a
+    // block, and no shared counter: a single-address ticket atomic was 30 % of the stall samples of the first version)
+    const unsigned n_warps = gridDim.x * kTickWarps;
+    for (unsigned item = blockIdx.x * kTickWarps + warp; item < a.n_items; item += n_warps) {
+        if (item < (unsigned)a.n_far_words) {
+            // far list: every rank checks all of it; window warps wait for these words (taken first, and waiting for nobody)
+            tick_list_word<false, false>(a, peers, item);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(a.far_done, 1u);
+            continue;
+        }
+        const size_t rel = (size_t)item - a.n_far_words;
+        const size_t sh = kPeers ? rel * a.stride + a.first : rel;
+        if (sh < (size_t)a.n_tree_words) {
+            if (a.parts & 1) tick_list_word<kPeers, true>(a, peers, sh);
+            continue;
+        }
+        if (!(a.parts & 2)) continue;
+        {
+            {
+                const size_t grp = sh - a.n_tree_words;
                 const int sc = a.group_sc[grp];
                 if (sc != cur_sc) { // warp-uniform: bring the supercell's window in
                     cur_sc = sc;
@@ -475,11 +484,11 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
                 // window cannot serve, whose window coordinates are a stand-in) skip this shortcut: the far list has their verdicts.
                 if (srcb && fmask != vmask) row = vmask;
                 else if (fmask) {
-                    // verdicts of this node's far edges, checked by the launch's first blocks
-                    if (a.n_far_blocks) {
+                    // verdicts of this node's far edges: the queue's first items, long taken (and usually finished) by now
+                    if (a.n_far_words) {
                         for (long long it = 0; (int)(*(volatile unsigned *)a.far_done - a.far_target) < 0; it++) {
                             __nanosleep(32);
-                            if (it > (1ll << 26)) __trap(); // cannot happen: the far blocks precede every window block
+                            if (it > (1ll << 26)) __trap(); // cannot happen: the far words precede every group in the queue
                         }
                         __threadfence();
                     }
@@ -704,36 +713,48 @@ static int plan_build(rtpp_ctx *ctx, int divisor) {
     return RTPP_OK;
 }
 
-static void tick_fill_args(rtpp_ctx *ctx, const PlaneView &pv, int divisor, uint32_t *d_tree_bits, uint32_t *d_row_bits, TickArgs *a) {
+// one resident wave of persistent blocks
+static int tick_grid(rtpp_ctx *ctx, bool peers, bool bulk) {
+    int per_sm = 0;
+    cudaError_t e;
+    if (peers) e = bulk ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick_check_kernel<true, true>, 32 * kTickWarps, 0)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick_check_kernel<true, false>, 32 * kTickWarps, 0);
+    else e = bulk ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick_check_kernel<false, true>, 32 * kTickWarps, 0)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tick_check_kernel<false, false>, 32 * kTickWarps, 0);
+    if (e != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 2;
+    }
+    return ctx->sm_count * per_sm;
+}
+
+// fills the launch arguments and advances the plan's monotonic far counter for ONE launch
+static void tick_fill_args(rtpp_ctx *ctx, const PlaneView &pv, int divisor, uint32_t *d_tree_bits, uint32_t *d_row_bits, int rank, int world, TickArgs *a) {
     NodeStore *s = ctx->nodes;
     TickPlan *p = s->plan;
-    static const int gpw = getenv("RTPP_TICK_GPW") ? std::max(1, atoi(getenv("RTPP_TICK_GPW"))) : 2;
     static const int parts = getenv("RTPP_TICK_PARTS") ? atoi(getenv("RTPP_TICK_PARTS")) : 3;
     a->pl = pv;
     rtpp_march_thresholds(divisor, &a->mt);
     volatile float one = 1.0f;
     a->one = one;
-    const size_t per_block = (size_t)kTickWarps * kListChunk;
     a->far_list = p->far_list, a->far_bits = p->far_bits, a->far_done = p->far_done, a->n_far = (int)p->far_edges;
-    a->n_far_blocks = (int)((((size_t)p->far_edges + 31) / 32 + per_block - 1) / per_block);
-    p->far_target += (unsigned)a->n_far_blocks; // this launch's far blocks bring the counter here
+    a->n_far_words = (int)(((size_t)p->far_edges + 31) / 32);
+    p->far_target += (unsigned)a->n_far_words; // this launch's far words bring the counter here
     a->far_target = p->far_target;
     a->xy = s->xy, a->cp = s->cp, a->n = s->n;
-    a->n_tree_blocks = (int)((((size_t)(s->n - 1) + 31) / 32 + per_block - 1) / per_block);
+    a->n_tree_words = (int)(((size_t)(s->n - 1) + 31) / 32);
     a->tree_bits = d_tree_bits;
-    a->n_groups = p->n_groups, a->k = p->order_k, a->groups_per_warp = gpw, a->scw = p->scw;
+    a->n_groups = p->n_groups, a->k = p->order_k, a->scw = p->scw;
     a->group_sc = p->group_sc, a->far_off = p->far_off, a->slot_xy = p->slot_xy, a->ent = p->ent;
     a->far_mask = p->far_mask, a->valid_mask = p->valid_mask;
     a->row_bits = d_row_bits;
-    a->blk_stride = 1, a->blk_first = 0, a->parts = parts;
-}
-// tree + window blocks of the tick (the far blocks come on top, on every rank)
-static size_t tick_shared_blocks(const TickArgs &a) {
-    const size_t per_block = (size_t)kTickWarps * a.groups_per_warp;
-    return (size_t)a.n_tree_blocks + ((size_t)a.n_groups + per_block - 1) / per_block;
+    a->stride = world, a->first = rank, a->parts = parts;
+    const size_t shared = (size_t)a->n_tree_words + (size_t)a->n_groups;
+    const size_t mine = shared > (size_t)rank ? (shared - rank + world - 1) / world : 0;
+    a->n_items = (unsigned)((size_t)a->n_far_words + mine);
 }
 static bool tick_use_bulk() {
-    static const bool bulk = getenv("RTPP_TICK_BULK") && atoi(getenv("RTPP_TICK_BULK")) != 0;
+    static const bool bulk = !(getenv("RTPP_TICK_BULK") && atoi(getenv("RTPP_TICK_BULK")) == 0);
     return bulk;
 }
 
@@ -748,10 +769,10 @@ int rtpp_tick_window_run(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d
     TickPlan *p = ctx->nodes->plan;
     if (!p->usable) return RTPP_OK;
     TickArgs a;
-    tick_fill_args(ctx, pv, divisor, d_tree_bits, d_row_bits, &a);
+    const int grid = tick_grid(ctx, false, tick_use_bulk());
+    tick_fill_args(ctx, pv, divisor, d_tree_bits, d_row_bits, 0, 1, &a);
     TickPeers none;
     memset(&none, 0, sizeof(none));
-    const unsigned grid = (unsigned)(a.n_far_blocks + tick_shared_blocks(a));
     if (tick_use_bulk()) tick_check_kernel<false, true><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, none);
     else tick_check_kernel<false, false><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, none);
     RTPP_LAUNCHED(ctx);
@@ -851,10 +872,8 @@ int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, ui
     if (!p->usable) RTPP_FAIL(ctx, RTPP_ERR_STATE, "the windowed tick plan does not apply to this node store");
     if (!p->canonical) RTPP_FAIL(ctx, RTPP_ERR_STATE, "a hash cell holds too many nodes for a rank-independent slot order");
     TickArgs a;
-    tick_fill_args(ctx, pv, divisor, tree_all[rank], row_all[rank], &a);
-    a.blk_stride = world, a.blk_first = rank;
-    const size_t blocks = tick_shared_blocks(a);
-    const size_t mine = blocks > (size_t)rank ? (blocks - rank + world - 1) / world : 0;
+    const int grid = tick_grid(ctx, true, tick_use_bulk());
+    tick_fill_args(ctx, pv, divisor, tree_all[rank], row_all[rank], rank, world, &a);
     TickPeers peers;
     memset(&peers, 0, sizeof(peers));
     peers.rank = rank, peers.world = world, peers.epoch = epoch;
@@ -864,13 +883,16 @@ int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, ui
     }
     peers.own_row = row_all[rank], peers.own_tree = tree_all[rank];
     peers.row_words = (size_t)p->n_slots, peers.tree_words = ((size_t)(s->n - 1) + 31) / 32;
-    static const double timeout_ms = getenv("RTPP_PEER_TIMEOUT_MS") ? atof(getenv("RTPP_PEER_TIMEOUT_MS")) : 1000.0;
-    peers.spin_limit = (long long)(timeout_ms * 1e6 / 100.0) + 1; // one poll is ~100 ns (64 ns sleep + a system-scope load)
-    const unsigned grid = (unsigned)(a.n_far_blocks + mine);
-    if (grid == 0) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "empty tick");
+    peers.spin_limit = (long long)(ctx->peer_timeout_ms * 1e6 / 100.0) + 1; // one poll is ~100 ns (64 ns sleep + a system-scope load)
     if (tick_use_bulk()) tick_check_kernel<true, true><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, peers);
     else tick_check_kernel<true, false><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, peers);
     RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
+int rtpp_peer_set_timeout_ms(rtpp_ctx *ctx, double ms) {
+    if (!ctx || !(ms > 0.0)) return RTPP_ERR_INVALID;
+    ctx->peer_timeout_ms = ms;
     return RTPP_OK;
 }
 

@@ -96,7 +96,7 @@ class PeerEdgeBatch:
         self.epoch = 0
         mine = []
         handles = []
-        for nbytes in (self.n_words * 4, self.n_words * 4, 64):  # two result buffers, then the flags
+        for nbytes in (self.n_words * 4, self.n_words * 4, 64):  # two result buffers, then the flags (RTPP_PEER_FLAG_INTS ints)
             ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
             ctx._ck(ctx.L.rtpp_peer_alloc(ctx.h, C.c_size_t(nbytes), C.byref(ptr), h))
             mine.append(ptr.value)
@@ -129,10 +129,17 @@ class PeerEdgeBatch:
                                                                self.tabs[b], self.tabs[2], self.rank, self.world, self.epoch))
         return self.own[b]
 
+    def status(self):
+        """Synchronises; raises when a fused exchange timed out since the last call (its verdict words read blocked)."""
+        t = self.C.c_int()
+        self.ctx._ck(self.ctx.L.rtpp_peer_status(self.ctx.h, self.C.c_void_p(self.own[2]), self.C.byref(t)))
+        if t.value:
+            raise RuntimeError(f"{t.value} fused edge-batch exchange(s) timed out: a peer rank did not arrive; verdicts read blocked")
+
     def read(self, d_words):
         out = self.np.zeros(self.n_words, self.np.int32)
         self.ctx.d2h(out, d_words)
-        self.ctx.sync()
+        self.status()
         return out
 
     def close(self):
@@ -145,3 +152,91 @@ class PeerEdgeBatch:
             self.ctx.dev_free(p)
         self.opened, self.own = [], []
 
+
+
+class PeerTick:
+    """Grain 2 on the RESIDENT tree: ONE tick (tree edges + node -> k-NN edges of the replicated tree) checked by all ranks of a
+    node, rtpp_tick_check_allgather_dev.  The tick's work items go round-robin over the ranks; every warp stores its verdict words
+    straight into every rank's result buffers over NVLink (CUDA IPC mappings of rtpp_peer_alloc buffers) and the last block of a
+    rank's launch exchanges flags with the peers, so no collective call sits on the data path.  torch.distributed only carries the
+    64-byte IPC handles (and a digest of the slot order, which must be the same on every rank) at set-up.  Two result buffer pairs
+    alternate by call parity (include/rtpp_gpu.h).  A peer that never arrives makes the call fail closed: status() raises and the
+    buffers read "blocked"."""
+
+    FLAG_INTS = 16
+
+    def __init__(self, ctx, divisor):
+        import ctypes as C
+        import hashlib
+
+        import numpy as np
+
+        self.C, self.np, self.ctx, self.divisor = C, np, ctx, divisor
+        self.rank, self.world = world()
+        assert dist.is_initialized() and 1 <= self.world <= 8
+        info = ctx.tick_plan_info(divisor)
+        if not info["usable"]:
+            raise RuntimeError("the windowed tick plan does not apply to this node store")
+        self.n_slots = info["n_slots"]
+        self.slot_of_id = info["slot_of_id"]
+        self.tree_words = (max(ctx.nodes_count() - 1, 0) + 31) // 32
+        digest = hashlib.sha256(info["slot_id"].tobytes()).hexdigest()
+        self.epoch = 0
+        mine, handles = [], []
+        for nbytes in (self.tree_words * 4, self.n_slots * 4, self.tree_words * 4, self.n_slots * 4, self.FLAG_INTS * 4):
+            ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+            ctx._ck(ctx.L.rtpp_peer_alloc(ctx.h, C.c_size_t(max(nbytes, 4)), C.byref(ptr), h))
+            mine.append(ptr.value)
+            handles.append(bytes(h))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (digest, handles))
+        if any(e[0] != digest for e in everyone):
+            raise RuntimeError("the ranks disagree on the tick's slot order (different node sets?)")
+        self.own, self.opened = mine, []
+        self.ptrs = [[0] * self.world for _ in range(5)]  # [buffer kind][rank]: tree0, row0, tree1, row1, flags
+        for r in range(self.world):
+            for b in range(5):
+                if r == self.rank:
+                    self.ptrs[b][r] = mine[b]
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(everyone[r][1][b])
+                    ctx._ck(ctx.L.rtpp_peer_open(ctx.h, hb, C.byref(p)))
+                    self.ptrs[b][r] = p.value
+                    self.opened.append(p.value)
+        self.tabs = [(C.c_void_p * self.world)(*self.ptrs[b]) for b in range(5)]
+        dist.barrier()
+
+    def check(self, plane_mask):
+        """Launches this rank's share.  Returns (tree words, row words) device pointers of the WHOLE tick's verdicts on this rank
+        (valid once the ctx stream has passed this call)."""
+        self.epoch += 1
+        b = (self.epoch & 1) * 2
+        self.ctx._ck(self.ctx.L.rtpp_tick_check_allgather_dev(self.ctx.h, int(self.divisor), int(plane_mask), self.tabs[b], self.tabs[b + 1], self.tabs[4],
+                                                              self.rank, self.world, self.epoch))
+        return self.own[b], self.own[b + 1]
+
+    def status(self):
+        """Synchronises; raises when a fused exchange timed out since the last call (its verdicts read blocked)."""
+        t = self.C.c_int()
+        self.ctx._ck(self.ctx.L.rtpp_peer_status(self.ctx.h, self.C.c_void_p(self.own[4]), self.C.byref(t)))
+        if t.value:
+            raise RuntimeError(f"{t.value} fused tick exchange(s) timed out: a peer rank did not arrive; verdicts read blocked")
+
+    def read(self, ptrs):
+        tree = self.np.zeros(max(self.tree_words, 1), self.np.uint32)
+        rows = self.np.zeros(max(self.n_slots, 1), self.np.uint32)
+        self.ctx.d2h(tree, ptrs[0])
+        self.ctx.d2h(rows, ptrs[1])
+        self.status()
+        return tree[: self.tree_words], rows[: self.n_slots]
+
+    def close(self):
+        self.ctx.sync()
+        dist.barrier()
+        for p in self.opened:
+            self.ctx.L.rtpp_peer_close(self.ctx.h, self.C.c_void_p(p))
+        dist.barrier()
+        for p in self.own:
+            self.ctx.dev_free(p)
+        self.opened, self.own = [], []

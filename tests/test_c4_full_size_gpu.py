@@ -17,6 +17,7 @@ def wl():
 
     prev = torch.cuda.current_stream()
     w = bench.Workload(0, seed=0)
+    w.explicit_step()
     w.step()
     torch.cuda.synchronize()
     yield w
@@ -70,6 +71,45 @@ def test_edge_verdicts_full_size(wl, oracle):
     wl.ctx.edges_check_dev(wl.edges.data_ptr(), n, bench.DIVISOR, 1, bits2.data_ptr())
     torch.cuda.synchronize()
     assert int((bits2 & ~wl.bits).count_nonzero().item()) == 0
+
+
+def test_tick_window_full_size(wl, oracle):
+    """The bench's timed step — the windowed tick over the resident tree (csrc/tick.cu) — gives, for all 25 999 999 edges, the
+    verdicts of the explicit end-point list (checked against the oracle above), also through the legacy edge order of
+    rtpp_tick_edges_check_dev, after a change of the dynamic plane, and for divisor 5 (a second plan: other far edges)."""
+    import ctypes as C
+
+    import torch
+
+    import bench
+
+    n = wl.n_edges
+    want = _bits(wl.bits, n)
+    got = wl.tick_verdicts(wl.tree_bits.cpu().numpy(), wl.row_bits.cpu().numpy())
+    assert np.array_equal(got, want)
+    assert wl.plan["far_fraction"] < 0.01
+    legacy = torch.zeros_like(wl.bits)
+    ne = C.c_size_t()
+    wl.ctx.call("tick_edges_check_dev", bench.DIVISOR, 3, C.c_void_p(legacy.data_ptr()), C.byref(ne))
+    torch.cuda.synchronize()
+    assert ne.value == n and torch.equal(legacy, wl.bits)
+    # other obstacle poses, divisor 5: window and explicit list must still agree everywhere
+    circles = [(x + 37, y - 21, r) for (x, y, r) in wl.obstacles[0]]
+    wl.ctx.map_draw_dynamic(circles, wl.obstacles[1])
+    bits5 = torch.zeros_like(wl.bits)
+    wl.ctx.edges_check_dev(wl.edges.data_ptr(), n, 5, 3, bits5.data_ptr())
+    plan5 = wl.ctx.tick_plan_info(5)
+    assert plan5["usable"] and np.array_equal(plan5["slot_of_id"], wl.plan["slot_of_id"])  # the slot order does not depend on the divisor
+    tree5, rows5 = torch.zeros_like(wl.tree_bits), torch.zeros_like(wl.row_bits)
+    wl.ctx.tick_check_dev(5, 3, tree5.data_ptr(), rows5.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(wl.tick_verdicts(tree5.cpu().numpy(), rows5.cpu().numpy()), _bits(bits5, n))
+    pick = np.arange(0, n, 257)
+    D5 = wl.ctx.map_get_plane(2) * np.uint8(127)
+    assert np.array_equal(_bits(bits5, n)[pick], oracle.edges_check(wl.S, D5, wl.edges.cpu().numpy()[pick], 5, 3, nthreads=8))
+    wl.ctx.map_draw_dynamic(*wl.obstacles)  # restore for the tests below
+    wl.step()
+    torch.cuda.synchronize()
 
 
 def test_knn_table_full_size(wl, oracle):

@@ -159,3 +159,115 @@ def test_legacy_tick_order_goes_through_the_window_kernel(ctx, oracle):
     assert ctx.kernel_launches() - launches == 2  # tick_check_kernel + tick_repack_kernel
     e = np.concatenate([np.concatenate([xy[par[1:]], xy[1:]], 1), np.concatenate([np.repeat(xy, k, axis=0), xy[idx.reshape(-1)]], 1)])
     assert np.array_equal(got, oracle.edges_check(S, D, np.ascontiguousarray(e, np.float32), 5, 3, nthreads=8))
+
+
+def _peer_alloc(c, nbytes):
+    import ctypes as C
+
+    ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+    c._ck(c.L.rtpp_peer_alloc(c.h, C.c_size_t(max(nbytes, 4)), C.byref(ptr), h))
+    return ptr.value
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tick_allgather_protocol_on_one_gpu(ctx, oracle, world):
+    """rtpp_tick_check_allgather_dev with every 'rank' on this GPU, one after the other on one stream (kernels that wait for one
+    another must not share a GPU): before a rank's launch the flags of the ranks that have not run yet are set by hand, as if
+    they had already signalled; the flags of the ranks that HAVE run are the ones their kernels wrote.  After the last rank every
+    rank's buffers hold the whole tick, equal to the single-GPU verdicts; the work items each rank took are disjoint."""
+    import ctypes as C
+
+    S = oracle.load_map("MESS6")
+    rng = np.random.default_rng(600 + world)
+    D = dyn_plane(S.shape, rng, n_blobs=8)
+    H, W = S.shape
+    ctx.map_set_plane(1, S)
+    ctx.map_set_plane(2, D)
+    xy = _nodes(rng, 50_000, W, H, S)
+    n, k = len(xy), 25
+    ctx.nodes_reset(4, n, W, H)
+    ctx.nodes_append(xy)
+    ctx.knn_table_build(k)
+    par = rng.integers(0, n, n).astype(np.int32)
+    par[0] = -1
+    ctx.tree_set(par, np.zeros(n, np.float32), np.zeros(n, np.uint8))
+    want_tree, want_rows = ctx.tick_check(2, 3)
+    n_slots, tree_words = len(want_rows), (n - 1 + 31) // 32
+    bufs = [[_peer_alloc(ctx, tree_words * 4), _peer_alloc(ctx, n_slots * 4)] for _ in range(world)]
+    flags = [_peer_alloc(ctx, 64) for _ in range(world)]
+    try:
+        ttab = (C.c_void_p * world)(*[b[0] for b in bufs])
+        rtab = (C.c_void_p * world)(*[b[1] for b in bufs])
+        ftab = (C.c_void_p * world)(*flags)
+        for epoch in (1, 2):
+            for r in range(world):
+                later = np.zeros(16, np.int32)
+                ctx.d2h(later, flags[r])
+                ctx.sync()
+                for q in range(r + 1, world):
+                    later[q] = epoch  # rank q has "already signalled" rank r
+                ctx.h2d(flags[r], later)
+                ctx.call("tick_check_allgather_dev", 2, 3, ttab, rtab, ftab, r, world, epoch)
+                t = C.c_int()
+                ctx.call("peer_status", C.c_void_p(flags[r]), C.byref(t))
+                assert t.value == 0
+            for r in range(world):
+                tree = np.zeros(tree_words, np.uint32)
+                rows = np.zeros(n_slots, np.uint32)
+                ctx.d2h(tree, bufs[r][0])
+                ctx.d2h(rows, bufs[r][1])
+                f = np.zeros(16, np.int32)
+                ctx.d2h(f, flags[r])
+                ctx.sync()
+                assert np.array_equal(ctx.unpack_bits(tree, n - 1), want_tree), (world, epoch, r)
+                assert np.array_equal(rows, want_rows), (world, epoch, r)
+                assert all(f[q] == epoch for q in range(world) if q != r)
+    finally:
+        for b in bufs:
+            ctx.dev_free(b[0]), ctx.dev_free(b[1])
+        for f in flags:
+            ctx.dev_free(f)
+
+
+def test_tick_allgather_fails_closed_when_a_peer_never_arrives(ctx, oracle):
+    """A rank whose peer never signals gives up after the bounded wait: rtpp_peer_status reports the timeout and the rank's
+    result buffers read BLOCKED everywhere (a lost peer must never look like free edges)."""
+    import ctypes as C
+
+    S = oracle.load_map("MESS6")
+    rng = np.random.default_rng(33)
+    H, W = S.shape
+    ctx.map_set_plane(1, S)
+    ctx.map_clear_plane(2)
+    xy = _nodes(rng, 30_000, W, H, S)
+    n = len(xy)
+    ctx.nodes_reset(4, n, W, H)
+    ctx.nodes_append(xy)
+    ctx.knn_table_build(25)
+    par = rng.integers(0, n, n).astype(np.int32)
+    par[0] = -1
+    ctx.tree_set(par, np.zeros(n, np.float32), np.zeros(n, np.uint8))
+    n_slots, tree_words = ctx.tick_plan_info(2, want_ids=False)["n_slots"], (n - 1 + 31) // 32
+    bufs = [[_peer_alloc(ctx, tree_words * 4), _peer_alloc(ctx, n_slots * 4)] for _ in range(2)]
+    flags = [_peer_alloc(ctx, 64) for _ in range(2)]
+    try:
+        ctx.call("peer_set_timeout_ms", C.c_double(20.0))
+        ttab, rtab, ftab = ((C.c_void_p * 2)(*v) for v in ([b[0] for b in bufs], [b[1] for b in bufs], flags))
+        ctx.call("tick_check_allgather_dev", 2, 3, ttab, rtab, ftab, 0, 2, 1)  # rank 1 is never launched
+        t = C.c_int()
+        ctx.call("peer_status", C.c_void_p(flags[0]), C.byref(t))
+        assert t.value == 1
+        rows = np.zeros(n_slots, np.uint32)
+        tree = np.zeros(tree_words, np.uint32)
+        ctx.d2h(rows, bufs[0][1])
+        ctx.d2h(tree, bufs[0][0])
+        ctx.sync()
+        assert (rows == 0xFFFFFFFF).all() and (tree == 0xFFFFFFFF).all()
+        ctx.call("peer_status", C.c_void_p(flags[0]), C.byref(t))
+        assert t.value == 0  # cleared by the read
+    finally:
+        ctx.call("peer_set_timeout_ms", C.c_double(1000.0))
+        for b in bufs:
+            ctx.dev_free(b[0]), ctx.dev_free(b[1])
+        for f in flags:
+            ctx.dev_free(f)

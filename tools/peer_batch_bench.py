@@ -49,7 +49,7 @@ for r in range(world):
     if r == rank:
         print(f"rank {rank}: edges [{e0}, {e0 + nel})", {k: f"{v[0]:.4f} ms dev, {v[1]:.4f} ms host/call" for k, v in res.items()}, flush=True)
 words = peer.read(peer.check(wl.edges.data_ptr(), bench.DIVISOR, 3))
-wl.step()
+wl.explicit_step()
 torch.cuda.synchronize()
 print(f"rank {rank}: fused result equals the one-GPU verdicts:", bool((torch.from_numpy(words).to(wl.dev) == wl.bits).all().item()), flush=True)
 peer.close()

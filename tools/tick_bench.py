@@ -25,7 +25,7 @@ def main():
     out = {"n_slots": info["n_slots"], "usable": info["usable"], "far_fraction": info["far_fraction"]}
     tree = torch.zeros((n - 1 + 31) // 32, dtype=torch.int32, device=wl.dev)
     rows = torch.zeros(info["n_slots"], dtype=torch.int32, device=wl.dev)
-    wl.step()
+    wl.explicit_step()
     ctx.tick_check_dev(bench.DIVISOR, 3, tree.data_ptr(), rows.data_ptr())
     torch.cuda.synchronize()
     # verdict equality with the explicit list (itself checked against the oracle in tests/)
@@ -58,7 +58,7 @@ def main():
     import ctypes as C
 
     ne = C.c_size_t()
-    for name, fn in (("explicit_k1", wl.step),
+    for name, fn in (("explicit_k1", wl.explicit_step),
                      ("tick_window", lambda: ctx.tick_check_dev(bench.DIVISOR, 3, tree.data_ptr(), rows.data_ptr())),
                      ("tick_legacy_order", lambda: ctx.call("tick_edges_check_dev", bench.DIVISOR, 3, C.c_void_p(legacy.data_ptr()), C.byref(ne)))):
         out[name + "_ms_flushed"] = timed(fn, True)
