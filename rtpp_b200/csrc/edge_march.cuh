@@ -11,6 +11,8 @@ static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 3
 // (their verdict bit stays 0) and marched one warp per edge by edge_deferred_kernel, which ORs their bits in afterwards —
 // a block that meets a run of thousand-pixel edges otherwise becomes the kernel's critical path once the batch is split.
 static constexpr int kDeferP = 128;
+// kRound = 32-probe chunks issued together per round of the warp-wide march of a long edge
+template <int kRound = 1>
 __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, const float4 e, const bool valid, const MarchThresholds &mt,
                                                        uint32_t *defer_list = nullptr, unsigned *defer_count = nullptr,
                                                        uint32_t edge_index = 0) {
@@ -69,9 +71,14 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
         const int Ps = __shfl_sync(full, P, src);
         const float inv = rt_inv_pow2(Ps);
         bool hit = false;
-        for (int j0 = 1; j0 < Ps; j0 += 32) { // warp-uniform trip count, early exit per chunk
-            const int j = j0 + lane;
-            if (j < Ps) hit = rt_probe_interior(pl, sx, sy, tx, ty, __fmul_rn((float)j, inv));
+        // warp-uniform trip count, early exit per round.  A round is kRound 32-probe chunks issued together: the exit test makes
+        // the rounds a chain of dependent L2 / L1 latencies, and a thousand-pixel edge (a hub's child) is tens of chunks long
+        for (int j0 = 1; j0 < Ps; j0 += 32 * kRound) {
+#pragma unroll
+            for (int c = 0; c < kRound; c++) {
+                const int j = j0 + 32 * c + lane;
+                if (j < Ps) hit |= rt_probe_interior(pl, sx, sy, tx, ty, __fmul_rn((float)j, inv));
+            }
             if (__any_sync(full, hit)) {
                 hit = true;
                 break;

@@ -22,7 +22,8 @@
 // up when it writes its rows.  The tree edges (parent -> child, any length) take the same general routine.
 // The launch is ONE resident wave of persistent warps drawing work items from a queue (one atomicAdd per item): the far
 // list's 32-edge words first (so nobody waits for them), then the tree's words (a hub's thousand-pixel edges sit at its
-// head and are marched warp-wide), then the window groups — no block-sized tail and no warp idling inside a block.
+// head and are marched warp-wide), then the window groups — no block-sized tail and no warp idling inside a block.  The first
+// four fifths of the items are dealt round-robin; the rest is drawn from a counter by whichever warp is free (item times differ).
 //
 // Multi-GPU (SURVEY 8(e) grain 2): with kPeers the tree words and window groups of ONE tick are dealt round-robin over the
 // ranks (the small far list is checked by every rank); a warp stores its verdict words into every rank's result buffers
@@ -115,7 +116,7 @@ struct TickPlan {
     float4 *far_list = nullptr; // [far_edges] explicit end points
     uint32_t *far_bits = nullptr; // [far_edges / 32 + 1] their verdicts, rewritten by every launch
     unsigned *far_done = nullptr; // far words finished so far (monotonic across launches; a launch waits for its own target)
-    unsigned far_target = 0;
+    unsigned far_target = 0, work_base = 0; // far_done[1] is the tail's ticket counter
     unsigned long long *stats = nullptr; // [3] far edges, valid edges, cells too large to rank
     uint32_t *row_scratch = nullptr, *tree_scratch = nullptr; // for the legacy packed-bit entry points / pageable host buffers
     size_t cap_sc = 0, cap_slot_id = 0, cap_slot_xy = 0, cap_far = 0, cap_valid = 0, cap_far_off = 0, cap_group = 0, cap_ent = 0,
@@ -266,6 +267,10 @@ struct TickArgs {
     // work items: [0, n_far_words) = 32-edge words of the far list, then this rank's share of the tick's tree words and window
     // groups (shared item s: s < n_tree_words tree word s, else group s - n_tree_words), dealt round-robin to the launch's warps
     unsigned n_items;
+    // the first n_static items are dealt round-robin; the rest (the last fifth) is drawn from a counter by whichever warp is free:
+    // item = atomicAdd(work) - work_base, monotonic across launches
+    unsigned n_static, work_base;
+    unsigned *work;
     // far list
     const float4 *far_list;
     uint32_t *far_bits;
@@ -284,7 +289,8 @@ struct TickArgs {
     const uint32_t *far_mask, *valid_mask;
     uint32_t *row_bits;
     int stride, first;         // multi-GPU: this launch's shared item i is item i * stride + first of the tick
-    int parts;                 // bit 0: tree edges, bit 1: rewire edges (RTPP_TICK_PARTS, profiling only; default 3)
+    int parts;                 // bit 0: tree edges, bit 1: rewire edges, bit 3: skip the far merge (RTPP_TICK_PARTS, profiling only; default 3)
+    unsigned long long *timing; // RTPP_TICK_TIMING=1 (profiling only): per block {start, work done, exit} in globaltimer ns
 };
 
 // One probe of the shared window.  q = packed (x, y) + 2^23 rounded toward zero: the low mantissa bits are the pixel.
@@ -348,6 +354,11 @@ __global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel
     __shared__ __align__(8) unsigned long long bars[kTickWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
+    if (a.timing && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.timing[3 * blockIdx.x] = t;
+    }
     const unsigned wbase = (unsigned)__cvta_generic_to_shared(&win[warp][0]);
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[warp]);
     unsigned parity = 0;
@@ -361,11 +372,22 @@ __global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel
     int cur_sc = -1;
     unsigned cblk = 0;
     const u64 one2 = pk2(a.one, a.one);
-    // persistent warps: one resident wave; warp w takes items w, w + W, w + 2W, ... (far words first, then the tree — whose long
-    // edges sit at its head and so spread over all warps — then the window groups: no block-sized tail, no warp idling inside a
-    // block, and no shared counter: a single-address ticket atomic was 30 % of the stall samples of the first version)
+    // persistent warps: one resident wave.  Warp w takes items w, w + W, w + 2W, ... of the first four fifths (far words first, then
+    // the tree — whose long edges sit at its head and so spread over all warps — then the window groups) and draws the rest from a
+    // counter.  (Drawing EVERY item from one counter made that atomic 30 % of the stall samples; dealing ALL items round-robin left
+    // the slowest block 25 % behind the mean.)
     const unsigned n_warps = gridDim.x * kTickWarps;
-    for (unsigned item = blockIdx.x * kTickWarps + warp; item < a.n_items; item += n_warps) {
+    unsigned next_static = blockIdx.x * kTickWarps + warp;
+    for (;;) {
+        unsigned item;
+        if (next_static < a.n_static) {
+            item = next_static, next_static += n_warps;
+        } else { // the tail: equal item counts are not equal times (march levels, window reloads, long tree edges)
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(a.work, 1u) - a.work_base;
+            item = a.n_static + __shfl_sync(full, t, 0);
+            if (item >= a.n_items) break;
+        }
         if (item < (unsigned)a.n_far_words) {
             // far list: every rank checks all of it; window warps wait for these words (taken first, and waiting for nobody)
             tick_list_word<false, false>(a, peers, item);
@@ -483,7 +505,7 @@ __global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel
                 // A blocked source blocks every edge of the node (RTRRT.cpp:204-207).  Nodes whose edges are all far (also: sources the
                 // window cannot serve, whose window coordinates are a stand-in) skip this shortcut: the far list has their verdicts.
                 if (srcb && fmask != vmask) row = vmask;
-                else if (fmask) {
+                else if (fmask && !(a.parts & 8)) {
                     // verdicts of this node's far edges: the queue's first items, long taken (and usually finished) by now
                     if (a.n_far_words) {
                         for (long long it = 0; (int)(*(volatile unsigned *)a.far_done - a.far_target) < 0; it++) {
@@ -492,9 +514,12 @@ __global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel
                         }
                         __threadfence();
                     }
-                    int f = a.far_off[slot];
+                    // the slot's far verdicts are consecutive bits of the far list's words (at most k <= 32 of them: two words)
+                    const int f = a.far_off[slot];
+                    const uint32_t w0 = __ldcg(a.far_bits + (f >> 5)), w1 = __ldcg(a.far_bits + (f >> 5) + 1);
+                    uint32_t fb = __funnelshift_r(w0, w1, f & 31);
                     row &= ~fmask;
-                    for (uint32_t m = fmask; m; m &= m - 1, f++) row |= ((__ldcg(a.far_bits + (f >> 5)) >> (f & 31)) & 1u) << (__ffs(m) - 1);
+                    for (uint32_t m = fmask; m; m &= m - 1, fb >>= 1) row |= (fb & 1u) << (__ffs(m) - 1);
                 }
                 row &= vmask;
                 a.row_bits[slot] = row;
@@ -504,6 +529,14 @@ __global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel
                         if (r < peers.n) peers.row[r][slot] = row;
                 }
             }
+        }
+    }
+    if (a.timing) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.timing[3 * blockIdx.x + 1] = t;
         }
     }
     if (kPeers) {
@@ -540,6 +573,11 @@ __global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel
             }
             if (threadIdx.x == 0) mine[kFlagDone] = 0;
         }
+    }
+    if (a.timing && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.timing[3 * blockIdx.x + 2] = t;
     }
 }
 
@@ -638,7 +676,7 @@ static int plan_order(rtpp_ctx *ctx) {
     if (!p->far_done) {
         RTPP_CK(ctx, cudaMalloc(&p->far_done, 16));
         RTPP_CK(ctx, cudaMemsetAsync(p->far_done, 0, 16, ctx->stream));
-        p->far_target = 0;
+        p->far_target = 0, p->work_base = 0;
     }
     if (!p->slot_of_id) RTPP_CK(ctx, cudaMalloc(&p->slot_of_id, s->capacity * sizeof(int)));
     // padded counts -> first slots (the scan's scratch of the hash build is large enough: nsc <= cells)
@@ -729,7 +767,8 @@ static int tick_grid(rtpp_ctx *ctx, bool peers, bool bulk) {
 }
 
 // fills the launch arguments and advances the plan's monotonic far counter for ONE launch
-static void tick_fill_args(rtpp_ctx *ctx, const PlaneView &pv, int divisor, uint32_t *d_tree_bits, uint32_t *d_row_bits, int rank, int world, TickArgs *a) {
+static void tick_fill_args(rtpp_ctx *ctx, const PlaneView &pv, int divisor, uint32_t *d_tree_bits, uint32_t *d_row_bits, int rank, int world, int grid,
+                           TickArgs *a) {
     NodeStore *s = ctx->nodes;
     TickPlan *p = s->plan;
     static const int parts = getenv("RTPP_TICK_PARTS") ? atoi(getenv("RTPP_TICK_PARTS")) : 3;
@@ -748,14 +787,49 @@ static void tick_fill_args(rtpp_ctx *ctx, const PlaneView &pv, int divisor, uint
     a->group_sc = p->group_sc, a->far_off = p->far_off, a->slot_xy = p->slot_xy, a->ent = p->ent;
     a->far_mask = p->far_mask, a->valid_mask = p->valid_mask;
     a->row_bits = d_row_bits;
-    a->stride = world, a->first = rank, a->parts = parts;
+    a->stride = world, a->first = rank, a->parts = parts, a->timing = nullptr;
     const size_t shared = (size_t)a->n_tree_words + (size_t)a->n_groups;
     const size_t mine = shared > (size_t)rank ? (shared - rank + world - 1) / world : 0;
     a->n_items = (unsigned)((size_t)a->n_far_words + mine);
+    // four fifths of the items are dealt round-robin (whole rounds of the launch's warps), the rest is drawn dynamically
+    static const int static_pct = getenv("RTPP_TICK_STATIC_PCT") ? std::min(100, std::max(0, atoi(getenv("RTPP_TICK_STATIC_PCT")))) : 80;
+    const unsigned n_warps = (unsigned)grid * kTickWarps;
+    a->n_static = (unsigned)((unsigned long long)a->n_items * static_pct / 100 / n_warps) * n_warps;
+    a->work = p->far_done + 1;
+    a->work_base = p->work_base;
+    p->work_base += (a->n_items - a->n_static) + n_warps; // every warp draws one ticket past the end
 }
 static bool tick_use_bulk() {
     static const bool bulk = !(getenv("RTPP_TICK_BULK") && atoi(getenv("RTPP_TICK_BULK")) == 0);
     return bulk;
+}
+
+// RTPP_TICK_TIMING=1 (profiling only): every launch is followed by a synchronisation and a one-line summary of the blocks' time
+// stamps on stderr — when the first / last block started, when the blocks finished their items, when they left the kernel
+static int tick_timing_begin(rtpp_ctx *ctx, int grid, TickArgs *a) {
+    static const bool on = getenv("RTPP_TICK_TIMING") != nullptr;
+    if (!on) return RTPP_OK;
+    void *d = nullptr;
+    int rc = rtpp_scratch(ctx, 2, (size_t)grid * 24, &d);
+    if (rc) return rc;
+    a->timing = (unsigned long long *)d;
+    return RTPP_OK;
+}
+static int tick_timing_end(rtpp_ctx *ctx, int grid, TickArgs *a) {
+    if (!a->timing) return RTPP_OK;
+    std::vector<unsigned long long> h((size_t)grid * 3);
+    RTPP_CK(ctx, cudaMemcpyAsync(h.data(), a->timing, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long t0 = ~0ull, s1 = 0, w0 = ~0ull, w1 = 0, e1 = 0;
+    double wsum = 0;
+    for (int b = 0; b < grid; b++) {
+        t0 = std::min(t0, h[3 * b]), s1 = std::max(s1, h[3 * b]);
+        w0 = std::min(w0, h[3 * b + 1]), w1 = std::max(w1, h[3 * b + 1]), e1 = std::max(e1, h[3 * b + 2]);
+    }
+    for (int b = 0; b < grid; b++) wsum += (double)(h[3 * b + 1] - t0);
+    fprintf(stderr, "[rtpp tick timing] blocks %d items %u: last start +%.1f us, work done first +%.1f mean +%.1f last +%.1f us, exit +%.1f us\n", grid, a->n_items,
+            (s1 - t0) * 1e-3, (w0 - t0) * 1e-3, wsum / grid * 1e-3, (w1 - t0) * 1e-3, (e1 - t0) * 1e-3);
+    return RTPP_OK;
 }
 
 // shared with edges.cu: runs the windowed tick when the plan applies.  *ran = false: the caller takes its own path.
@@ -770,12 +844,16 @@ int rtpp_tick_window_run(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d
     if (!p->usable) return RTPP_OK;
     TickArgs a;
     const int grid = tick_grid(ctx, false, tick_use_bulk());
-    tick_fill_args(ctx, pv, divisor, d_tree_bits, d_row_bits, 0, 1, &a);
+    tick_fill_args(ctx, pv, divisor, d_tree_bits, d_row_bits, 0, 1, grid, &a);
     TickPeers none;
     memset(&none, 0, sizeof(none));
+    rc = tick_timing_begin(ctx, grid, &a);
+    if (rc) return rc;
     if (tick_use_bulk()) tick_check_kernel<false, true><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, none);
     else tick_check_kernel<false, false><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, none);
     RTPP_LAUNCHED(ctx);
+    rc = tick_timing_end(ctx, grid, &a);
+    if (rc) return rc;
     *ran = true;
     return RTPP_OK;
 }
@@ -873,7 +951,7 @@ int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, ui
     if (!p->canonical) RTPP_FAIL(ctx, RTPP_ERR_STATE, "a hash cell holds too many nodes for a rank-independent slot order");
     TickArgs a;
     const int grid = tick_grid(ctx, true, tick_use_bulk());
-    tick_fill_args(ctx, pv, divisor, tree_all[rank], row_all[rank], rank, world, &a);
+    tick_fill_args(ctx, pv, divisor, tree_all[rank], row_all[rank], rank, world, grid, &a);
     TickPeers peers;
     memset(&peers, 0, sizeof(peers));
     peers.rank = rank, peers.world = world, peers.epoch = epoch;
@@ -884,9 +962,13 @@ int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, ui
     peers.own_row = row_all[rank], peers.own_tree = tree_all[rank];
     peers.row_words = (size_t)p->n_slots, peers.tree_words = ((size_t)(s->n - 1) + 31) / 32;
     peers.spin_limit = (long long)(ctx->peer_timeout_ms * 1e6 / 100.0) + 1; // one poll is ~100 ns (64 ns sleep + a system-scope load)
+    rc = tick_timing_begin(ctx, grid, &a);
+    if (rc) return rc;
     if (tick_use_bulk()) tick_check_kernel<true, true><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, peers);
     else tick_check_kernel<true, false><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, peers);
     RTPP_LAUNCHED(ctx);
+    rc = tick_timing_end(ctx, grid, &a);
+    if (rc) return rc;
     return RTPP_OK;
 }
 
