@@ -938,12 +938,15 @@ def measure_sharded_batch(wl, rank, world, torch, dist, reps=20):
                      "how": "contiguous word ranges (rank 0's holds the long tree edges); K1 + all_gather_into_tensor of the verdict words, %d bytes per rank" % (4 * (((ne + 31) // 32 + world - 1) // world))}}
 
 
-def measure_sweep(ctx, rank, world, torch, dist, dev, n_inst=8192, ticks=3, dt=5000, n_samples=2000):
-    """BASELINE configs[4]: 8192 independent RT-RRT* planner instances (8 bundled maps x the reference's scripted
-    start/goal tables x seeds, tools/sweep_bench.py), sharded by instance id round-robin over the ranks (strong
-    scaling: the instance count is fixed).  One tick = UpdateTree + ExpandRewiring(50 ms) + GetPath under the
-    virtual clock (dt ns per clock read => 50e6/dt = 10^4 queue pops per tick).  No data-path collective; the
-    fixed-size per-scenario result records are all-gathered at the end (NCCL), tick time = max over ranks."""
+def measure_sweep(ctx, rank, world, torch, dist, dev, n_seeds=32, dt=5000, n_samples=2000, max_ticks=200, check_every=128):
+    """BASELINE configs[4] as SURVEY 8(d) defines C5: 8192 independent RT-RRT* planner instances = 8 bundled maps x 32 (start,
+    goal) pairs (16 from the reference's scripted tables, 16 seeded free pairs) x 32 sample streams; every instance runs
+    replanning ticks (UpdateTree + ExpandRewiring(50 ms) + GetPath under the virtual clock: dt ns per clock read => 10^4 clock
+    reads per tick) until it has consumed its 2000 samples, after which ExpandRewiring returns at once (RTRRT.cpp:228-232) —
+    the sweep ends when the last instance is there.  Sharded by instance id round-robin over the ranks (strong scaling: the
+    instance count is fixed); no data-path collective; the fixed-size per-scenario result records are all-gathered at the
+    end (NCCL); tick time = max over ranks.  Rank 0 keeps the trees of every `check_every`-th instance (all its own) for the
+    tree-byte comparison against the CPU oracle in measure_replanning."""
     import hashlib
 
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -952,10 +955,16 @@ def measure_sweep(ctx, rank, world, torch, dist, dev, n_inst=8192, ticks=3, dt=5
     from rtpp_b200 import shard
 
     maps = {name: orc.load_map(name) for name in sb.SCEN}
-    inst = sb.make_instances(n_inst, maps)
+    inst = sb.make_instances_c5(maps, n_seeds)
+    n_inst = len(inst)
     ids = shard.instance_ids(n_inst, rank, world)
-    lat, st, _ = sb.run_gpu(ctx, orc, [inst[i] for i in ids], maps, n_samples, ticks, dt)
-    t = torch.tensor(lat, dtype=torch.float64, device=dev)
+    lat, st, samples, eng = sb.run_gpu(ctx, orc, [inst[i] for i in ids], maps, n_samples, max_ticks, dt, until_exhausted=True, keep=True)
+    # every rank must tick the same number of times for the max-over-ranks tick times to line up: pad with zeros
+    nt = torch.tensor([len(lat)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(nt, op=dist.ReduceOp.MAX)
+    n_ticks = int(nt.item())
+    t = torch.tensor(list(lat) + [0.0] * (n_ticks - len(lat)), dtype=torch.float64, device=dev)
     # record = n_nodes, samples_used, iters, pops_r, pops_s, status, path_len, path_cost_bits
     rec = torch.from_numpy(np.ascontiguousarray(st[:, [0, 2, 4, 5, 6, 9, 10, 12]])).to(dev)
     if world > 1:
@@ -964,43 +973,57 @@ def measure_sweep(ctx, rank, world, torch, dist, dev, n_inst=8192, ticks=3, dt=5
     lat = t.cpu().numpy()
     rec = rec.cpu().numpy()
     tot = float(lat.sum())
-    return {"inst": inst, "maps": maps, "records": rec, "n_samples": n_samples, "ticks": ticks, "dt": dt,
+    checked = {}
+    if rank == 0:
+        for k in range(0, n_inst, check_every):
+            if k % world == 0:
+                checked[k] = (eng.read_tree(k // world), int(st[k // world, 2]))
+    eng.close()
+    return {"inst": inst, "maps": maps, "records": rec, "n_samples": n_samples, "ticks": n_ticks, "dt": dt, "checked": checked,
+            "samples": {k: samples[k // world] for k in checked},
             "out": {"planner": "RT-RRT*", "instances": n_inst, "n_gpus": world, "sharding": "instance id mod n_gpus; records all-gathered (NCCL)" if world > 1 else "single GPU",
-                    "scaling": "strong", "ticks": ticks, "virtual_dt_ns": dt,
-                    "gpu_planner_ticks_per_s": n_inst * ticks / tot,
+                    "definition": "C5 (SURVEY 8(d)): 8 maps x 32 (start, goal) pairs x 32 seeds, every instance ticks until its 2000 samples are consumed",
+                    "scaling": "strong", "ticks": n_ticks, "virtual_dt_ns": dt, "sweep_s": tot,
+                    "gpu_planner_ticks_per_s": n_inst * n_ticks / tot,
                     "gpu_iters_per_s": float(rec[:, 2].sum() / tot), "gpu_queue_pops_per_s": float((rec[:, 3] + rec[:, 4]).sum() / tot),
                     "gpu_sweep_tick_ms_p50": float(np.median(lat) * 1e3), "gpu_status_max": int(rec[:, 5].max()),
+                    "samples_consumed_min": int(rec[:, 1].min()),
                     "nodes_mean": float(rec[:, 0].mean()), "paths_found": int((rec[:, 6] > 0).sum()),
                     "records_sha256": hashlib.sha256(rec.tobytes()).hexdigest()[:16]}}
 
 
 def measure_replanning(ctx, sweep):
-    """Replan iterations/s and tick latency: the sweep's engine numbers (measure_sweep, all ranks) against the CPU
-    oracle port of the same loops on all host threads over a sample of the same instances (same maps, start/goal,
-    injected sample streams; node counts and stream positions compared), plus the one-planner tick latency."""
+    """Replan iterations/s and tick latency: the sweep's engine numbers (measure_sweep, all ranks) against the CPU oracle port of
+    the same loops on all host threads over every 128th instance of the sweep (same maps, start / goal, injected sample streams,
+    the same number of ticks) — their TREES (coordinates, parents, cost bits, flags) are compared byte for byte with the
+    engine's — plus the one-planner tick latency."""
     from concurrent.futures import ThreadPoolExecutor
 
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import sweep_bench as sb
     from oracle import loader as orc
 
-    inst, maps, rec, ticks, dt, n_samples = sweep["inst"], sweep["maps"], sweep["records"], sweep["ticks"], sweep["dt"], sweep["n_samples"]
+    inst, maps, ticks, dt, n_samples = sweep["inst"], sweep["maps"], sweep["ticks"], sweep["dt"], sweep["n_samples"]
     out = {"replan": dict(sweep["out"])}
     threads = os.cpu_count() or 1
-    m = min(len(inst), 2 * threads)
-    samples = [sb.uniform_samples(orc, inst[k][4], n_samples, maps[inst[k][1]].shape[1], maps[inst[k][1]].shape[0]) for k in range(m)]
+    ks = sorted(sweep["checked"])
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
-        res = list(ex.map(lambda k: sb.run_cpu_instance(orc, maps[inst[k][1]], inst[k][2], inst[k][3], samples[k], ticks, dt), range(m)))
+        res = list(ex.map(lambda k: sb.run_cpu_instance(orc, maps[inst[k][1]], inst[k][2], inst[k][3], sweep["samples"][k], ticks, dt, want_tree=True), ks))
     wall = time.perf_counter() - t0
+    same = True
+    for k, (lat, c, tree) in zip(ks, res):
+        gpu_tree, gpu_used = sweep["checked"][k]
+        same &= c["samples_used"] == gpu_used and len(tree) == len(gpu_tree)
+        same &= all(np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8)) for a, b in zip(tree, gpu_tree))
     out["replan"].update({
         "cpu_iters_per_s": sum(r[1]["iters"] for r in res) / wall,
         "cpu_queue_pops_per_s": sum(r[1]["pops_r"] + r[1]["pops_s"] for r in res) / wall,
+        "cpu_planner_ticks_per_s": len(ks) * ticks / wall,
         "cpu_threads": threads, "cpu_kind": "port (oracle loops, grid k-NN; the reference rebuilds a kd-tree per insert)",
-        "cpu_sample": f"{m} of the {len(inst)} instances",
+        "cpu_sample": f"every 128th of the {len(inst)} instances ({len(ks)}), {ticks} ticks each",
         "cpu_single_thread_tick_ms_p50": float(np.median([x for r in res for x in r[0]]) * 1e3),
-        "trees_match_gpu": bool(all(res[k][1]["n_nodes"] == int(rec[k, 0]) and res[k][1]["samples_used"] == int(rec[k, 1])
-                                    and res[k][1]["iters"] == int(rec[k, 2]) for k in range(m)))})
+        "trees_match_gpu": bool(same), "trees_compared": len(ks)})
     lat1, st1, _ = sb.run_gpu(ctx, orc, inst[:1], maps, n_samples, 9, dt)
     out["replan"]["gpu_single_instance_tick_ms_p50"] = float(np.median(lat1) * 1e3)
     return out

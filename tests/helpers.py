@@ -51,14 +51,27 @@ def golden_cases():
                  dobs_ticks=(2, 5), move_ticks=(3,)),
             dict(name="game0", map="GAME0", agent=(350.0, 2350.0), goal=(1400.0, 2050.0), seed=3, n_rand=3_000_000, dt=2000, ticks=6,
                  dobs_ticks=(2,), move_ticks=()),
+            # the two largest bundled maps (2339 x 2338, 3318 x 3319: the longest edges and, on MAZE0, rows != columns)
+            dict(name="floor5", map="FLOOR5", agent=(1000.0, 1200.0), goal=(1920.0, 600.0), seed=21, n_rand=3_000_000, dt=5000, ticks=6,
+                 dobs_ticks=(1, 4), move_ticks=(2,)),
+            dict(name="maze0", map="MAZE0", agent=(1500.0, 1850.0), goal=(3100.0, 3100.0), seed=22, n_rand=3_000_000, dt=5000, ticks=6,
+                 dobs_ticks=(2,), move_ticks=(3,)),
         ],
         "rtfmt": [
             dict(name="mess6", map="MESS6", agent=(720.0, 720.0), goal=(70.0, 70.0), seed=7, n_rand=100_000, samples=2000, rounds=8,
                  dobs_rounds=(0, 4), move_rounds=(5,)),
+            dict(name="floor5", map="FLOOR5", agent=(1000.0, 1200.0), goal=(1460.0, 2100.0), seed=23, n_rand=100_000, samples=2000, rounds=6,
+                 dobs_rounds=(1, 3), move_rounds=(4,)),
+            dict(name="maze0", map="MAZE0", agent=(1500.0, 1850.0), goal=(200.0, 3100.0), seed=24, n_rand=100_000, samples=2000, rounds=6,
+                 dobs_rounds=(2,), move_rounds=(3,)),
         ],
         "amrrt": [
             dict(name="mess6", map="MESS6", agent=(720.0, 720.0), goal=(1240.0, 1240.0), seed=9, n_rand=3_000_000, dt=500000, ticks=25,
                  dobs_ticks=(0, 12), diffusion=synthetic_diffusion),
+            dict(name="floor5", map="FLOOR5", agent=(1000.0, 1200.0), goal=(1750.0, 900.0), seed=25, n_rand=3_000_000, dt=500000, ticks=16,
+                 dobs_ticks=(0, 8), diffusion=synthetic_diffusion),
+            dict(name="maze0", map="MAZE0", agent=(1500.0, 1850.0), goal=(3100.0, 200.0), seed=26, n_rand=3_000_000, dt=500000, ticks=16,
+                 dobs_ticks=(3,), diffusion=synthetic_diffusion),
         ],
     }
 

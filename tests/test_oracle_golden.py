@@ -16,7 +16,7 @@ def _bits(a, n):
     return np.unpackbits(a)[:n]
 
 
-@pytest.mark.parametrize("name", ["GAME0", "MESS6"])
+@pytest.mark.parametrize("name", ["GAME0", "MESS6", "FLOOR5", "MAZE0"])
 def test_edge_checks_match_reference(oracle, name):
     g = np.load(os.path.join(GOLD, f"edges_{name}.npz"))
     S = oracle.load_map(name)

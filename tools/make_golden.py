@@ -119,9 +119,13 @@ def amrrt_case(case):
 
 def main():
     O.build(ref=True)
-    for name in ("GAME0", "MESS6"):
-        edges_case(name)
+    only = set(sys.argv[1:])  # e.g. `make_golden.py floor5 maze0 FLOOR5 MAZE0`: regenerate just these cases / edge maps
+    for name in ("GAME0", "MESS6", "FLOOR5", "MAZE0"):
+        if not only or name in only:
+            edges_case(name)
     cases = golden_cases()
+    if only:
+        cases = {k: [c for c in v if c["name"] in only] for k, v in cases.items()}
     for c in cases["rtrrt"]:
         rtrrt_case(c)
     for c in cases["rtfmt"]:

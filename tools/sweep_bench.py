@@ -29,13 +29,45 @@ def make_instances(n_inst, maps):
     return inst
 
 
+def c5_pairs(name, S):
+    """The 32 (start, goal) pairs of a map for BASELINE configs[4]: 16 from the reference's scripted table —
+    ordered pairs of its start and four goals (RTRRT/test/testD.cpp:36-47) — and 16 seeded random pairs of free pixels."""
+    start, goals = SCEN[name]
+    pts = [start] + list(goals)
+    table = [(a, b) for a in pts for b in pts if a != b][:16]
+    rng = np.random.Generator(np.random.PCG64(sum(map(ord, name))))
+    free = np.argwhere(S == 0)
+    rnd = []
+    while len(rnd) < 16:
+        (ay, ax), (by, bx) = free[rng.integers(len(free))], free[rng.integers(len(free))]
+        if min(ax, ay, bx, by) > 2 and (ax, ay) != (bx, by):
+            rnd.append(((int(ax), int(ay)), (int(bx), int(by))))
+    return table + rnd
+
+
+def make_instances_c5(maps, n_seeds=32):
+    """8 maps x 32 (start, goal) pairs x n_seeds sample streams; instance id = ((seed * 32) + pair) * 8 + map, so that any
+    contiguous or strided subset mixes maps and pairs.  Entries as make_instances: (map slot, map, start, goal, rand seed)."""
+    names = list(maps)
+    pairs = {name: c5_pairs(name, maps[name]) for name in names}
+    inst = []
+    for seed in range(n_seeds):
+        for pr in range(32):
+            for slot, name in enumerate(names):
+                a, b = pairs[name][pr]
+                inst.append((slot, name, a, b, 5000 + (seed * 32 + pr) * len(names) + slot))
+    return inst
+
+
 def uniform_samples(orc, seed, n, W, H):
     """n points exactly as the reference's uniform branch draws them (p0 discarded, then x, y)."""
     r = orc.rand31(seed, 3 * n).astype(np.float32) / np.float32(2147483648.0)
     return np.stack([r[1::3] * np.float32(W), r[2::3] * np.float32(H)], 1).astype(np.float32)
 
 
-def run_gpu(ctx, orc, inst, maps, n_samples, ticks, dt, run_ms=50, cap=4096):
+def run_gpu(ctx, orc, inst, maps, n_samples, ticks, dt, run_ms=50, cap=4096, until_exhausted=False, keep=False):
+    """ticks replanning ticks of every instance; until_exhausted: tick until every instance has consumed its n_samples samples
+    (at most `ticks`).  keep: returns the live engine as a 4th value (the caller reads trees and closes it)."""
     import rtpp_b200
     W = max(m.shape[1] for m in maps.values()); H = max(m.shape[0] for m in maps.values())
     n = len(inst)
@@ -53,12 +85,17 @@ def run_gpu(ctx, orc, inst, maps, n_samples, ticks, dt, run_ms=50, cap=4096):
         eng.tick(update_tree=True, run_ms=run_ms, dt_ns=dt, get_path=True)
         ctx.sync()
         lat.append(time.perf_counter() - t0)
+        if until_exhausted and int(eng.stats()[:, 2].min()) >= n_samples:
+            break
     st = eng.stats()
+    if keep:
+        return lat, st, samples, eng
     eng.close()
     return lat, st, samples
 
 
-def run_cpu_instance(orc, S, start, goal, samples, ticks, dt, run_ms=50):
+def run_cpu_instance(orc, S, start, goal, samples, ticks, dt, run_ms=50, want_tree=False):
+    """The CPU oracle port of the same loop; `ticks` ticks exactly (the GPU run's count).  want_tree: also returns o.dump()."""
     o = orc.OrcRTRRT(S)
     o.set_clock(dt)
     o.set_agent(float(start[0]), float(start[1])); o.set_goal(float(goal[0]), float(goal[1]))
@@ -71,8 +108,9 @@ def run_cpu_instance(orc, S, start, goal, samples, ticks, dt, run_ms=50):
         o.get_path()
         lat.append(time.perf_counter() - t0)
     c = o.counters(); c["n_nodes"] = o.num_nodes(); c["samples_used"] = pos
+    tree = o.dump() if want_tree else None
     o.close()
-    return lat, c
+    return (lat, c, tree) if want_tree else (lat, c)
 
 
 def main():
