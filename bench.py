@@ -625,6 +625,10 @@ def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdi
         out["rtfmt_sweep"] = {"error": repr(exc)}
     out.update(measure_cdrt(ctx))
     out.update(measure_amrrt(ctx))
+    try:  # last: its edge batches load GAME0 into the ctx's planes (nothing after it uses the C4 planes)
+        out.update(measure_c1(ctx, torch, timed, peak or 6650.0))
+    except Exception as exc:  # an extra must not cost the bench line
+        out["c1_rtrrt_game0"] = {"error": repr(exc)}
     return out
 
 
@@ -780,53 +784,43 @@ def measure_amrrt(ctx, n_inst=1024, ticks=4, dt=20000, cap_rand=60_000):
 
 def measure_cdrt(ctx):
     """BASELINE configs[1]: CDRT-RRT* on bundled GAME0 with its four moving obstacles, continuous replanning on
-    virtual time (tools/cdrt_bench.py): tick latency of one planner and the throughput of 1024 planners (one warp
-    each) against the CPU port on the host threads; states compared bit for bit."""
+    virtual time (tools/cdrt_bench.py): tick latency of one planner over the scripted loop's 600 ticks (30 s at 20 Hz,
+    CDRT2/test/testD.cpp:197-241) and the throughput of 1024 planners (one warp each) against the CPU port on the host
+    threads; states compared bit for bit."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import cdrt_bench
     from oracle import loader as orc
 
-    return {"cdrt": {"single": cdrt_bench.single(ctx, orc), "sweep": cdrt_bench.sweep(ctx, orc, n_inst=1024, threads=os.cpu_count() or 1)}}
+    return {"cdrt": {"single": cdrt_bench.single(ctx, orc, ticks=600), "sweep": cdrt_bench.sweep(ctx, orc, n_inst=1024, threads=os.cpu_count() or 1)}}
 
 
-def measure_fmt(ctx, samples=100_000, iters=20_000):
-    """BASELINE configs[2]: RT-FMT on GAME0 with 1e5 free-space samples (the reference ships 2000).
-    GPU: rtpp_fmt_start (hash + static 25-NN table) and `iters` rounds of ExpandFMT + both rewires on
-    the engine; CPU: the oracle port of the same loops (1 thread: one planner instance is sequential)."""
-    import rtpp_b200
+def measure_fmt(ctx):
+    """BASELINE configs[2] at its stated size: RT-FMT on GAME0 with 1e5 free-space samples (the reference ships 2000), rounds of
+    ExpandFMT + both rewires until V_unv is exhausted (tools/config_runs.py c3_rtfmt); the CPU port (1 thread: one planner
+    instance is sequential) runs the first 40 000 rounds and its state is compared with the engine's after the same rounds
+    (the run to exhaustion is compared in tests/test_configs_gpu.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import config_runs as cr
     from oracle import loader as orc
 
-    S = orc.load_map("GAME0")
-    H, W = S.shape
-    o = orc.OrcRTFMT(S)
-    o.set_agent(360.0, 540.0)  # RTFMT/test/test.cpp:56
-    o.set_goal(2000.0, 400.0)
-    t0 = time.perf_counter()
-    o.start(orc.rand31(1, 3 * samples + 1000), samples)
-    cpu_start = time.perf_counter() - t0
-    xy = o.dump()[0]
-    eng = rtpp_b200.FmtEngine(ctx, 1, len(xy) + 32, 5, W, H)
-    eng.set_map(0, 1, S)
-    t0 = time.perf_counter()
-    eng.start(np.zeros(1, np.int32), [xy], np.array([[2000.0, 400.0]], np.float32))
-    ctx.sync()
-    gpu_start = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    eng.tick(update_tree=True, iters=iters, with_rewire=True, get_path=True)
-    ctx.sync()
-    gpu_s = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    o.update_tree()
-    o.expand(iters, True)
-    cpu_s = time.perf_counter() - t0
-    par, c, cl, st = eng.read_tree(0)
-    oxy, opar, oc, ocl, ost = o.dump()
-    same = bool(np.array_equal(par, opar) and np.array_equal(st, ost) and np.array_equal(c.view(np.uint32), oc.view(np.uint32)))
-    eng.close()
-    o.close()
-    return {"rtfmt_1e5": {"samples": samples, "rounds": iters, "gpu_start_ms": gpu_start * 1e3, "gpu_rounds_per_s": iters / gpu_s,
-                          "cpu_start_ms": cpu_start * 1e3, "cpu_rounds_per_s": iters / cpu_s, "cpu_kind": "port, 1 thread",
-                          "state_matches_cpu": same}}
+    return {"rtfmt_1e5": cr.c3_rtfmt(ctx, orc, check_rounds=40_000)}
+
+
+def measure_c1(ctx, torch, timed, peak):
+    """BASELINE configs[0] at its stated size: RT-RRT* on GAME0 with 20 000 injected samples (tree compared with
+    the CPU port after the first 3000 ticks; the full run is compared in tests/test_configs_gpu.py), then the 2^24 (node, one of
+    its 25-NN) edge batch and the 2^20 long-edge batch through rtpp_edges_check_dev (E1: divisor 5, S|D), each with its own
+    roofline by SURVEY 8(d)'s formula and every 16th verdict compared with the CPU oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import config_runs as cr
+    from oracle import loader as orc
+
+    out, tree, S = cr.c1_rtrrt(ctx, orc, check_ticks=3000)
+    batches = cr.c1_edge_batches(ctx, orc, tree[0], S, check=16, timed=lambda fn: timed(fn, 10))
+    for r in batches.values():
+        r["roofline_frac"] = r["algorithmic_GBs"] / peak
+    out["edge_batches"] = batches
+    return {"c1_rtrrt_game0": out}
 
 
 def measure_fmt_sweep(ctx, n_inst=512, samples=2000, iters=2000, cpu_inst=16):

@@ -263,6 +263,11 @@ RTPP_API int rtpp_engine_draw_dynamic(rtpp_engine *e, int slot, const int32_t *c
 RTPP_API int rtpp_engine_init_instances(rtpp_engine *e, const int32_t *map_slot, const float *agent_xy, const float *goal_xy);
 RTPP_API int rtpp_engine_set_inputs(rtpp_engine *e, const float *agent_xy, const float *goal_xy, const float *samples_xy,
                                     const int32_t *n_samples);
+/* RT-RRT* (planner_kind 1): the rand() stream of the next tick(s), n_inst rows of max_samples raw rand() values (n_rand[i] valid);
+ * the engine then draws its samples ON THE DEVICE — SamplePoint RTRRT.cpp:234-262, uniform or the informed ellipse of the last
+ * GetPath's c_base, with glibc's atan2f / cosf / sinf bits (csrc/glibc_math.cuh) — instead of taking the injected points of
+ * rtpp_engine_set_inputs.  rand == NULL switches back.  Stats slot 14 = draws consumed, 15 = the stream ran out. */
+RTPP_API int rtpp_engine_set_rand(rtpp_engine *e, const int32_t *rand, const int32_t *n_rand);
 RTPP_API int rtpp_engine_tick(rtpp_engine *e, int do_update_tree, long run_ms, long long dt_ns, int do_get_path);
 /* planner_kind 2 = AM-RRT* (divisor 2): the tick runs UpdateTree AMRRT.cpp:156-200, then the MainTask loop
  * AMRRT.cpp:598-613 = { Expand :395-481 (sampler, Steer :354-390 with CrashDetectionStart :287-308 and
@@ -365,6 +370,16 @@ RTPP_API int rtpp_cdrt_read_tree(rtpp_cdrt_engine *e, int inst, int max_nodes, d
 RTPP_API int rtpp_cdrt_read_path(rtpp_cdrt_engine *e, int inst, int max_len, double *xy, int *len_out);
 /* obsKdtreeMap: per free polygon, whether it holds a kd-tree and how many points */
 RTPP_API int rtpp_cdrt_read_islands(rtpp_cdrt_engine *e, int inst, int32_t *has_tree, int32_t *count);
+
+/* --- glibc's binary32 transcendentals on the device (csrc/glibc_math.cuh) ---
+ * The informed-ellipse samplers (RTRRT.cpp:241-262, AMRRT.cpp:415-432) call glibc's sinf / cosf / atan2f / sqrtf; a device sampler
+ * must return the same bits.  rtpp_glibc_host_fma: 1 when the running host's libm uses its fused-multiply-add build of sinf / cosf
+ * (the two builds differ on 12 of the 2^32 arguments); the engines follow the host they run next to.
+ * rtpp_glibc_checksum: sum over the binary32 bit patterns b in [first, first + count) of canon(f(b)) * (2b + 1) mod 2^64 (NaNs
+ * canonicalised), fn 0 sinf, 1 cosf, 2 atanf; rtpp_glibc_eval: out[i] = f(in[i]); fn 3 = atan2f(in[2i], in[2i+1]).  Test hooks. */
+RTPP_API int rtpp_glibc_host_fma(void);
+RTPP_API int rtpp_glibc_checksum(rtpp_ctx *ctx, int fn, int fma, uint32_t first_bits, unsigned long long count, unsigned long long *out);
+RTPP_API int rtpp_glibc_eval(rtpp_ctx *ctx, int fn, int fma, const float *in, size_t n, float *out);
 
 #ifdef __cplusplus
 }

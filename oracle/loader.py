@@ -684,3 +684,24 @@ class CdrtCpu:
 
     def error(self):
         return self.L.orc_cdrt_error(self.h) if self.impl == "oracle" else 0
+
+
+# ------------------------------------------------------------------ glibc transcendentals ---------
+def glibc_host_fma():
+    """1 when this host's libm runs its fused-multiply-add build of sinf / cosf."""
+    return int(lib().orc_glibc_host_fma())
+
+
+def glibc_checksum(impl, fn, first, count, nthreads=1):
+    """Checksum of fn (0 sinf, 1 cosf, 2 atanf) over the binary32 bit patterns [first, first + count): impl 0 = the host's libm,
+    1 / 2 = rtpp_b200/csrc/glibc_math.cuh compiled for the host without / with fused operations."""
+    L = lib()
+    L.orc_glibc_checksum.restype = C.c_ulonglong
+    return int(L.orc_glibc_checksum(int(impl), int(fn), C.c_uint32(first & 0xFFFFFFFF), C.c_ulonglong(count), int(nthreads)))
+
+
+def glibc_atan2f(impl, yx):
+    yx = _c(yx, np.float32).reshape(-1, 2)
+    out = np.zeros(len(yx), np.float32)
+    lib().orc_glibc_atan2f(int(impl), _ptr(yx), C.c_longlong(len(yx)), _ptr(out))
+    return out

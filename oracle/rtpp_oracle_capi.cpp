@@ -6,6 +6,8 @@
 #include "pool.hpp"
 #include <cstring>
 #include <thread>
+#include <atomic>
+#include <mutex>
 
 using namespace orc;
 #define ORC_EXPORT extern "C" __attribute__((visibility("default")))
@@ -416,4 +418,62 @@ ORC_EXPORT int orc_amrrt_get_path(void *h, float *out_xy, int cap, int *collisio
         n++;
     }
     return n;
+}
+
+// ---------------------------------------------------------------- glibc transcendentals ---------
+// Checker for rtpp_b200/csrc/glibc_math.cuh (the restatement of glibc's sinf / cosf / atanf / atan2f that the device samplers
+// use): the same checksum computed with the host's own libm and with the header's host instantiation.
+#include <math.h>
+#include "../rtpp_b200/csrc/glibc_math.cuh"
+static inline uint32_t orc_canon(float r) {
+    uint32_t b;
+    memcpy(&b, &r, 4);
+    return r != r ? 0x7fc00000u : b;
+}
+template <class F> static unsigned long long orc_checksum(uint32_t first, unsigned long long count, int nthreads, F f) {
+    std::vector<unsigned long long> part((size_t)std::max(nthreads, 1) * 64 + 64, 0);
+    std::atomic<int> slot{0};
+    par_for((long long)count, nthreads, [&](long long a, long long b) {
+        unsigned long long acc = 0;
+        for (long long i = a; i < b; i++) {
+            const uint32_t bits = first + (uint32_t)i;
+            float x;
+            memcpy(&x, &bits, 4);
+            acc += (unsigned long long)orc_canon(f(x)) * (2ull * bits + 1ull);
+        }
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        part[0] += acc;
+    });
+    (void)slot;
+    return part[0];
+}
+ORC_EXPORT int orc_glibc_host_fma(void) {
+    volatile float x;
+    const uint32_t xb = 0x4255b0a9u;
+    memcpy((void *)&x, &xb, 4);
+    const float r = sinf(x);
+    uint32_t rb;
+    memcpy(&rb, &r, 4);
+    return rb == 0xbc7d08a9u ? 1 : 0;
+}
+// fn: 0 sinf, 1 cosf, 2 atanf.  impl: 0 = the host's libm, 1 = glibc_math.cuh without fused operations, 2 = with
+ORC_EXPORT unsigned long long orc_glibc_checksum(int impl, int fn, uint32_t first, unsigned long long count, int nthreads) {
+    namespace gm = glibc_math;
+    if (impl == 0) {
+        if (fn == 0) return orc_checksum(first, count, nthreads, [](float x) { return sinf(x); });
+        if (fn == 1) return orc_checksum(first, count, nthreads, [](float x) { return cosf(x); });
+        return orc_checksum(first, count, nthreads, [](float x) { return atanf(x); });
+    }
+    if (fn == 2) return orc_checksum(first, count, nthreads, [](float x) { return gm::atanf_(x); });
+    if (impl == 2) {
+        if (fn == 0) return orc_checksum(first, count, nthreads, [](float x) { return gm::sinf_<true>(x); });
+        return orc_checksum(first, count, nthreads, [](float x) { return gm::cosf_<true>(x); });
+    }
+    if (fn == 0) return orc_checksum(first, count, nthreads, [](float x) { return gm::sinf_<false>(x); });
+    return orc_checksum(first, count, nthreads, [](float x) { return gm::cosf_<false>(x); });
+}
+// out[i] = atan2f(yx[2i], yx[2i+1]): impl 0 = libm, 1 = glibc_math.cuh
+ORC_EXPORT void orc_glibc_atan2f(int impl, const float *yx, long long n, float *out) {
+    for (long long i = 0; i < n; i++) out[i] = impl ? glibc_math::atan2f_(yx[2 * i], yx[2 * i + 1]) : atan2f(yx[2 * i], yx[2 * i + 1]);
 }

@@ -320,6 +320,14 @@ class Engine:
         ns = None if n_samples is None else _c(n_samples, np.int32)
         self._ck(self.L.rtpp_engine_set_inputs(self.h, _p(a), _p(g), _p(sm), _p(ns)))
 
+    def set_rand(self, rand=None, n_rand=None):
+        """RT-RRT*: the rand() stream of the next tick(s); the engine draws its samples on the device.  None switches back."""
+        if rand is None:
+            self._ck(self.L.rtpp_engine_set_rand(self.h, None, None))
+            return
+        r = _c(rand, np.int32).reshape(self.n, self.max_samples)
+        self._ck(self.L.rtpp_engine_set_rand(self.h, _p(r), _p(_c(n_rand, np.int32))))
+
     def tick(self, update_tree=True, run_ms=50, dt_ns=100000, get_path=False):
         self._ck(self.L.rtpp_engine_tick(self.h, int(update_tree), C.c_long(run_ms), C.c_longlong(dt_ns), int(get_path)))
 

@@ -26,6 +26,8 @@
 int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t *circles, int n_circles, const int32_t *poly_xy,
                      const int32_t *poly_sizes, int n_polys); // raster.cu
 
+#include "glibc_math.cuh"
+
 #define FULL 0xffffffffu
 
 struct EngInst {
@@ -47,6 +49,7 @@ struct EngInst {
     int goal_node;                          // id of the tree node that IS the goal point (Node_Map.find(goal), AMRRT.cpp:606), -1 = none
     int gs_top, gq_head, gq_tail, g_epoch;  // RewireGoal: Sgoal (stack), Qgoal (FIFO), seen_goal (epoch marks)
     float ell_a, ell_b, ell_cos, ell_sin, ell_mx, ell_my;
+    int ell_host; // 1: the caller supplied the ellipse for the next tick (rtpp_engine_set_am_inputs), 0: computed on the device
 };
 
 struct EngView {
@@ -67,10 +70,11 @@ struct EngView {
     PlaneView planes[16]; // merged S|D plane per map slot
     int divisor;
     int kind; // 1 RT-RRT*, 2 AM-RRT*
-    // AM-RRT*: rand stream with host-tabulated cosf/sinf of the angle each draw would produce, and
-    // the diffusion-map table (AMRRT.cpp:58-116)
+    // injected rand() stream (AM-RRT*: always; RT-RRT*: when set with rtpp_engine_set_rand, the samples are then drawn on the
+    // device), the libm build whose sinf / cosf bits the samplers reproduce (glibc_math.cuh), and AM-RRT*'s diffusion-map table
+    // (AMRRT.cpp:58-116)
     const int *rand_stream;
-    const float2 *rand_cs;
+    int glibc_fma;
     int rand_cap;
     const int *diff_cell; // [diff_gw * diff_gh] row index or -1
     const float *diff_rows;
@@ -86,7 +90,6 @@ struct rtpp_engine {
     size_t plane_words[16];
     MarchThresholds mt;
     int *d_rand = nullptr, *d_diff_cell = nullptr;
-    float2 *d_rand_cs = nullptr;
     float *d_diff_rows = nullptr;
 };
 
@@ -103,8 +106,8 @@ struct Inst {
     const float2 *samples;
     int *path;
     PlaneView pl;
-    const int *rand_stream; // AM-RRT*
-    const float2 *rand_cs;
+    const int *rand_stream; // injected rand() values of this instance (nullptr: RT-RRT* with injected samples)
+    int glibc_fma;
 };
 
 __device__ __forceinline__ GridView inst_grid(const EngView &ev, const Inst &in) {
@@ -437,12 +440,85 @@ __device__ __forceinline__ bool relax_neighbours(const EngView &ev, Inst &in, co
     return improved;
 }
 
+// glibc's cosf / sinf of one angle, in the build (fused or not) of the libm the host runs (glibc_math.cuh)
+__device__ __forceinline__ float2 glibc_cos_sin(float th, int fma) {
+    return fma ? make_float2(glibc_math::cosf_<true>(th), glibc_math::sinf_<true>(th)) : make_float2(glibc_math::cosf_<false>(th), glibc_math::sinf_<false>(th));
+}
+// "random_theta = rand() / float(RAND_MAX) * 2 * 3.141592954f" (RTRRT.cpp:248, AMRRT.cpp:423): (cosf, sinf) of it for raw draw r
+__device__ __forceinline__ float2 theta_cos_sin(int r, int fma) {
+    const float u = __fdiv_rn((float)r, 2147483648.0f);
+    return glibc_cos_sin(__fmul_rn(__fmul_rn(u, 2.0f), 3.141592954f), fma);
+}
+// the informed sampler's ellipse (RTRRT.cpp:243-246, AMRRT.cpp:418-421) from c_base, root and goal: binary32 throughout, glibc's
+// atan2f / cosf / sinf.  {a, b, cos(angle), sin(angle), mid.x, mid.y}
+__device__ __forceinline__ void informed_ellipse(Inst &in) {
+    const float2 root = in.xy[in.s.root], goal = in.s.goal;
+    const float c_min = rt_dist(goal.x, goal.y, root.x, root.y), cb = in.s.c_base;
+    in.s.ell_a = __fdiv_rn(cb, 2.0f);
+    in.s.ell_b = __fdiv_rn(__fsqrt_rn(__fsub_rn(__fmul_rn(cb, cb), __fmul_rn(c_min, c_min))), 2.0f);
+    const float angle = glibc_math::atan2f_(__fsub_rn(goal.y, root.y), __fsub_rn(goal.x, root.x));
+    const float2 cs = glibc_cos_sin(angle, in.glibc_fma);
+    in.s.ell_cos = cs.x, in.s.ell_sin = cs.y;
+    in.s.ell_mx = __fdiv_rn(__fadd_rn(goal.x, root.x), 2.0f), in.s.ell_my = __fdiv_rn(__fadd_rn(goal.y, root.y), 2.0f);
+}
+
+// SamplePoint of RT-RRT* (RTRRT.cpp:234-262) from the injected rand() stream, on the device: one draw decides between the uniform
+// sample and the informed ellipse around (root, goal) of the path cost c_base the last GetPath found; glibc's atan2f / cosf / sinf
+// bits (glibc_math.cuh).  Defined behaviour where the reference loops forever (c_base < |goal - root|: b = sqrt(negative)):
+// uniform, as the oracle and the CPU planners do.  Returns false when the stream ran out inside the sample (the position is
+// restored: the caller refills the stream from there).
+__device__ bool rt_sample_point(Inst &in, float2 &out) {
+    const int pos0 = in.s.rand_pos;
+    const float W = (float)in.pl.W, H = (float)in.pl.H;
+    auto u = [&]() -> float {
+        if (in.s.rand_pos >= in.s.rand_n) {
+            in.s.rand_exhausted = 1;
+            return 0.0f;
+        }
+        return __fdiv_rn((float)in.rand_stream[in.s.rand_pos++], 2147483648.0f);
+    };
+    const float p0 = u();
+    const float2 root = in.xy[in.s.root], goal = in.s.goal;
+    const float cb = in.s.c_base, c_min = rt_dist(goal.x, goal.y, root.x, root.y);
+    float rx, ry;
+    if (p0 < 0.1f || cb < 0.0f || cb < c_min) {
+        rx = __fmul_rn(u(), W);
+        ry = __fmul_rn(u(), H);
+    } else {
+        informed_ellipse(in);
+        for (int guard = 0;; guard++) {
+            const int r_th = in.s.rand_pos < in.s.rand_n ? in.rand_stream[in.s.rand_pos] : 0;
+            u();
+            const float2 cs = theta_cos_sin(r_th, in.glibc_fma);
+            const float rr = __fsqrt_rn(u());
+            const float x = __fmul_rn(__fmul_rn(in.s.ell_a, cs.x), rr), y = __fmul_rn(__fmul_rn(in.s.ell_b, cs.y), rr);
+            rx = __fadd_rn(__fsub_rn(__fmul_rn(in.s.ell_cos, x), __fmul_rn(in.s.ell_sin, y)), in.s.ell_mx);
+            ry = __fadd_rn(__fadd_rn(__fmul_rn(in.s.ell_sin, x), __fmul_rn(in.s.ell_cos, y)), in.s.ell_my);
+            if (rx >= 0.0f && rx < W && ry >= 0.0f && ry < H) break;
+            if (in.s.rand_exhausted || guard >= 100000) break;
+        }
+    }
+    if (in.s.rand_exhausted) {
+        in.s.rand_pos = pos0;
+        return false;
+    }
+    out = make_float2(rx, ry);
+    return true;
+}
+
 __device__ void expand_rewiring(const EngView &ev, Inst &in, const MarchThresholds &mt, long long run_ns, long long dt) {
     const int lane = threadIdx.x & 31;
     const long long t0 = clk_now(in, dt);
     while (clk_now(in, dt) - t0 < run_ns) {
-        if (in.s.samp_pos >= in.s.samp_n || in.s.status) break;
-        const float2 p = in.samples[in.s.samp_pos++];
+        if (in.s.status) break;
+        float2 p;
+        if (in.rand_stream) { // samples drawn here from the injected rand() stream (rtpp_engine_set_rand)
+            if (in.s.rand_exhausted || !rt_sample_point(in, p)) break;
+            in.s.samp_pos++;
+        } else { // samples injected by the caller (rtpp_engine_set_inputs)
+            if (in.s.samp_pos >= in.s.samp_n) break;
+            p = in.samples[in.s.samp_pos++];
+        }
         expand_one(ev, in, mt, p);
         // rewire from the random queue
         while (in.s.qr_tail != in.s.qr_head && (clk_now(in, dt) - t0 < run_ns)) {
@@ -565,13 +641,12 @@ __device__ __forceinline__ int am_rand(Inst &in) { // orc::RandStream::next
     return in.rand_stream[in.s.rand_pos++];
 }
 __device__ __forceinline__ float am_u(Inst &in) { return __fdiv_rn((float)am_rand(in), 2147483648.0f); }
-// u and the tabulated (cosf, sinf) of theta = u*2*3.141592954f for the same draw
-__device__ __forceinline__ float am_u_cs(Inst &in, float2 &cs) {
+// draws theta and returns the (cosf, sinf) of it
+__device__ __forceinline__ float2 am_theta(Inst &in) {
     const int pos = in.s.rand_pos;
-    cs = pos < in.s.rand_n ? in.rand_cs[pos] : make_float2(1.0f, 0.0f);
-    return am_u(in);
+    const int r = am_rand(in);
+    return pos < in.s.rand_n ? theta_cos_sin(r, in.glibc_fma) : make_float2(1.0f, 0.0f);
 }
-
 // DiffusivityMetric (AMRRT.cpp:94-116)
 __device__ float am_diffusivity(const EngView &ev, float ax, float ay, float bx, float by) {
     const int is = __float2int_rz(__fmul_rn(ax, ev.diff_ratio)), js = __float2int_rz(__fmul_rn(ay, ev.diff_ratio));
@@ -650,7 +725,7 @@ __device__ float2 am_steer(const EngView &ev, Inst &in, const MarchThresholds &m
             const int pos = in.s.rand_pos + 2 * k;
             float2 cs = make_float2(1.0f, 0.0f);
             float rr = 0.0f;
-            if (pos < in.s.rand_n) cs = in.rand_cs[pos];
+            if (pos < in.s.rand_n) cs = theta_cos_sin(in.rand_stream[pos], in.glibc_fma);
             if (pos + 1 < in.s.rand_n) rr = __fdiv_rn((float)in.rand_stream[pos + 1], 2147483648.0f);
             rr = __fmul_rn(__fsqrt_rn(rr), r_sam);
             cand = make_float2(__fadd_rn(__fmul_rn(cs.x, rr), xi.x), __fadd_rn(__fmul_rn(cs.y, rr), xi.y));
@@ -695,8 +770,7 @@ __device__ void am_expand(const EngView &ev, Inst &in, const MarchThresholds &mt
                 break;
             }
         } else if (in.s.goal.x >= 0.0f) {
-            float2 cs;
-            am_u_cs(in, cs); // theta draw: only its cosf/sinf are needed
+            const float2 cs = am_theta(in); // theta draw: only its cosf/sinf are needed
             const float rr = __fsqrt_rn(am_u(in));
             const float x = __fmul_rn(__fmul_rn(in.s.ell_a, cs.x), rr), y = __fmul_rn(__fmul_rn(in.s.ell_b, cs.y), rr);
             float rx = __fsub_rn(__fmul_rn(in.s.ell_cos, x), __fmul_rn(in.s.ell_sin, y));
@@ -867,6 +941,9 @@ __device__ void am_main_loop(const EngView &ev, Inst &in, const MarchThresholds 
             }
         in.s.goal_node = __reduce_max_sync(FULL, hit);
     }
+    // the informed sampler's constants for this MainTask (AMRRT.cpp:418-421), from the root UpdateTree has just chosen
+    if (!in.s.ell_host) informed_ellipse(in);
+    in.s.ell_host = 0;
     const long long t0 = clk_now(in, dt);
     while (clk_now(in, dt) - t0 < 80000000LL && !in.s.rand_exhausted && !in.s.status) {
         am_expand(ev, in, mt, dt);
@@ -942,7 +1019,7 @@ __device__ __forceinline__ bool load_inst(const EngView &ev, int w, Inst &in) {
     in.pl = ev.planes[in.s.map_slot & 15];
     in.pl_epoch = ev.plane_epoch[in.s.map_slot & 15];
     in.rand_stream = ev.rand_stream ? ev.rand_stream + (size_t)w * ev.rand_cap : nullptr;
-    in.rand_cs = ev.rand_cs ? ev.rand_cs + (size_t)w * ev.rand_cap : nullptr;
+    in.glibc_fma = ev.glibc_fma;
     return true;
 }
 
@@ -1046,6 +1123,7 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
     v.shift = cell_log2;
     v.gw = ((domain_w - 1) >> cell_log2) + 1, v.gh = ((domain_h - 1) >> cell_log2) + 1, v.ncells = v.gw * v.gh;
     v.kind = planner_kind;
+    v.glibc_fma = rtpp_glibc_host_fma();
     v.divisor = planner_kind == 2 ? 2 : 5; // AMRRT.cpp:273 vs RTRRT.cpp:209
     rtpp_march_thresholds(v.divisor, &e->mt);
     const size_t N = (size_t)n_instances, C = N * node_capacity, G = N * (v.ncells + 1);
@@ -1072,8 +1150,7 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
     if (planner_kind == 2) { // max_samples = rand() draws available per instance and call
         v.rand_cap = max_samples;
         rc |= eng_alloc(e, &e->d_rand, N * max_samples);
-        rc |= eng_alloc(e, &e->d_rand_cs, N * max_samples);
-        v.rand_stream = e->d_rand, v.rand_cs = e->d_rand_cs;
+        v.rand_stream = e->d_rand;
     }
     rc |= eng_alloc(e, &v.path, N * v.path_cap);
     if (rc) return RTPP_ERR_NOMEM;
@@ -1090,7 +1167,7 @@ int rtpp_engine_destroy(rtpp_engine *e) {
     cudaFree(v.child_start), cudaFree(v.children), cudaFree(v.frontier), cudaFree(v.samples), cudaFree(v.path);
     cudaFree(v.nn_ids), cudaFree(v.nn_n), cudaFree(v.nn_blk), cudaFree(v.nn_blk_ep), cudaFree(v.gs), cudaFree(v.gq), cudaFree(v.g_mark);
     for (int i = 0; i < 16; i++) cudaFree(e->plane_s[i]), cudaFree(e->plane_d[i]), cudaFree(e->plane_sd[i]);
-    cudaFree(e->d_rand), cudaFree(e->d_rand_cs), cudaFree(e->d_diff_cell), cudaFree(e->d_diff_rows);
+    cudaFree(e->d_rand), cudaFree(e->d_diff_cell), cudaFree(e->d_diff_rows);
     delete e;
     return RTPP_OK;
 }
@@ -1225,18 +1302,46 @@ __global__ void engine_set_am_kernel(EngView ev, const int *__restrict__ n_rand,
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= ev.n_inst) return;
     EngInst &s = ev.inst[w];
-    if (n_rand) s.rand_n = n_rand[w], s.rand_pos = 0, s.rand_exhausted = 0;
+    if (n_rand) s.rand_n = n_rand[w], s.rand_pos = 0, s.rand_exhausted = 0, s.samp_pos = 0; // samp_pos: samples drawn from this stream (RT-RRT*)
     if (ell) {
         const float *p = ell + 6 * w;
         s.ell_a = p[0], s.ell_b = p[1], s.ell_cos = p[2], s.ell_sin = p[3], s.ell_mx = p[4], s.ell_my = p[5];
+        s.ell_host = 1;
     }
     if (outpath) s.outpath_nonempty = outpath[w];
 }
 
-// AM-RRT* per-call inputs.  rand: n_inst rows of rand capacity raw rand() values (n_rand[i] valid);
-// the (cosf, sinf) table of theta = u*2*3.141592954f is computed here on the host with glibc.
-// ellipse: 6 floats per instance {a, b, cos(angle), sin(angle), (goal.x+root.x)/2, (goal.y+root.y)/2}
-// of the informed sampler (AMRRT.cpp:418-432), computed by the caller after UpdateTree;
+// RT-RRT*: hands the engine the rand() stream of the next tick(s) — n_inst rows of max_samples raw rand() values, n_rand[i] valid —
+// and switches it to drawing its samples on the device (SamplePoint, RTRRT.cpp:234-262) instead of taking injected sample points;
+// rand == NULL switches back.  rtpp_engine_read_stats reports the draws consumed (slot 14) and whether the stream ran out (15).
+int rtpp_engine_set_rand(rtpp_engine *e, const int32_t *rand, const int32_t *n_rand) {
+    if (!e || e->v.kind != 1) return RTPP_ERR_INVALID;
+    rtpp_ctx *ctx = e->ctx;
+    const int n = e->v.n_inst, cap = e->v.max_samples;
+    if (!rand) {
+        e->v.rand_stream = nullptr;
+        return RTPP_OK;
+    }
+    if (!n_rand) return RTPP_ERR_INVALID;
+    for (int w = 0; w < n; w++)
+        if (n_rand[w] < 0 || n_rand[w] > cap) RTPP_FAIL(ctx, RTPP_ERR_CAPACITY, "more rand draws than the engine's capacity");
+    if (!e->d_rand && eng_alloc(e, &e->d_rand, (size_t)n * cap)) return RTPP_ERR_NOMEM;
+    e->v.rand_stream = e->d_rand, e->v.rand_cap = cap;
+    ENG_CK(e, cudaMemcpyAsync(e->d_rand, rand, (size_t)n * cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+    void *dn;
+    int rc = upload(e, 0, n_rand, (size_t)n * 4, &dn);
+    if (rc) return rc;
+    engine_set_am_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(e->v, (const int *)dn, nullptr, nullptr);
+    RTPP_LAUNCHED(ctx);
+    ENG_CK(e, cudaStreamSynchronize(ctx->stream));
+    return RTPP_OK;
+}
+
+// AM-RRT* per-call inputs.  rand: n_inst rows of rand capacity raw rand() values (n_rand[i] valid); cosf / sinf of the angles
+// they stand for are evaluated on the device with glibc's bits (glibc_math.cuh).
+// ellipse: NULL = the informed sampler's constants (AMRRT.cpp:418-432) are computed on the device from c_base, the root and the
+// goal at the start of the next tick's MainTask loop; or 6 floats per instance {a, b, cos(angle), sin(angle), (goal.x+root.x)/2,
+// (goal.y+root.y)/2} computed by the caller after UpdateTree, used for the next tick only.
 // outpath_nonempty: OutPath.size() != 0 (AMRRT.cpp:402,404).  Any pointer may be NULL = unchanged.
 int rtpp_engine_set_am_inputs(rtpp_engine *e, const int32_t *rand, const int32_t *n_rand, const float *ellipse,
                               const int32_t *outpath_nonempty) {
@@ -1245,18 +1350,9 @@ int rtpp_engine_set_am_inputs(rtpp_engine *e, const int32_t *rand, const int32_t
     const int n = e->v.n_inst, cap = e->v.rand_cap;
     if (rand) {
         if (!n_rand) return RTPP_ERR_INVALID;
-        std::vector<float2> cs((size_t)n * cap);
-        for (int w = 0; w < n; w++) {
+        for (int w = 0; w < n; w++)
             if (n_rand[w] < 0 || n_rand[w] > cap) RTPP_FAIL(ctx, RTPP_ERR_CAPACITY, "more rand draws than the engine's capacity");
-            for (int i = 0; i < n_rand[w]; i++) {
-                volatile float u = (float)rand[(size_t)w * cap + i] / 2147483648.0f;
-                volatile float t2 = u * 2;
-                const float th = t2 * 3.141592954f;
-                cs[(size_t)w * cap + i] = make_float2(cosf(th), sinf(th));
-            }
-        }
         ENG_CK(e, cudaMemcpyAsync(e->d_rand, rand, (size_t)n * cap * 4, cudaMemcpyHostToDevice, ctx->stream));
-        ENG_CK(e, cudaMemcpyAsync(e->d_rand_cs, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         ENG_CK(e, cudaStreamSynchronize(ctx->stream));
     }
     void *dn, *de, *dout;

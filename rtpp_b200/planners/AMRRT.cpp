@@ -185,14 +185,7 @@ void AMRRTplanner::MainTask(void) {
     if (!started_) return;
     if (auto_draw_) DrawDObsmap();
     UpdateTree();
-    // informed-sampler constants (AMRRT.cpp:418-432); NaN b (c_base < c_min) behaves as in the reference
-    const float c_min = goal % root;
-    float ell[6];
-    ell[0] = c_base / 2.0f;
-    ell[1] = sqrtf(c_base * c_base - c_min * c_min) / 2.0f;
-    const float angle = atan2f(goal.y - root.y, goal.x - root.x);
-    ell[2] = cosf(angle), ell[3] = sinf(angle);
-    ell[4] = (goal.x + root.x) / 2, ell[5] = (goal.y + root.y) / 2;
+    // the informed sampler's constants (AMRRT.cpp:418-432) are computed on the device from c_base, the new root and the goal
     std::vector<int32_t> r(rand_capacity_);
     int32_t n = rand_capacity_;
     if (rand_stream_) {
@@ -201,7 +194,7 @@ void AMRRTplanner::MainTask(void) {
     } else
         for (int i = 0; i < n; i++) r[i] = rand();
     const int32_t outpath = OutPath.size() != 0;
-    int rc = rtpp_engine_set_am_inputs(eng_, r.data(), &n, ell, &outpath);
+    int rc = rtpp_engine_set_am_inputs(eng_, r.data(), &n, nullptr, &outpath);
     if (!rc) rc = rtpp_engine_tick(eng_, 0, 80, dt_ns_, 0);
     long long st[16] = {0};
     if (!rc) rc = rtpp_engine_read_stats(eng_, st);

@@ -1,6 +1,6 @@
 // AMRRT.h — drop-in AM-RRT* planner class over the B200 engine (planner_kind 2), host side, C++.
 // Mirrors AMRRTplanner (reference AMRRT/lib/AMrrt/AMRRT.h:126-183).  MainTask runs UpdateTree on the
-// device, computes the informed-sampler ellipse on the host (glibc atan2f/cosf/sinf, needs the root),
+// device; the informed-sampler ellipse and the cosf / sinf of the drawn angles are evaluated on the device too (csrc/glibc_math.cuh),
 // then runs the Expand / RewireRoot loop on the device with rand() drawn from a host-filled stream.
 // Expand / RewireRoot / RewireGoal / Steer are not individually callable: they live inside MainTask.
 #ifndef RTPP_B200_AMRRT_H

@@ -199,59 +199,23 @@ void RTRRTplanner::UpdateTree(void) {
     }
 }
 
-int RTRRTplanner::NextRand() {
-    if (rand_stream_) return rand_pos_ < rand_n_ ? rand_stream_[rand_pos_++] : 0;
-    return rand();
-}
-
-// reference RTRRT.cpp:234-262 (host-only: glibc sinf/cosf/atan2f/sqrtf).  The float overloads of
-// sqrt/atan2 are what the reference's translation unit resolves to (CGAL/double.h:26 pulls <math.h>).
-// Guard: a degenerate ellipse (c_base < |goal-root|, reference loops forever) samples uniformly.
-RTpoint RTRRTplanner::SamplePoint() {
-    const float p0 = NextRand() / (float(RAND_MAX));
-    float rx, ry;
-    const bool degenerate = c_base >= 0 && c_base < (goal % root);
-    if (p0 < 0.1f || c_base < 0 || degenerate) {
-        rx = NextRand() / (float(RAND_MAX)) * shapeX;
-        ry = NextRand() / (float(RAND_MAX)) * shapeY;
-    } else {
-        const float c_min = goal % root;
-        const float a = c_base / 2.0f;
-        const float b = sqrtf(c_base * c_base - c_min * c_min) / 2.0f;
-        const float angle = atan2f(goal.y - root.y, goal.x - root.x);
-        for (int guard = 0;; guard++) {
-            const float th = NextRand() / (float(RAND_MAX)) * 2 * 3.141592954f;
-            const float rr = sqrtf(NextRand() / (float(RAND_MAX)));
-            const float x = a * cosf(th) * rr, y = b * sinf(th) * rr;
-            rx = cosf(angle) * x - sinf(angle) * y;
-            ry = sinf(angle) * x + cosf(angle) * y;
-            rx = rx + (goal.x + root.x) / 2;
-            ry = ry + (goal.y + root.y) / 2;
-            if (rx >= 0 && rx < shapeX && ry >= 0 && ry < shapeY) break;
-            if (guard > 100000 || (rand_stream_ && rand_pos_ >= rand_n_)) break;
-        }
-    }
-    return {rx, ry};
-}
-
-// reference RTRRT.cpp:226-355.  The samples of one call depend only on (c_base, root, goal, shape),
-// all fixed during the call, so they are drawn up front on the host and the engine consumes as
-// many as the (virtual) time budget allows; unused draws are returned to the stream.
+// reference RTRRT.cpp:226-355.  The samples are drawn ON THE DEVICE (SamplePoint, RTRRT.cpp:234-262: rtpp_engine_set_rand; glibc's
+// sinf / cosf / atan2f bits, csrc/glibc_math.cuh) from the rand() values handed over here: the injected stream when there is one,
+// else this process's rand().  Values the tick did not consume stay in `pending_` for the next one.
 void RTRRTplanner::ExpandRewiring(long RunTime) {
     if (!started_) return;
-    const long long reads = (long long)RunTime * 1000000LL / dt_ns_;
-    const int n = (int)std::min<long long>(max_samples_, reads + 1);
-    std::vector<float> pts((size_t)max_samples_ * 2, 0.f);
-    std::vector<long long> offs(n + 1);
-    const long long pos0 = rand_pos_;
-    for (int i = 0; i < n; i++) {
-        offs[i] = rand_pos_;
-        const RTpoint p = SamplePoint();
-        pts[2 * i] = p.x, pts[2 * i + 1] = p.y;
+    int32_t n;
+    const int32_t *src;
+    if (rand_stream_) {
+        n = (int32_t)std::min<long long>(max_samples_, rand_n_ - rand_pos_);
+        src = rand_stream_ + rand_pos_;
+    } else {
+        while ((int)pending_.size() < max_samples_) pending_.push_back(rand());
+        n = max_samples_, src = pending_.data();
     }
-    offs[n] = rand_pos_;
-    const int32_t ns = n;
-    int rc = rtpp_engine_set_inputs(eng_, nullptr, nullptr, pts.data(), &ns);
+    std::vector<int32_t> r((size_t)max_samples_, 0);
+    memcpy(r.data(), src, (size_t)n * 4);
+    int rc = rtpp_engine_set_rand(eng_, r.data(), &n);
     if (!rc) rc = rtpp_engine_tick(eng_, 0, RunTime, dt_ns_, 0);
     long long st[16] = {0};
     if (!rc) rc = rtpp_engine_read_stats(eng_, st);
@@ -260,8 +224,8 @@ void RTRRTplanner::ExpandRewiring(long RunTime) {
         return;
     }
     if (st[9]) fprintf(stderr, "RTRRTplanner: engine capacity exceeded (status %lld)\n", st[9]);
-    if (rand_stream_) rand_pos_ = offs[st[2] < n ? st[2] : n]; // give back the draws of unused samples
-    (void)pos0;
+    if (rand_stream_) rand_pos_ += st[14];
+    else pending_.erase(pending_.begin(), pending_.begin() + (size_t)std::min<long long>(st[14], (long long)pending_.size()));
 }
 
 void RTRRTplanner::Start(void) {}

@@ -29,8 +29,7 @@ class RTRRTplanner {
     const int32_t *rand_stream_ = nullptr;
     long long rand_n_ = 0, rand_pos_ = 0;
     int node_capacity_ = 65536, max_samples_ = 16384;
-    int NextRand();
-    RTpoint SamplePoint();
+    std::vector<int32_t> pending_; // rand() values drawn for the engine and not consumed yet
     bool EnsureEngine();
     void UploadAgentGoal();
     bool Fail(const char *what, int rc);

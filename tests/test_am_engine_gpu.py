@@ -50,7 +50,7 @@ def test_am_engine_reproduces_reference_golden(ctx, oracle, case):
             p = np.array([case["goal"] if j == -2 else xy[j] for j in ids], np.float32)
             assert np.array_equal(p, g[k + "path"])
             assert np.uint32(d["path_cost_bits"]) == g[k + "path_cost"].view(np.uint32)
-    assert len(xy) > 80
+    assert len(xy) > (80 if case["name"] == "mess6" else 60)  # the tree really grew
     eng.close()
 
 
@@ -73,8 +73,9 @@ def _ellipse(c_base, goal, root):
 
 
 def test_am_engine_informed_sampling_against_oracle(ctx, oracle):
-    """OutPath filled by the caller (AMRRT/test/testD.cpp) switches the sampler to the informed ellipse:
-    the engine with host-computed ellipse parameters and host-tabulated cos/sin against the oracle."""
+    """OutPath filled by the caller (AMRRT/test/testD.cpp) switches the sampler to the informed ellipse: the engine evaluates the
+    ellipse (atan2f, cosf, sinf of the axis) and the cosf / sinf of every drawn angle on the device with glibc's bits
+    (csrc/glibc_math.cuh) — even ticks; odd ticks take the ellipse from the caller (host libm) — against the oracle."""
     import rtpp_b200
     from helpers import synthetic_diffusion
 
@@ -99,10 +100,13 @@ def test_am_engine_informed_sampling_against_oracle(ctx, oracle):
         chunk = np.zeros((1, cap_rand), np.int32)
         chunk[0] = r[pos: pos + cap_rand]
         eng.set_am_inputs(rand=chunk, n_rand=np.array([cap_rand], np.int32), outpath_nonempty=np.array([int(found)], np.int32))
-        eng.tick(update_tree=True, run_ms=0, dt_ns=500000, get_path=False)  # UpdateTree first: the ellipse needs the root
-        root = eng.read_tree(0)[0][eng.stats()[0][1]]
-        eng.set_am_inputs(ellipse=np.array([_ellipse(c_base, goal, root)], np.float32))
-        eng.tick(update_tree=False, run_ms=80, dt_ns=500000, get_path=True)
+        if tick % 2:
+            eng.tick(update_tree=True, run_ms=0, dt_ns=500000, get_path=False)  # UpdateTree first: the ellipse needs the root
+            root = eng.read_tree(0)[0][eng.stats()[0][1]]
+            eng.set_am_inputs(ellipse=np.array([_ellipse(c_base, goal, root)], np.float32))
+            eng.tick(update_tree=False, run_ms=80, dt_ns=500000, get_path=True)
+        else:
+            eng.tick(update_tree=True, run_ms=80, dt_ns=500000, get_path=True)
         orc.main_task()
         d = dict(zip(eng.STAT, eng.stats()[0].tolist()))
         pos += d["rand_pos"]

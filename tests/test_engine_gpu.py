@@ -9,12 +9,13 @@ from helpers import dyn_plane
 pytestmark = pytest.mark.gpu
 
 
-def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=True):
+def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=True, device_sampler=False):
     import rtpp_b200
 
     S = oracle.load_map(name)
     H, W = S.shape
-    max_samples = 4096
+    max_samples = 16384 if device_sampler else 4096
+    informed = 0
     eng = rtpp_b200.Engine(ctx, n_inst, 8192, 5, W, H, max_samples)
     eng.set_map(0, 1, S)
     orcs = []
@@ -43,13 +44,25 @@ def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=T
             samples[i, : len(pts)] = pts
             ns[i] = len(pts)
             offs_all.append(offs)
-        eng.set_inputs(samples=samples, n_samples=ns)
+        if device_sampler:
+            # the engine draws the samples itself from the raw rand() stream (SamplePoint on the device, glibc's sinf / cosf /
+            # atan2f bits); the oracle's pre-drawn points above are what it must come up with
+            chunk = np.zeros((n_inst, max_samples), np.int32)
+            for i in range(n_inst):
+                part = streams[i][pos[i]: pos[i] + max_samples]
+                chunk[i, : len(part)] = part
+            eng.set_rand(chunk, np.full(n_inst, max_samples, np.int32))
+        else:
+            eng.set_inputs(samples=samples, n_samples=ns)
         eng.tick(update_tree=True, run_ms=50, dt_ns=dt, get_path=True)
         st = eng.stats()
         for i, o in enumerate(orcs):
             used = o.expand_rewiring(50, samples[i, : ns[i]])
+            if device_sampler:
+                assert st[i][14] == int(offs_all[i][used]), f"tick {tick} inst {i}: rand() draws consumed"
             pos[i] += int(offs_all[i][used])
             opath, ocol, ocost, ocb = o.get_path()
+            informed += int(ocb >= 0)  # a path was found: the next tick samples the informed ellipse
             a = o.dump()
             b = eng.read_tree(i)
             d = dict(zip(eng.STAT, st[i].tolist()))
@@ -81,6 +94,8 @@ def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=T
             eng.set_inputs(agent_xy=new_agents)
     sizes = [o.num_nodes() for o in orcs]
     eng.close()
+    if device_sampler:
+        return sizes, informed
     return sizes
 
 
@@ -97,3 +112,14 @@ def test_rtrrt_engine_game0_reaches_goal(ctx, oracle):
 def test_rtrrt_engine_many_instances(ctx, oracle):
     sizes = _run_pair(ctx, oracle, "Trap", (660.0, 660.0), (1160.0, 1160.0), dt=20000, ticks=5, seed=100, n_inst=12)
     assert len(set(sizes)) > 1  # different seeds -> different trees
+
+
+def test_rtrrt_engine_device_sampler_uniform_and_informed(ctx, oracle):
+    """rtpp_engine_set_rand: the engine draws its samples on the device from the raw rand() stream (SamplePoint, RTRRT.cpp:234-262).
+    On FLOOR5 (the scenario of test_oracle_ref.py::test_rtrrt_live_with_informed_sampling) a path to the goal is found after a
+    few ticks, which switches 90 % of the samples to the informed ellipse (glibc's atan2f / cosf / sinf on the device): trees,
+    paths, clock reads AND the number of rand() draws consumed must equal the oracle's."""
+    sizes, informed = _run_pair(ctx, oracle, "FLOOR5", (1000.0, 1200.0), (1750.0, 900.0), dt=2000, ticks=24, seed=21, moves=False, device_sampler=True)
+    assert sizes[0] > 300 and informed >= 2
+    sizes, informed = _run_pair(ctx, oracle, "Trap", (660.0, 660.0), (1160.0, 1160.0), dt=20000, ticks=6, seed=100, n_inst=12, device_sampler=True)
+    assert len(set(sizes)) > 1

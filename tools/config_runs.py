@@ -15,13 +15,14 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def c1_rtrrt(ctx, orc, n_samples=20_000, dt=1_000_000, max_ticks=40_000, seed=1, check_cpu=True):
+def c1_rtrrt(ctx, orc, n_samples=20_000, dt=1_000_000, max_ticks=40_000, seed=1, check_cpu=True, check_ticks=None):
     """RT-RRT* single agent on GAME0 (RTRRT/test/test.cpp:60-67: agent (550, 550), no goal => uniform sampling only,
     RTRRT.cpp:234-239), samples injected from rand31(seed) exactly as the uniform branch draws them; ticks of
     UpdateTree + ExpandRewiring(50 ms virtual) + GetPath until the samples are consumed.  The virtual clock advances dt = 1 ms per
     read, i.e. 50 loop iterations (one sample, then queue pops) per tick: once the tree is larger than the budget a tick takes ONE
     sample whatever the budget is (the rewire-from-root sweep, RTRRT.cpp:323-353, eats the rest), so the budget only sets how
-    much rewiring rides along; 20 000 samples are then 20 000 ticks."""
+    much rewiring rides along; 20 000 samples are then 20 000 ticks.  check_ticks: compare the trees after that many ticks (a
+    bounded CPU run, for bench.py) instead of at the end (tests/test_configs_gpu.py)."""
     import rtpp_b200
     import sweep_bench as sb
 
@@ -33,17 +34,21 @@ def c1_rtrrt(ctx, orc, n_samples=20_000, dt=1_000_000, max_ticks=40_000, seed=1,
     eng.init_instances(np.zeros(1, np.int32), np.array([[550.0, 550.0]], np.float32), np.array([[-1.0, -1.0]], np.float32))
     eng.set_inputs(samples=samples[None], n_samples=np.array([n_samples], np.int32))
     ctx.sync()
-    lat = []
+    lat, snap = [], None
     while len(lat) < max_ticks:
         t0 = time.perf_counter()
         eng.tick(update_tree=True, run_ms=50, dt_ns=dt, get_path=True)
         ctx.sync()
         lat.append(time.perf_counter() - t0)
+        if check_ticks is not None and len(lat) == check_ticks:
+            snap = (eng.read_tree(0), int(eng.stats()[0, 2]))
         if int(eng.stats()[0, 2]) >= n_samples:
             break
     st = eng.stats_dict(0)
     tree = eng.read_tree(0)
     eng.close()
+    if check_ticks is None or len(lat) < check_ticks:
+        snap, check_ticks = (tree, int(st["samples_used"])), len(lat)
     out = {"map": "GAME0", "samples": n_samples, "ticks": len(lat), "virtual_dt_ns": dt, "nodes": int(st["n_nodes"]), "samples_used": int(st["samples_used"]),
            "gpu_status": int(st["status"]), "gpu_tick_ms_p50": float(np.median(lat) * 1e3), "gpu_total_s": float(sum(lat)),
            "gpu_iters_per_s": st["iters"] / sum(lat), "gpu_queue_pops_per_s": (st["pops_r"] + st["pops_s"]) / sum(lat)}
@@ -53,7 +58,7 @@ def c1_rtrrt(ctx, orc, n_samples=20_000, dt=1_000_000, max_ticks=40_000, seed=1,
         o.set_agent(550.0, 550.0)
         o.set_goal(-1.0, -1.0)
         pos, tl = 0, []
-        for _ in range(len(lat)):
+        for _ in range(check_ticks):
             t0 = time.perf_counter()
             o.update_tree()
             pos += o.expand_rewiring(50, samples[pos:])
@@ -64,8 +69,9 @@ def c1_rtrrt(ctx, orc, n_samples=20_000, dt=1_000_000, max_ticks=40_000, seed=1,
         out["cpu_tick_ms_p50"] = float(np.median(tl) * 1e3)
         out["cpu_total_s"] = float(sum(tl))
         out["cpu_kind"] = "port (oracle loops), 1 thread"
-        out["tree_matches_cpu"] = bool(pos == st["samples_used"] and all(np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
-                                                                          for a, b in zip(cpu_tree, tree)))
+        out["ticks_compared"] = check_ticks
+        out["tree_matches_cpu"] = bool(pos == snap[1] and all(np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+                                                              for a, b in zip(cpu_tree, snap[0])))
     return out, tree, S
 
 
@@ -110,7 +116,7 @@ def c1_edge_batches(ctx, orc, tree_xy, S, n_knn_edges=1 << 24, n_long=1 << 20, s
     return out
 
 
-def c3_rtfmt(ctx, orc, samples=100_000, chunk=20_000, max_rounds=2_000_000, check_cpu=True):
+def c3_rtfmt(ctx, orc, samples=100_000, chunk=20_000, max_rounds=2_000_000, check_cpu=True, check_rounds=None):
     """RT-FMT on GAME0 with 1e5 free-space samples (RTFMT/test/test.cpp:56 agent (360, 540); the reference ships 2000): rounds
     of ExpandFMT + RewireFromObstacles + RewireFromRoot (RTFMT.cpp:423-703) until V_unv is exhausted or no z is left."""
     import rtpp_b200
@@ -130,7 +136,7 @@ def c3_rtfmt(ctx, orc, samples=100_000, chunk=20_000, max_rounds=2_000_000, chec
     eng.start(np.zeros(1, np.int32), [xy], np.array([[2000.0, 400.0]], np.float32))
     ctx.sync()
     gpu_start = time.perf_counter() - t0
-    rounds, gpu_s, first = 0, 0.0, True
+    rounds, gpu_s, first, snap = 0, 0.0, True, None
     while rounds < max_rounds:
         t0 = time.perf_counter()
         eng.tick(update_tree=first, iters=chunk, with_rewire=True, get_path=False)
@@ -138,6 +144,8 @@ def c3_rtfmt(ctx, orc, samples=100_000, chunk=20_000, max_rounds=2_000_000, chec
         gpu_s += time.perf_counter() - t0
         rounds += chunk
         first = False
+        if check_rounds is not None and rounds == check_rounds:
+            snap = eng.read_tree(0)
         st = eng.stats_dict(0)
         if st["n_unv"] == 0 or st["z"] < 0:
             break
@@ -145,15 +153,18 @@ def c3_rtfmt(ctx, orc, samples=100_000, chunk=20_000, max_rounds=2_000_000, chec
     out = {"samples": samples, "nodes": int(st["n_nodes"]), "rounds": rounds, "n_unv_left": int(st["n_unv"]), "z": int(st["z"]), "gpu_status": int(st["status"]),
            "gpu_start_ms": gpu_start * 1e3, "gpu_s": gpu_s, "gpu_rounds_per_s": rounds / gpu_s, "cpu_start_ms": cpu_start * 1e3}
     if check_cpu:
+        if snap is None:
+            snap, check_rounds = eng.read_tree(0), rounds
         t0 = time.perf_counter()
         o.update_tree()
-        for _ in range(rounds // chunk):
+        for _ in range(check_rounds // chunk):
             o.expand(chunk, True)
         cpu_s = time.perf_counter() - t0
-        par, c, cl, stt = eng.read_tree(0)
+        par, c, cl, stt = snap
         oxy, opar, oc, ocl, ost = o.dump()
         out["cpu_s"] = cpu_s
-        out["cpu_rounds_per_s"] = rounds / cpu_s
+        out["rounds_compared"] = check_rounds
+        out["cpu_rounds_per_s"] = check_rounds / cpu_s
         out["cpu_kind"] = "port (oracle loops), 1 thread"
         out["state_matches_cpu"] = bool(np.array_equal(par, opar) and np.array_equal(stt, ost) and np.array_equal(cl, ocl) and
                                         np.array_equal(c.view(np.uint32), oc.view(np.uint32)))
