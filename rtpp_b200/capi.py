@@ -444,7 +444,7 @@ class FmtEngine:
 
 
 # ---------------------------------------------------------------------------------------------
-# C++ drop-in planner classes (rtpp_b200/planners, librtpp_planners.so) through their C harness
+# C++ drop-in planner classes (rtpp_b200/planners, librtpp_planners.so) through their C harness (librtpp_planners_harness.so, test only)
 # ---------------------------------------------------------------------------------------------
 _plib = None
 
@@ -452,7 +452,7 @@ _plib = None
 def planners_lib():
     global _plib
     if _plib is None:
-        path = os.path.join(HERE, "librtpp_planners.so")
+        path = os.path.join(HERE, "librtpp_planners_harness.so")
         if not os.path.exists(path):
             raise RtppError(f"{path} is missing: run __graft_entry__.build()")
         lib()  # librtpp_gpu.so first (same directory, rpath $ORIGIN)

@@ -82,6 +82,9 @@ int rtpp_raster_batch(rtpp_ctx *ctx, uint32_t *planes, size_t stride_words, int 
                       int n_circles, const int32_t *poly_xy, const int32_t *poly_sizes, const int32_t *poly_inst, int n_polys,
                       const RasterShapes *prev);
 int rtpp_select_plane(rtpp_ctx *ctx, int plane_mask, PlaneView *pv);
+// map.cu: byte plane -> bit tiles; word-wise OR of two tile planes (b == nullptr: copy)
+int rtpp_plane_pack(rtpp_ctx *ctx, const uint8_t *d_src, int W, int H, uint32_t *d_dst);
+int rtpp_plane_merge(rtpp_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t words);
 struct MarchThresholds;
 void rtpp_march_thresholds(int divisor, MarchThresholds *out);
 

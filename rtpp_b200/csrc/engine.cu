@@ -1071,27 +1071,6 @@ __global__ void engine_set_agents_kernel(EngView ev, const float2 *__restrict__ 
     if (samp_n) ev.inst[w].samp_n = samp_n[w], ev.inst[w].samp_pos = 0;
 }
 
-__global__ void __launch_bounds__(256) engine_pack_plane_kernel(const uint8_t *__restrict__ src, int W, int H, int tilesX,
-                                                               size_t n_words, uint32_t *__restrict__ dst) {
-    const int lane = threadIdx.x & 31;
-    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t wi = warp; wi < n_words; wi += nwarps) {
-        size_t tile = wi >> 5;
-        int r = (int)(wi & 31);
-        int ty = (int)(tile / tilesX), tx = (int)(tile - (size_t)ty * tilesX);
-        int y = (ty << 5) + r, x = (tx << 5) + lane;
-        bool on = (y < H && x < W) ? (src[(size_t)y * W + x] != 0) : false;
-        uint32_t word = __ballot_sync(FULL, on);
-        if (lane == 0) dst[wi] = word;
-    }
-}
-__global__ void __launch_bounds__(256) engine_merge_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
-                                                          uint32_t *__restrict__ out, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = a[i] | (b ? b[i] : 0u);
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1196,12 +1175,14 @@ int rtpp_engine_set_map(rtpp_engine *e, int slot, int plane, const uint8_t *src,
         int rc = rtpp_scratch(ctx, 0, (size_t)W * H, &d);
         if (rc) return rc;
         ENG_CK(e, cudaMemcpyAsync(d, src, (size_t)W * H, cudaMemcpyHostToDevice, ctx->stream));
-        engine_pack_plane_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint8_t *)d, W, H, tilesX, words, dst);
-        RTPP_LAUNCHED(ctx);
+        rc = rtpp_plane_pack(ctx, (const uint8_t *)d, W, H, dst);
+        if (rc) return rc;
     } else
         ENG_CK(e, cudaMemsetAsync(dst, 0, words * 4, ctx->stream));
-    engine_merge_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
-    RTPP_LAUNCHED(ctx);
+    {
+        const int rcm = rtpp_plane_merge(ctx, e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
+        if (rcm) return rcm;
+    }
     ENG_CK(e, cudaStreamSynchronize(ctx->stream));
     e->v.plane_epoch[slot]++; // cached edge verdicts of this slot's instances are stale now
     e->v.planes[slot].w = e->plane_sd[slot];
@@ -1222,8 +1203,10 @@ int rtpp_engine_draw_dynamic(rtpp_engine *e, int slot, const int32_t *circles, i
     const size_t words = e->plane_words[slot];
     int rc = rtpp_raster_into(ctx, e->plane_d[slot], W, H, circles, n_circles, poly_xy, poly_sizes, n_polys); // clears first
     if (rc) return rc;
-    engine_merge_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
-    RTPP_LAUNCHED(ctx);
+    {
+        const int rcm = rtpp_plane_merge(ctx, e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
+        if (rcm) return rcm;
+    }
     e->v.plane_epoch[slot]++; // cached edge verdicts of this slot's instances are stale now
     return RTPP_OK;
 }

@@ -587,26 +587,6 @@ __global__ void fmt_set_agents_kernel(FmtView ev, const float2 *__restrict__ age
     if (goal) ev.inst[w].goal = goal[w];
 }
 
-__global__ void __launch_bounds__(256) fmt_pack_plane_kernel(const uint8_t *__restrict__ src, int W, int H, int tilesX, size_t n_words,
-                                                            uint32_t *__restrict__ dst) {
-    const int lane = threadIdx.x & 31;
-    size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t wi = warp; wi < n_words; wi += nwarps) {
-        size_t tile = wi >> 5;
-        int r = (int)(wi & 31);
-        int ty = (int)(tile / tilesX), tx = (int)(tile - (size_t)ty * tilesX);
-        int y = (ty << 5) + r, x = (tx << 5) + lane;
-        bool on = (y < H && x < W) ? (src[(size_t)y * W + x] != 0) : false;
-        uint32_t word = __ballot_sync(FULL, on);
-        if (lane == 0) dst[wi] = word;
-    }
-}
-__global__ void __launch_bounds__(256) fmt_merge_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
-                                                       uint32_t *__restrict__ out, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = a[i] | b[i];
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -685,12 +665,14 @@ int rtpp_fmt_set_map(rtpp_fmt_engine *e, int slot, int plane, const uint8_t *src
         int rc = rtpp_scratch(ctx, 0, (size_t)W * H, &d);
         if (rc) return rc;
         FMT_CK(e, cudaMemcpyAsync(d, src, (size_t)W * H, cudaMemcpyHostToDevice, ctx->stream));
-        fmt_pack_plane_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint8_t *)d, W, H, tilesX, words, dst);
-        RTPP_LAUNCHED(ctx);
+        rc = rtpp_plane_pack(ctx, (const uint8_t *)d, W, H, dst);
+        if (rc) return rc;
     } else
         FMT_CK(e, cudaMemsetAsync(dst, 0, words * 4, ctx->stream));
-    fmt_merge_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
-    RTPP_LAUNCHED(ctx);
+    {
+        const int rcm = rtpp_plane_merge(ctx, e->plane_s[slot], e->plane_d[slot], e->plane_sd[slot], words);
+        if (rcm) return rcm;
+    }
     FMT_CK(e, cudaStreamSynchronize(ctx->stream));
     PlaneView pv;
     pv.W = W, pv.H = H, pv.tilesX = tilesX;

@@ -36,6 +36,30 @@ __global__ void __launch_bounds__(256) unpack_plane_kernel(PlaneView p, uint8_t 
     }
 }
 
+// shared with the planner engines (one pack kernel, one merge kernel in the library)
+int rtpp_plane_pack(rtpp_ctx *ctx, const uint8_t *d_src, int W, int H, uint32_t *d_dst) {
+    const int tilesX = (W + 31) >> 5, tilesY = (H + 31) >> 5;
+    const size_t words = (size_t)tilesX * tilesY * 32;
+    int grid = (int)((words * 32 + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    pack_plane_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, W, H, tilesX, words, d_dst);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+// out = a | b word by word (b == nullptr: out = a); words is a multiple of 32 (whole tiles)
+int rtpp_plane_merge(rtpp_ctx *ctx, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t words) {
+    if (!b) {
+        RTPP_CK(ctx, cudaMemcpyAsync(out, a, words * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return RTPP_OK;
+    }
+    const size_t n4 = words / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    merge_planes_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)out, n4);
+    RTPP_LAUNCHED(ctx);
+    return RTPP_OK;
+}
+
 static int ensure_planes(rtpp_ctx *ctx, int W, int H) {
     if (W <= 0 || H <= 0 || W > (1 << 20) || H > (1 << 20)) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "bad plane shape");
     if ((long long)W * H >= (1LL << 31)) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "plane larger than 2^31 pixels");
@@ -62,15 +86,7 @@ static int ensure_planes(rtpp_ctx *ctx, int W, int H) {
     return RTPP_OK;
 }
 
-static int remerge(rtpp_ctx *ctx) {
-    size_t n4 = ctx->plane_words / 4;
-    int grid = (int)((n4 + 255) / 256);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    merge_planes_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4 *)ctx->plane[0], (const uint4 *)ctx->plane[1],
-                                                        (uint4 *)ctx->plane[2], n4);
-    RTPP_LAUNCHED(ctx);
-    return RTPP_OK;
-}
+static int remerge(rtpp_ctx *ctx) { return rtpp_plane_merge(ctx, ctx->plane[0], ctx->plane[1], ctx->plane[2], ctx->plane_words); }
 
 int rtpp_select_plane(rtpp_ctx *ctx, int plane_mask, PlaneView *pv) {
     if (!ctx->plane[0]) RTPP_FAIL(ctx, RTPP_ERR_STATE, "no map plane has been set");
@@ -88,10 +104,8 @@ int rtpp_map_set_plane_dev(rtpp_ctx *ctx, int plane, const uint8_t *d_src, int W
     RTPP_CK(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_planes(ctx, W, H);
     if (rc) return rc;
-    int grid = (int)((ctx->plane_words * 32 + 255) / 256);
-    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
-    pack_plane_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, W, H, ctx->tilesX, ctx->plane_words, ctx->plane[plane - 1]);
-    RTPP_LAUNCHED(ctx);
+    rc = rtpp_plane_pack(ctx, d_src, W, H, ctx->plane[plane - 1]);
+    if (rc) return rc;
     ctx->plane_set[plane - 1] = true;
     return remerge(ctx);
 }

@@ -143,12 +143,6 @@ __global__ void __launch_bounds__(128) raster_poly_fill_kernel(TileTarget t0, co
         raster_poly_fill_row(t, pts, pd, y);
 }
 
-__global__ void __launch_bounds__(256) raster_merge_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ out, size_t n4) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 u = a[i], v = b[i];
-        out[i] = make_uint4(u.x | v.x, u.y | v.y, u.z | v.z, u.w | v.w);
-    }
-}
 
 // One pass over a set of shapes: circle c = (cx, cy, r, plane), polygon p into plane poly_inst[p]; erase = 1 clears their
 // pixels.  The shapes go up in ONE copy — [circles | polygon vertices | polygon descriptors]; steps, edges and rows are
@@ -248,12 +242,7 @@ int rtpp_map_draw_dynamic(rtpp_ctx *ctx, const int32_t *circles, int n_circles, 
     int rc = rtpp_raster_into(ctx, ctx->plane[1], ctx->W, ctx->H, circles, n_circles, poly_xy, poly_sizes, n_polys);
     if (rc) return rc;
     ctx->plane_set[1] = true;
-    const size_t n4 = ctx->plane_words / 4;
-    int grid = (int)((n4 + 255) / 256);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    raster_merge_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4 *)ctx->plane[0], (const uint4 *)ctx->plane[1], (uint4 *)ctx->plane[2], n4);
-    RTPP_LAUNCHED(ctx);
-    return RTPP_OK;
+    return rtpp_plane_merge(ctx, ctx->plane[0], ctx->plane[1], ctx->plane[2], ctx->plane_words);
 }
 
 } // extern "C"

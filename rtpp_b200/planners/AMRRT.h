@@ -13,7 +13,7 @@ struct DIFFpoint {
     bool operator<(const DIFFpoint &o) const { return x != o.x ? x < o.x : y < o.y; }
 };
 
-class AMRRTplanner : public rtppPlannerBase {
+class RTPP_PLANNER_API AMRRTplanner : public rtppPlannerBase {
   private:
     RTpoint agent = {-1, -1};
     RTpoint root = {-1, -1};

@@ -95,7 +95,10 @@ typedef struct {
 } CTrtrt_DynamicObstacle;
 #define doubleMax (1.79769e+307)
 
-class BImap {
+#ifndef RTPP_PLANNER_API
+#define RTPP_PLANNER_API __attribute__((visibility("default")))
+#endif
+class RTPP_PLANNER_API BImap {
   private:
     rtpp_ctx *ctx_ = nullptr;
     rtpp_cdrt_engine *eng_ = nullptr;

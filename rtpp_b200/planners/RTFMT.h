@@ -6,7 +6,7 @@
 #define RTPP_B200_RTFMT_H
 #include "rtpp_types.h"
 
-class RTFMTplanner : public rtppPlannerBase {
+class RTPP_PLANNER_API RTFMTplanner : public rtppPlannerBase {
   private:
     RTpoint agent = {-1, -1};
     RTpoint root = {-1, -1};

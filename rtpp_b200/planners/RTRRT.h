@@ -17,7 +17,7 @@
 #define RTPP_B200_RTRRT_H
 #include "rtpp_types.h"
 
-class RTRRTplanner {
+class RTPP_PLANNER_API RTRRTplanner {
   private:
     RTpoint root = {-1, -1};
     RTpoint goal = {-1, -1};

@@ -58,7 +58,10 @@ typedef RTrrt_NodeAttribute RTFMT_NodeAttribute;
 
 // What the three image-based planners share verbatim in the reference: planes, obstacle set,
 // InitializeInvironment (RTRRT.cpp:57-80), DrawDObsmap (RTRRT.cpp:138-169), injected rand().
-class rtppPlannerBase {
+// the planner classes are the library's C++ surface: exported although the library is built with hidden visibility
+#define RTPP_PLANNER_API __attribute__((visibility("default")))
+
+class RTPP_PLANNER_API rtppPlannerBase {
   protected:
     rtpp_ctx *ctx_ = nullptr;
     const int32_t *rand_stream_ = nullptr;
