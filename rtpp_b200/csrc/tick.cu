@@ -348,8 +348,9 @@ __device__ __forceinline__ void tick_list_word(const TickArgs &a, const TickPeer
     }
 }
 
-template <bool kPeers, bool kBulk, int kMinBlocks = 4>
-__global__ void __launch_bounds__(32 * kTickWarps, kMinBlocks) tick_check_kernel(const TickArgs a, const TickPeers peers) {
+// (5 blocks per SM at 48 registers measured the same 0.097 ms as 4 at 62: the kernel is not short of warps)
+template <bool kPeers, bool kBulk>
+__global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const TickArgs a, const TickPeers peers) {
     __shared__ __align__(128) uint32_t win[kTickWarps][kWinWords];
     __shared__ __align__(8) unsigned long long bars[kTickWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
