@@ -1082,6 +1082,15 @@ template <class T> static int eng_alloc(rtpp_engine *e, T **p, size_t count) {
     return RTPP_OK;
 }
 
+// host staging for the read-back helpers: malloc, not std::string — a bad_alloc must not unwind through the C ABI
+struct HostBuf {
+    void *p = nullptr;
+    explicit HostBuf(size_t bytes) { p = malloc(bytes ? bytes : 1); }
+    ~HostBuf() { free(p); }
+    HostBuf(const HostBuf &) = delete;
+    HostBuf &operator=(const HostBuf &) = delete;
+};
+
 extern "C" {
 
 int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int node_capacity, int cell_log2, int domain_w,
@@ -1132,7 +1141,10 @@ int rtpp_engine_create(rtpp_ctx *ctx, int planner_kind, int n_instances, int nod
         v.rand_stream = e->d_rand;
     }
     rc |= eng_alloc(e, &v.path, N * v.path_cap);
-    if (rc) return RTPP_ERR_NOMEM;
+    if (rc) {
+        rtpp_engine_destroy(e); // frees what was allocated (cudaFree(nullptr) is a no-op)
+        RTPP_FAIL(ctx, RTPP_ERR_NOMEM, "engine buffers do not fit the device");
+    }
     *out = e;
     return RTPP_OK;
 }
@@ -1158,6 +1170,7 @@ int rtpp_engine_set_map(rtpp_engine *e, int slot, int plane, const uint8_t *src,
     if (plane == 1 && !src) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "static plane needs data");
     if (plane == 2 && !e->plane_s[slot]) RTPP_FAIL(ctx, RTPP_ERR_STATE, "set the static plane of the slot first");
     if (plane == 2) W = e->W[slot], H = e->H[slot];
+    if (W < 1 || H < 1 || (long long)W * H >= (1ll << 31)) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "plane shape: 1 <= W, H and W*H < 2^31 (as rtpp_map_set_plane)");
     const int tilesX = (W + 31) >> 5, tilesY = (H + 31) >> 5;
     const size_t words = (size_t)tilesX * tilesY * 32;
     if (plane == 1) {
@@ -1225,6 +1238,9 @@ int rtpp_engine_init_instances(rtpp_engine *e, const int32_t *map_slot, const fl
     if (!e || !map_slot || !agent_xy || !goal_xy) return RTPP_ERR_INVALID;
     rtpp_ctx *ctx = e->ctx;
     const int n = e->v.n_inst;
+    for (int i = 0; i < n; i++)
+        if (map_slot[i] < 0 || map_slot[i] >= 16 || !e->plane_s[map_slot[i]])
+            RTPP_FAIL(ctx, RTPP_ERR_INVALID, "map_slot: 0..15, and the slot's static plane must have been set (rtpp_engine_set_map)");
     void *ds, *da, *dg;
     int rc = upload(e, 0, map_slot, (size_t)n * 4, &ds);
     rc |= upload(e, 1, agent_xy, (size_t)n * 8, &da);
@@ -1246,6 +1262,10 @@ int rtpp_engine_set_inputs(rtpp_engine *e, const float *agent_xy, const float *g
     if (!e) return RTPP_ERR_INVALID;
     rtpp_ctx *ctx = e->ctx;
     const int n = e->v.n_inst;
+    if (n_samples)
+        for (int i = 0; i < n; i++)
+            if (n_samples[i] < 0 || n_samples[i] > e->v.max_samples)
+                RTPP_FAIL(ctx, RTPP_ERR_INVALID, "n_samples: 0 .. max_samples of rtpp_engine_create");
     void *da, *dg, *dn;
     int rc = upload(e, 0, agent_xy, (size_t)n * 8, &da);
     rc |= upload(e, 1, goal_xy, (size_t)n * 8, &dg);
@@ -1373,10 +1393,11 @@ int rtpp_engine_read_stats(rtpp_engine *e, long long *out16) {
     if (!e || !out16) return RTPP_ERR_INVALID;
     rtpp_ctx *ctx = e->ctx;
     const int n = e->v.n_inst;
-    std::string buf((size_t)n * sizeof(EngInst), '\0');
-    ENG_CK(e, cudaMemcpyAsync(&buf[0], e->v.inst, buf.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    HostBuf buf((size_t)n * sizeof(EngInst));
+    if (!buf.p) return RTPP_ERR_NOMEM;
+    ENG_CK(e, cudaMemcpyAsync(buf.p, e->v.inst, (size_t)n * sizeof(EngInst), cudaMemcpyDeviceToHost, ctx->stream));
     ENG_CK(e, cudaStreamSynchronize(ctx->stream));
-    const EngInst *s = (const EngInst *)buf.data();
+    const EngInst *s = (const EngInst *)buf.p;
     for (int i = 0; i < n; i++) {
         long long *o = out16 + (size_t)i * 16;
         uint32_t pc, cb;
@@ -1400,11 +1421,12 @@ int rtpp_engine_read_tree(rtpp_engine *e, int inst, int max_nodes, float *xy, in
     const int n = s.n < max_nodes ? s.n : max_nodes;
     *n_out = s.n;
     if (n <= 0 || !xy) return RTPP_OK;
-    std::string words((size_t)n * 8, '\0');
+    HostBuf words((size_t)n * 8);
+    if (!words.p) return RTPP_ERR_NOMEM;
     ENG_CK(e, cudaMemcpyAsync(xy, e->v.xy + (size_t)inst * e->v.cap, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    ENG_CK(e, cudaMemcpyAsync(&words[0], e->v.cp + (size_t)inst * e->v.cap, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ENG_CK(e, cudaMemcpyAsync(words.p, e->v.cp + (size_t)inst * e->v.cap, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     ENG_CK(e, cudaStreamSynchronize(ctx->stream));
-    const cpword *w = (const cpword *)words.data();
+    const cpword *w = (const cpword *)words.p;
     for (int i = 0; i < n; i++) {
         const uint32_t hi = cp_hi(w[i]), cb = hi & 0x7fffffffu;
         if (parent) parent[i] = cp_parent(w[i]);
@@ -1425,10 +1447,11 @@ int rtpp_engine_read_path(rtpp_engine *e, int inst, int max_len, int32_t *ids, i
     *len_out = s.path_len;
     if (n > max_len) n = max_len;
     if (n <= 0) return RTPP_OK;
-    std::string buf((size_t)n * 4, '\0');
-    ENG_CK(e, cudaMemcpyAsync(&buf[0], e->v.path + (size_t)inst * e->v.path_cap, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HostBuf buf((size_t)n * 4);
+    if (!buf.p) return RTPP_ERR_NOMEM;
+    ENG_CK(e, cudaMemcpyAsync(buf.p, e->v.path + (size_t)inst * e->v.path_cap, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ENG_CK(e, cudaStreamSynchronize(ctx->stream));
-    const int *p = (const int *)buf.data();
+    const int *p = (const int *)buf.p;
     // the device stores goal-first (push_front order reversed): emit root..goal like the std::list
     if (n >= 2 && p[0] == -2) for (int i = 0; i < n; i++) ids[i] = p[n - 1 - i];
     else memcpy(ids, p, (size_t)n * 4);

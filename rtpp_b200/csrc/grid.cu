@@ -194,17 +194,26 @@ int rtpp_nodes_reset(rtpp_ctx *ctx, int cell_log2, size_t capacity, int domain_w
     s->gh = ((domain_h - 1) >> cell_log2) + 1;
     s->capacity = capacity;
     const size_t m = (size_t)s->gw * s->gh + 1;
-    RTPP_CK(ctx, cudaMalloc(&s->xy, capacity * sizeof(float2)));
-    RTPP_CK(ctx, cudaMalloc(&s->sxy, capacity * sizeof(float2)));
-    RTPP_CK(ctx, cudaMalloc(&s->sid, capacity * sizeof(int)));
-    RTPP_CK(ctx, cudaMalloc(&s->cell_of, capacity * sizeof(int)));
-    RTPP_CK(ctx, cudaMalloc(&s->cell_start, m * sizeof(int)));
-    RTPP_CK(ctx, cudaMalloc(&s->cursor, m * sizeof(int)));
-    RTPP_CK(ctx, cudaMalloc(&s->gap, m));
-    RTPP_CK(ctx, cudaMalloc(&s->scan_totals, ((m > capacity ? m : capacity) / 2048 + 4) * sizeof(int)));
-    RTPP_CK(ctx, cudaMalloc(&s->cp, capacity * sizeof(unsigned long long)));
-    RTPP_CK(ctx, cudaMemsetAsync(s->cp, 0xff, capacity * sizeof(unsigned long long), ctx->stream));
-    RTPP_CK(ctx, cudaMemsetAsync(s->cell_start, 0, m * sizeof(int), ctx->stream));
+    // a failed allocation must not leave a half-built store behind: collect the first error, then tear down
+    cudaError_t ce = cudaSuccess;
+    auto keep = [&](cudaError_t r) {
+        if (ce == cudaSuccess) ce = r;
+    };
+    keep(cudaMalloc(&s->xy, capacity * sizeof(float2)));
+    keep(cudaMalloc(&s->sxy, capacity * sizeof(float2)));
+    keep(cudaMalloc(&s->sid, capacity * sizeof(int)));
+    keep(cudaMalloc(&s->cell_of, capacity * sizeof(int)));
+    keep(cudaMalloc(&s->cell_start, m * sizeof(int)));
+    keep(cudaMalloc(&s->cursor, m * sizeof(int)));
+    keep(cudaMalloc(&s->gap, m));
+    keep(cudaMalloc(&s->scan_totals, ((m > capacity ? m : capacity) / 2048 + 4) * sizeof(int)));
+    keep(cudaMalloc(&s->cp, capacity * sizeof(unsigned long long)));
+    if (ce == cudaSuccess) keep(cudaMemsetAsync(s->cp, 0xff, capacity * sizeof(unsigned long long), ctx->stream));
+    if (ce == cudaSuccess) keep(cudaMemsetAsync(s->cell_start, 0, m * sizeof(int), ctx->stream));
+    if (ce != cudaSuccess) {
+        rtpp_nodes_destroy(ctx);
+        RTPP_CK(ctx, ce);
+    }
     return RTPP_OK;
 }
 

@@ -405,7 +405,10 @@ __device__ __forceinline__ void relax_node(RelaxBlock &sm, int x, uint32_t hx, u
                 hn = cost_add(hx, we);
                 const cpword neww = rq_make(hn, x, 0);
                 // the test before the atomic also keeps a re-relaxation at unchanged cost from re-queueing a whole subtree
-                if (!(free_only && (hn >> 31)) && neww < (((volatile cpword *)cp)[sn] & ~1ull)) {
+                // hn > hx: an edge whose weight is absorbed by the rounding (coincident nodes) must not relax — two such nodes
+                // would otherwise adopt each other as parents at equal cost (smaller id wins the word compare) and leave the tree;
+                // the reference is strict on cost as well (RTRRT.cpp:311)
+                if (hn > hx && !(free_only && (hn >> 31)) && neww < (((volatile cpword *)cp)[sn] & ~1ull)) {
                     const cpword prev = atomicMin(&cp[sn], neww);
                     improved = neww < prev && (prev & 1ull); // the word was replaced and the node was idle: queue it
                 }

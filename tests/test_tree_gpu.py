@@ -273,3 +273,46 @@ def test_relax_ragged_tables_and_tiny_graphs(ctx, oracle, free_only):
     assert (got[2][n // 2 :] == 1).all()  # nothing on the far side is reachable without crossing the wall
     if free_only:
         assert np.array_equal(got[1][n // 2 :].view(np.uint32), cost0[n // 2 :].view(np.uint32))
+
+
+def test_relax_coincident_nodes_keep_the_tree_acyclic(ctx, oracle):
+    """Duplicated and nearly coincident nodes: the edge between them has a weight the binary32 sum absorbs
+    (cost + w == cost).  The bulk relax is strict on cost like RTRRT.cpp:311, so such a pair must not adopt each
+    other as parents: every free node still reaches the root by its parent links."""
+    H = W = 512
+    S = np.zeros((H, W), np.uint8)
+    ctx.map_set_plane(1, S)
+    ctx.map_clear_plane(2)
+    rng = np.random.default_rng(3)
+    base = (rng.random((600, 2)) * 60 + 66).astype(np.float32)     # a cloud ~ 600 px from the root: ulp(cost) = 6.1e-5
+    near = base[:150].copy()
+    near[:, 0] = np.nextafter(near[:, 0], np.float32(1e9))          # one coordinate ulp (7.6e-6) away: w < ulp(cost) / 2
+    xy = np.ascontiguousarray(np.concatenate([[[500.5, 500.5]], base, base[300:450], near]).astype(np.float32))
+    n, k = len(xy), 16
+    ctx.nodes_reset(4, n, W, H)
+    ctx.nodes_append(xy)
+    d_idx, idx = _device_knn_table(ctx, n, k)
+    # the worst start for the tie rule: every node hangs off the LAST node, so any smaller id looks better at equal cost
+    par = np.full(n, n - 1, np.int32)
+    par[0] = -1
+    cost0 = np.full(n, 3.4e38, np.float32)
+    col0 = np.ones(n, np.uint8)
+    cost0[0], col0[0] = 0.0, 0
+    for free_only in (True, False):
+        ctx.tree_set(par, cost0, col0)
+        ctx.relax_dev(d_idx, k, 5, 1, free_only=free_only)
+        p, c, l = ctx.tree_get()
+        fc, fl, _, _ = oracle.relax_fixpoint(S, None, xy, idx, 5, 1, cost0, col0, par, free_only=free_only)
+        assert np.array_equal(l, fl)
+        free = fl == 0
+        assert free.sum() > n // 2
+        assert np.array_equal(c[free].view(np.uint32), fc[free].view(np.uint32))
+        cur = np.nonzero(free)[0]
+        for _ in range(n):
+            cur = cur[cur != 0]
+            if len(cur) == 0:
+                break
+            assert (c[p[cur]] < c[cur]).all()   # strictly decreasing towards the root: no cycle can close
+            cur = np.unique(p[cur])
+        assert len(cur) == 0
+    ctx.dev_free(d_idx)
