@@ -27,6 +27,7 @@ int rtpp_raster_into(rtpp_ctx *ctx, uint32_t *plane, int W, int H, const int32_t
                      const int32_t *poly_sizes, int n_polys); // raster.cu
 
 #include "glibc_math.cuh"
+#include "path_fallback.cuh"
 
 #define FULL 0xffffffffu
 
@@ -563,7 +564,7 @@ __device__ void expand_rewiring(const EngView &ev, Inst &in, const MarchThreshol
 // ---------------------------------------------------------------------------------------------
 // GetPath (RTRRT.cpp:356-400): direct goal-root shortcut, else best entry among the 25-NN of the
 // goal, then the parent walk accumulating the binary32 length c_base.  The depth-5 fallback of
-// :401-437 (no collision-free entry) reports path_len = 0 with the reference's {1, 3.4e38} cost.
+// :401-437 (no collision-free entry) is path_fallback_warp: path root..nearest reachable node, cost {1, 3.4e38}.
 // ---------------------------------------------------------------------------------------------
 __device__ void get_path(const EngView &ev, Inst &in, const MarchThresholds &mt) {
     const int lane = threadIdx.x & 31;
@@ -619,6 +620,10 @@ __device__ void get_path(const EngView &ev, Inst &in, const MarchThresholds &mt)
         } else {
             in.s.path_len = len, in.s.path_col = 0, in.s.path_cost = cb, in.s.c_base = cb;
         }
+    } else { // RTRRT.cpp:401-437: no collision-free entry — the chain of the reachable node nearest the goal, cost {1, 3.4e38}
+        const int len = path_fallback_warp(in.xy, in.cp, in.s.n, in.s.root, g, in.path, ev.path_cap);
+        if (len < 0) in.s.path_cost = 2.4e38f;
+        else in.s.path_len = len; // path_col stays 1: rtpp_engine_read_path emits root..node, no goal point
     }
 }
 
@@ -1453,7 +1458,8 @@ int rtpp_engine_read_path(rtpp_engine *e, int inst, int max_len, int32_t *ids, i
     ENG_CK(e, cudaStreamSynchronize(ctx->stream));
     const int *p = (const int *)buf.p;
     // the device stores goal-first (push_front order reversed): emit root..goal like the std::list
-    if (n >= 2 && p[0] == -2) for (int i = 0; i < n; i++) ids[i] = p[n - 1 - i];
+    // (the direct root-goal shortcut is stored in order; the fallback chain, path_col = 1, is stored node-first as well)
+    if ((n >= 2 && p[0] == -2) || s.path_col) for (int i = 0; i < n; i++) ids[i] = p[n - 1 - i];
     else memcpy(ids, p, (size_t)n * 4);
     return RTPP_OK;
 }

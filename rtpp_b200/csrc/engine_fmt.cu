@@ -5,7 +5,7 @@
 //   F2a RewireFromObstacles  :531-595   -> rewire_from_obstacles()
 //   F2b RewireFromRoot       :665-703   -> rewire_from_root()
 //   R3  UpdateTree           :92-176    -> fmt_update_tree()   (re-root, BFS re-cost, N_b capture)
-//   P1  GetPath              :285-320   -> fmt_get_path()      (goal-entry branch)
+//   P1  GetPath              :285-391   -> fmt_get_path()      (goal-entry branch; depth-5 fallback: path_fallback.cuh)
 // The node set is fixed after Start (:393-422), so every Orthogonal_k_neighbor_search(.., 25) of
 // the loops (:427,440,477,549) is a row of a k-NN table built once per instance (:677's k = 20 is
 // the first 20 entries of the same sorted row).  The std::set<RTpoint> containers V_unv / V_open /
@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "nodes.cuh"
+#include "path_fallback.cuh"
 
 #define FULL 0xffffffffu
 static constexpr int FK = 25;
@@ -485,6 +486,9 @@ __device__ void fmt_get_path(const FmtView &ev, FI &in, const MarchThresholds &m
         len = __shfl_sync(FULL, len, 0), bad = __shfl_sync(FULL, bad, 0);
         in.s.path_ok = 1;
         in.s.path_len = bad ? 0 : len;
+    } else { // RTFMT.cpp:322-391: the chain of the reachable node nearest the goal (path_ok stays 0: no goal point in it)
+        const int len = path_fallback_warp(in.xy, in.cp, in.s.n, in.s.root, g, in.path, ev.path_cap);
+        in.s.path_len = len > 0 ? len : 0;
     }
 }
 

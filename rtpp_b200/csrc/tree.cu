@@ -405,12 +405,25 @@ __device__ __forceinline__ void relax_node(RelaxBlock &sm, int x, uint32_t hx, u
                 hn = cost_add(hx, we);
                 const cpword neww = rq_make(hn, x, 0);
                 // the test before the atomic also keeps a re-relaxation at unchanged cost from re-queueing a whole subtree
-                // hn > hx: an edge whose weight is absorbed by the rounding (coincident nodes) must not relax — two such nodes
-                // would otherwise adopt each other as parents at equal cost (smaller id wins the word compare) and leave the tree;
-                // the reference is strict on cost as well (RTRRT.cpp:311)
-                if (hn > hx && !(free_only && (hn >> 31)) && neww < (((volatile cpword *)cp)[sn] & ~1ull)) {
-                    const cpword prev = atomicMin(&cp[sn], neww);
-                    improved = neww < prev && (prev & 1ull); // the word was replaced and the node was idle: queue it
+                if (!(free_only && (hn >> 31)) && neww < (((volatile cpword *)cp)[sn] & ~1ull)) {
+                    if (hn > hx) {
+                        const cpword prev = atomicMin(&cp[sn], neww);
+                        improved = neww < prev && (prev & 1ull); // the word was replaced and the node was idle: queue it
+                    } else {
+                        // hn == hx: the edge's weight is absorbed by the rounding (coincident nodes).  Such an edge may carry a
+                        // strict cost improvement — the reference's sequential loop takes it too, RTRRT.cpp:311 — but not the
+                        // equal-cost parent-id tie-break of the word compare: two coincident nodes would adopt each other as
+                        // parents and drop out of the tree.  Rare, so a compare-and-swap loop instead of the atomicMin.
+                        cpword cur = ((volatile cpword *)cp)[sn];
+                        while (hn < cp_hi(cur)) {
+                            const cpword prev = atomicCAS(&cp[sn], cur, neww);
+                            if (prev == cur) {
+                                improved = prev & 1ull;
+                                break;
+                            }
+                            cur = prev;
+                        }
+                    }
                 }
             }
         }

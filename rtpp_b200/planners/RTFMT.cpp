@@ -139,7 +139,7 @@ void RTFMTplanner::SyncSets() {
         if (par[i] >= 0) Node_Map[pt(par[i])].subs.insert(pt(i));
 }
 
-// reference RTFMT.cpp:285-391: goal-entry branch on the device, depth-<=5 fallback on the host
+// reference RTFMT.cpp:285-391, both branches on the device (the depth-<=5 fallback is csrc/path_fallback.cuh)
 void RTFMTplanner::GetPath(std::list<RTpoint> &path) {
     path.clear();
     if (goal.x <= 0 || !started_) return;
@@ -147,36 +147,11 @@ void RTFMTplanner::GetPath(std::list<RTpoint> &path) {
     long long st[16] = {0};
     if (rtpp_fmt_read_stats(eng_, st)) return;
     auto pt = [&](int i) { return RTpoint{nodes_[2 * i], nodes_[2 * i + 1]}; };
-    if (st[14]) { // an entry with c_min < {0, 20000} exists
-        std::vector<int32_t> ids(st[13] > 0 ? st[13] : 1);
+    // st[14] = 1: an entry with c_min < {0, 20000} exists and the path ends in the goal; 0: the fallback chain root..nearest node
+    if (st[13] > 0) {
+        std::vector<int32_t> ids(st[13]);
         int len = 0;
         rtpp_fmt_read_path(eng_, 0, (int)ids.size(), ids.data(), &len);
         for (int k = 0; k < len && k < (int)ids.size(); k++) path.push_back(ids[k] == -2 ? goal : pt(ids[k]));
-        return;
-    }
-    SyncSets();
-    root = pt((int)st[1]);
-    RTpoint x_min = {-1, -1};
-    RTFMT_Cost c_min = {1, 3.3e38f};
-    std::queue<std::pair<int, RTpoint>> Q;
-    Q.push({0, root});
-    while (!Q.empty()) {
-        auto cur = Q.front();
-        Q.pop();
-        RTFMT_NodeAttribute &nc = Node_Map[cur.second];
-        if (cur.first < 5 && nc.subs.size())
-            for (const RTpoint &s : nc.subs)
-                if (!Node_Map[s].cost.collision) Q.push({cur.first + 1, s});
-        RTFMT_Cost c_now = {nc.cost.collision, cur.second % goal};
-        if (c_now < c_min) c_min = c_now, x_min = cur.second;
-    }
-    RTpoint x_i = x_min;
-    while (x_i.x >= 0) {
-        path.push_front(x_i);
-        x_i = Node_Map[x_i].par;
-        if (path.size() > 2000) {
-            path.clear();
-            return;
-        }
     }
 }

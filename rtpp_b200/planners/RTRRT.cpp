@@ -286,8 +286,8 @@ void RTRRTplanner::SyncNodeMap() {
         if (par[i] >= 0) Node_Map[{xy[2 * par[i]], xy[2 * par[i] + 1]}].subs.insert({xy[2 * i], xy[2 * i + 1]});
 }
 
-// reference RTRRT.cpp:356-478.  The goal-entry branches run on the device; the depth-<=5 fallback
-// (no collision-free entry among the 25-NN of the goal, :401-437) walks the materialised Node_Map.
+// reference RTRRT.cpp:356-478, all branches on the device (the depth-<=5 fallback of :401-437 is csrc/path_fallback.cuh):
+// only the path's node ids and the coordinates they index come back.
 RTrrt_Cost RTRRTplanner::GetPath(std::list<RTpoint> &path) {
     c_base = -1;
     path.clear();
@@ -304,7 +304,7 @@ RTrrt_Cost RTRRTplanner::GetPath(std::list<RTpoint> &path) {
     const uint32_t pc = (uint32_t)st[12], cbb = (uint32_t)st[13];
     memcpy(&pcost, &pc, 4), memcpy(&cb, &cbb, 4);
     c_base = cb;
-    if (st[11] == 0 && st[10] > 0) { // collision-free path found on the device
+    if (st[10] > 0) { // st[11] == 0: collision-free path to the goal; 1: the fallback chain root..nearest reachable node
         std::vector<int32_t> ids(st[10]);
         int len = 0;
         rtpp_engine_read_path(eng_, 0, (int)ids.size(), ids.data(), &len);
@@ -312,32 +312,8 @@ RTrrt_Cost RTRRTplanner::GetPath(std::list<RTpoint> &path) {
         std::vector<float> xy((size_t)n * 2);
         ReadTree(xy.data(), nullptr, nullptr, nullptr, n);
         for (int id : ids) path.push_back(id == -2 ? goal : RTpoint{xy[2 * id], xy[2 * id + 1]});
-        return {0, pcost};
     }
-    if (pcost == 2.4e38f) return {1, 2.4e38f}; // >2000 hops (reference :392-396)
-    SyncNodeMap();
-    RTpoint x_min = {-1, -1};
-    RTrrt_Cost c_min = {1, 3.3e38f};
-    std::queue<std::pair<int, RTpoint>> Q;
-    Q.push({0, root});
-    while (!Q.empty()) {
-        auto cur = Q.front();
-        Q.pop();
-        RTrrt_NodeAttribute &nc = Node_Map[cur.second];
-        if (cur.first < 5 && nc.subs.size())
-            for (const RTpoint &s : nc.subs)
-                if (!Node_Map[s].cost.collision) Q.push({cur.first + 1, s});
-        RTrrt_Cost c_now = {nc.cost.collision, cur.second % goal};
-        if (c_now < c_min) c_min = c_now, x_min = cur.second;
-    }
-    RTpoint x_i = x_min;
-    while (x_i.x >= 0) {
-        path.push_front(x_i);
-        x_i = Node_Map[x_i].par;
-        if (path.size() > 2000) {
-            path.clear();
-            return {1, 2.4e38f};
-        }
-    }
+    if (st[11] == 0 && st[10] > 0) return {0, pcost};
+    if (pcost == 2.4e38f) return {1, 2.4e38f}; // >2000 hops (reference :392-396, :428-432)
     return {1, 3.4e38f};
 }

@@ -15,7 +15,7 @@ def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=T
     S = oracle.load_map(name)
     H, W = S.shape
     max_samples = 16384 if device_sampler else 4096
-    informed = 0
+    informed = fallbacks = 0
     eng = rtpp_b200.Engine(ctx, n_inst, 8192, 5, W, H, max_samples)
     eng.set_map(0, 1, S)
     orcs = []
@@ -74,15 +74,15 @@ def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=T
             assert (d["qr_size"], d["qs_size"]) == o.queue_sizes()
             assert d["clock_reads"] == o.L.orc_rtrrt_clock_reads(o.h) - (0)  # GetPath reads no clock
             assert np.array_equal(b[0][d["root"]], o.root())
-            # path (goal-entry branches; the depth-5 fallback is host-side)
+            # path: the goal-entry branches and the depth-5 fallback (RTRRT.cpp:401-437: chain of the reachable node nearest
+            # the goal, reported with collision = 1 and cost 3.4e38), all on the device
             gcost = np.array([d["path_cost_bits"]], np.uint32).view(np.float32)[0]
-            if not ocol:
-                ids = eng.read_path(i)
-                gp = np.array([goal if j == -2 else b[0][j] for j in ids], np.float32)
-                assert d["path_col"] == 0 and np.array_equal(gp, opath)
-                assert np.array_equal(np.float32(gcost).view(np.uint32), np.float32(ocost).view(np.uint32))
-            else:
-                assert d["path_col"] == 1
+            ids = eng.read_path(i)
+            gp = np.array([goal if j == -2 else b[0][j] for j in ids], np.float32).reshape(-1, 2)
+            assert d["path_col"] == int(bool(ocol))
+            assert np.array_equal(gp, np.asarray(opath, np.float32).reshape(-1, 2)), f"tick {tick} inst {i}: path (collision {ocol})"
+            assert np.array_equal(np.float32(gcost).view(np.uint32), np.float32(ocost).view(np.uint32))
+            fallbacks += int(bool(ocol) and len(ids) > 0)
         if moves and tick in (3, 6):
             # the agent walks to some tree node: next UpdateTree re-roots there
             new_agents = np.zeros((n_inst, 2), np.float32)
@@ -94,6 +94,7 @@ def _run_pair(ctx, oracle, name, agent, goal, dt, ticks, seed, n_inst=1, moves=T
             eng.set_inputs(agent_xy=new_agents)
     sizes = [o.num_nodes() for o in orcs]
     eng.close()
+    _run_pair.fallbacks = fallbacks
     if device_sampler:
         return sizes, informed
     return sizes
@@ -107,6 +108,8 @@ def test_rtrrt_engine_single_instance_mess6(ctx, oracle):
 def test_rtrrt_engine_game0_reaches_goal(ctx, oracle):
     sizes = _run_pair(ctx, oracle, "GAME0", (350.0, 2350.0), (1400.0, 2050.0), dt=2000, ticks=8, seed=3)
     assert sizes[0] > 300
+    # the goal is out of reach in these 8 ticks: every GetPath took the depth-5 fallback (device: csrc/path_fallback.cuh)
+    assert _run_pair.fallbacks >= 4
 
 
 def test_rtrrt_engine_many_instances(ctx, oracle):

@@ -28,6 +28,7 @@ def test_fmt_engine_reproduces_reference_golden(ctx, oracle, case):
     eng.set_map(0, 1, S)
     eng.start(np.zeros(1, np.int32), [xy], np.array([case["goal"]], np.float32))
     rng = np.random.default_rng(case["seed"])
+    fallbacks = 0
     for rnd in range(case["rounds"]):
         if rnd in case["dobs_rounds"]:
             D = dyn_plane(S.shape, rng, n_blobs=5)
@@ -49,11 +50,12 @@ def test_fmt_engine_reproduces_reference_golden(ctx, oracle, case):
         # vs the oracle run side by side (also covers the counters)
         oxy, opar, oc, ocl, ost = orc.dump()
         assert np.array_equal(par, opar) and np.array_equal(st, ost)
-        gpath = g[k + "path"]
-        if d["path_ok"]:
-            ids = eng.read_path(0)
-            p = np.array([case["goal"] if j == -2 else xy[j] for j in ids], np.float32).reshape(-1, 2)
-            assert np.array_equal(p, gpath)
+        # GetPath, both branches on the device: path_ok = 1 ends in the goal, 0 is the depth-5 fallback chain (RTFMT.cpp:322-391)
+        gpath = np.asarray(g[k + "path"], np.float32).reshape(-1, 2)
+        ids = eng.read_path(0)
+        p = np.array([case["goal"] if j == -2 else xy[j] for j in ids], np.float32).reshape(-1, 2)
+        assert np.array_equal(p, gpath), f"round {rnd}: path (path_ok {d['path_ok']})"
+        fallbacks += int(not d["path_ok"] and len(ids) > 0)
         if rnd in case["move_rounds"]:
             p = orc.get_path()
             if len(p) > 2:

@@ -277,8 +277,9 @@ def test_relax_ragged_tables_and_tiny_graphs(ctx, oracle, free_only):
 
 def test_relax_coincident_nodes_keep_the_tree_acyclic(ctx, oracle):
     """Duplicated and nearly coincident nodes: the edge between them has a weight the binary32 sum absorbs
-    (cost + w == cost).  The bulk relax is strict on cost like RTRRT.cpp:311, so such a pair must not adopt each
-    other as parents: every free node still reaches the root by its parent links."""
+    (cost + w == cost).  Such an edge may carry a strict cost improvement (as in the reference's sequential loop,
+    RTRRT.cpp:311) but not the equal-cost parent-id tie-break, or two coincident nodes would adopt each other as
+    parents: costs equal the sequential fixpoint and every free node still reaches the root by its parent links."""
     H = W = 512
     S = np.zeros((H, W), np.uint8)
     ctx.map_set_plane(1, S)
@@ -312,7 +313,7 @@ def test_relax_coincident_nodes_keep_the_tree_acyclic(ctx, oracle):
             cur = cur[cur != 0]
             if len(cur) == 0:
                 break
-            assert (c[p[cur]] < c[cur]).all()   # strictly decreasing towards the root: no cycle can close
+            assert (c[p[cur]] <= c[cur]).all()
             cur = np.unique(p[cur])
-        assert len(cur) == 0
+        assert len(cur) == 0                    # everybody arrived at the root within n hops: no cycle
     ctx.dev_free(d_idx)

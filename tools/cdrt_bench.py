@@ -58,7 +58,15 @@ def single(ctx, orc, name="GAME0", goal=2, seed=7, dt=2000, ticks=60):
     out = {"map": name, "ticks": ticks, "virtual_dt_ns": dt, "pops_per_tick": st["pops"] / ticks, "pushes_per_tick": st["pushes"] / ticks,
            "nodes": len(da[0]), "gpu_tick_ms_p50": float(np.median(tg) * 1e3), "cpu_tick_ms_p50": float(np.median(tc) * 1e3),
            "cpu_kind": "port (oracle/cdrt_oracle.hpp), 1 thread", "state_matches_cpu": bool(same), "gpu_status": st["status"]}
+    # most of the 600 scripted ticks are light (no obstacle near the tree): p50 alone hides the heavy replanning ticks
+    def spread(key, ts):
+        a = np.asarray(ts) * 1e3
+        out[key + "_mean"], out[key + "_p90"], out[key + "_max"] = float(a.mean()), float(np.percentile(a, 90)), float(a.max())
+
+    spread("gpu_tick_ms", tg)
+    spread("cpu_tick_ms", tc)
     if ref is not None:
+        spread("reference_tick_ms", tr)
         dr = ref.dump()
         same_ref &= all(np.array_equal(x.view(np.uint8), y.view(np.uint8)) for x, y in zip(dr, db))
         out["reference_tick_ms_p50"] = float(np.median(tr) * 1e3)
