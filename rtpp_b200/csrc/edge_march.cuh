@@ -12,7 +12,8 @@ static constexpr int kShortMaxP = 16; // P <= 16 -> thread marches alone; P >= 3
 // a block that meets a run of thousand-pixel edges otherwise becomes the kernel's critical path once the batch is split.
 static constexpr int kDeferP = 128;
 // kRound = 32-probe chunks issued together per round of the warp-wide march of a long edge
-template <int kRound = 1>
+// kPre = probe positions of a long edge sampled by its own lane before the warp-wide march (0 = none)
+template <int kRound = 1, int kPre = 16>
 __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, const float4 e, const bool valid, const MarchThresholds &mt,
                                                        uint32_t *defer_list = nullptr, unsigned *defer_count = nullptr,
                                                        uint32_t edge_index = 0) {
@@ -49,6 +50,23 @@ __device__ __forceinline__ unsigned warp_edges_verdict(const PlaneView &pl, cons
             if (!acc && P <= kShortMaxP) {
                 const float inv = rt_inv_pow2(P);
                 for (int j = 1; j < P; j++) acc |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)j, inv));
+            }
+        }
+    }
+    // Long edges (P >= 32) are marched by the whole warp below, one edge after the other, each round a dependent L2 latency.
+    // Most long edges through a cluttered map are blocked somewhere, so every lane first samples kPre of its OWN edge's probe
+    // positions, spread evenly over the edge and issued together (one latency for all 32 edges): a hit settles the edge — the
+    // verdict is the OR over the probe set, any subset may be looked at first — and only the survivors are marched in full.
+    if (kPre) {
+        const bool mine = valid && !acc && P > kShortMaxP;
+        if (__any_sync(full, mine)) {
+            if (mine) {
+                const float inv = rt_inv_pow2(P);
+                const int step = (P - 1) / kPre; // P >= 32 > kPre: step >= 1, positions 1 + i*step < P are distinct probe indices
+                bool hit = false;
+#pragma unroll
+                for (int i = 0; i < kPre; i++) hit |= rt_probe_interior(pl, e.x, e.y, e.z, e.w, __fmul_rn((float)(1 + i * step), inv));
+                acc = hit;
             }
         }
     }

@@ -31,6 +31,9 @@
 // — the exchange is part of the launch: no collective call, no second kernel.
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "edge_march.cuh"
 #include "nodes.cuh"
 #include "scan.cuh"
@@ -109,6 +112,10 @@ struct TickPlan {
     int edges_divisor = 0;
     bool usable = false;                  // applies, and at most RTPP_TICK_MAX_FAR of the edges are far
     long long far_edges = 0, valid_edges = 0;
+    int *group_cost = nullptr; // [n_groups] march steps a warp spends on the group (sum over j of the largest level among its lanes)
+    std::vector<int> h_cost; // host copy of group_cost (profiling dump)
+    int *item_group = nullptr; // [n_groups] groups by decreasing cost: the order they are dealt in (longest first, so that the
+                               // items drawn last are the short ones); a function of the plan alone: identical on every rank
     float2 *slot_xy = nullptr; // [n_slots] source coordinates (a stand-in inside the supercell for padding / sources the window cannot serve)
     uint32_t *far_mask = nullptr, *valid_mask = nullptr; // [n_slots] bit j: edge j is in the far list / exists
     int *far_off = nullptr;    // [n_slots + 1] first far-list entry of a slot
@@ -120,7 +127,7 @@ struct TickPlan {
     unsigned long long *stats = nullptr; // [3] far edges, valid edges, cells too large to rank
     uint32_t *row_scratch = nullptr, *tree_scratch = nullptr; // for the legacy packed-bit entry points / pageable host buffers
     size_t cap_sc = 0, cap_slot_id = 0, cap_slot_xy = 0, cap_far = 0, cap_valid = 0, cap_far_off = 0, cap_group = 0, cap_ent = 0,
-           cap_far_list = 0, cap_far_bits = 0, cap_row_scratch = 0, cap_tree_scratch = 0;
+           cap_far_list = 0, cap_far_bits = 0, cap_row_scratch = 0, cap_tree_scratch = 0, cap_group_cost = 0, cap_item_group = 0;
 };
 
 struct PlanGeom {
@@ -130,6 +137,7 @@ struct PlanGeom {
     int W, H, tilesX, tilesY;
     int k;
     float t3;            // squared length from which a march has more than 16 steps (MarchThresholds::t[3])
+    MarchThresholds mt;  // for the groups' cost estimate
 };
 
 __global__ void __launch_bounds__(256) plan_count_kernel(PlanGeom g, const int *__restrict__ cell_start, int *__restrict__ cnt) {
@@ -195,10 +203,11 @@ __global__ void __launch_bounds__(256) plan_entries_kernel(PlanGeom g, int n_gro
                                                           const int *__restrict__ knn_pos, const float2 *__restrict__ sxy, float2 *__restrict__ ent,
                                                           uint32_t *__restrict__ far_mask, uint32_t *__restrict__ valid_mask, int *__restrict__ far_cnt,
                                                           const int *__restrict__ far_off, float4 *__restrict__ far_list,
-                                                          unsigned long long *__restrict__ stats) {
+                                                          unsigned long long *__restrict__ stats, int *__restrict__ group_cost) {
     const int lane = threadIdx.x & 31;
     const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (grp >= n_groups) return;
+    int cost = 0;
     const int sc = group_sc[grp], sx = sc % g.scw, sy = sc / g.scw;
     const int slot = grp * 32 + lane, id = slot_id[slot];
     const int px0 = sx * kSCT * 32, py0 = sy * kSCT * 32; // supercell origin in pixels
@@ -230,9 +239,15 @@ __global__ void __launch_bounds__(256) plan_entries_kernel(PlanGeom g, int n_gro
                 if (pass) far_list[f++] = make_float4(real.x, real.y, d.x, d.y);
             }
         }
-        if (!pass) out[(size_t)j * 32] = e;
+        if (!pass) {
+            out[(size_t)j * 32] = e;
+            // the kernel marches step j to the deepest level any lane needs
+            const int P = (e.x != src.x || e.y != src.y) ? rt_march_P(g.mt, rt_sqlen(e.x, e.y, src.x, src.y)) : 0;
+            cost += 2 + __reduce_max_sync(0xffffffffu, P);
+        }
     }
     if (pass) return;
+    if (lane == 0 && group_cost) group_cost[grp] = cost;
     slot_xy[slot] = src;
     far_mask[slot] = fm;
     valid_mask[slot] = vm;
@@ -284,13 +299,14 @@ struct TickArgs {
     uint32_t *tree_bits;
     // rewire edges (the rest)
     int n_groups, k, scw;
-    const int *group_sc, *far_off;
+    const int *group_sc, *far_off, *item_group;
     const float2 *slot_xy, *ent;
     const uint32_t *far_mask, *valid_mask;
     uint32_t *row_bits;
     int stride, first;         // multi-GPU: this launch's shared item i is item i * stride + first of the tick
-    int parts;                 // bit 0: tree edges, bit 1: rewire edges, bit 3: skip the far merge (RTPP_TICK_PARTS, profiling only; default 3)
-    unsigned long long *timing; // RTPP_TICK_TIMING=1 (profiling only): per block {start, work done, exit} in globaltimer ns
+    int parts;                 // bit 0: tree edges, bit 1: rewire edges, bit 3: skip the far merge, bit 4: skip the peer row stores (RTPP_TICK_PARTS, profiling only; default 3)
+    unsigned long long *item_log; // RTPP_TICK_ITEMS=<file> with RTPP_TICK_TIMING (multi-GPU kernels): per item start (low 32 bits of ns) << 32 | duration ns
+    unsigned long long *timing; // RTPP_TICK_TIMING=1 (profiling only): per block {start, work done, exit} in globaltimer ns + its longest item (ns << 32 | item)
 };
 
 // One probe of the shared window.  q = packed (x, y) + 2^23 rounded toward zero: the low mantissa bits are the pixel.
@@ -358,7 +374,7 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
     if (a.timing && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        a.timing[3 * blockIdx.x] = t;
+        a.timing[4 * blockIdx.x] = t;
     }
     const unsigned wbase = (unsigned)__cvta_generic_to_shared(&win[warp][0]);
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[warp]);
@@ -379,6 +395,8 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
     // the slowest block 25 % behind the mean.)
     const unsigned n_warps = gridDim.x * kTickWarps;
     unsigned next_static = blockIdx.x * kTickWarps + warp;
+    unsigned long long t_item = 0;
+    unsigned prev_item = 0;
     for (;;) {
         unsigned item;
         if (next_static < a.n_static) {
@@ -388,6 +406,15 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
             if (lane == 0) t = atomicAdd(a.work, 1u) - a.work_base;
             item = a.n_static + __shfl_sync(full, t, 0);
             if (item >= a.n_items) break;
+        }
+        if (kPeers && a.timing) { // profiling (multi-GPU launches): the longest item of the block (closed at the next draw)
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (lane == 0 && t_item) {
+                atomicMax(a.timing + 4 * blockIdx.x + 3, ((t - t_item) << 32) | prev_item);
+                if (a.item_log) a.item_log[prev_item] = (t_item << 32) | ((t - t_item) & 0xffffffffull);
+            }
+            t_item = t, prev_item = item;
         }
         if (item < (unsigned)a.n_far_words) {
             // far list: every rank checks all of it; window warps wait for these words (taken first, and waiting for nobody)
@@ -406,7 +433,7 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
         if (!(a.parts & 2)) continue;
         {
             {
-                const size_t grp = sh - a.n_tree_words;
+                const size_t grp = a.item_group ? (size_t)a.item_group[sh - a.n_tree_words] : sh - a.n_tree_words;
                 const int sc = a.group_sc[grp];
                 if (sc != cur_sc) { // warp-uniform: bring the supercell's window in
                     cur_sc = sc;
@@ -524,7 +551,7 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
                 }
                 row &= vmask;
                 a.row_bits[slot] = row;
-                if (kPeers) {
+                if (kPeers && !(a.parts & 16)) {
 #pragma unroll
                     for (int r = 0; r < RTPP_MAX_PEERS - 1; r++)
                         if (r < peers.n) peers.row[r][slot] = row;
@@ -533,11 +560,19 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
         }
     }
     if (a.timing) {
+        if (kPeers) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (lane == 0 && t_item) {
+                atomicMax(a.timing + 4 * blockIdx.x + 3, ((t - t_item) << 32) | prev_item);
+                if (a.item_log) a.item_log[prev_item] = (t_item << 32) | ((t - t_item) & 0xffffffffull);
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            a.timing[3 * blockIdx.x + 1] = t;
+            a.timing[4 * blockIdx.x + 1] = t;
         }
     }
     if (kPeers) {
@@ -545,18 +580,23 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
         // peers (their flag slot `rank` := epoch) and waits until every peer has signalled this rank.  The wait is bounded:
         // on a timeout the result buffers are filled with "blocked" (fail closed) and the sticky timeout counter is raised,
         // which rtpp_peer_status reports.
-        __threadfence_system();
+        // (one fence per block: the barrier orders the block's stores before thread 0's fence, which is cumulative)
         __syncthreads();
         __shared__ int is_last;
         int *mine = peers.flags[peers.rank];
-        if (threadIdx.x == 0) is_last = atomicAdd(mine + kFlagDone, 1) == (int)gridDim.x - 1;
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            is_last = atomicAdd(mine + kFlagDone, 1) == (int)gridDim.x - 1;
+        }
         __syncthreads();
         if (is_last) {
-            __threadfence_system();
+            // every block published its stores system-wide before it counted itself; the signalling threads order that count (read by
+            // thread 0, handed over by the barrier) before their flag store at system scope.  Nothing has to be ordered after the
+            // flag store on this side.
             bool timed_out = false;
             if (threadIdx.x < (unsigned)peers.world && (int)threadIdx.x != peers.rank) {
-                *(volatile int *)(peers.flags[threadIdx.x] + peers.rank) = peers.epoch;
                 __threadfence_system();
+                *(volatile int *)(peers.flags[threadIdx.x] + peers.rank) = peers.epoch;
                 volatile int *src = mine + threadIdx.x;
                 long long it = 0;
                 while (*src < peers.epoch && it < peers.spin_limit) {
@@ -566,7 +606,6 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
                 timed_out = *src < peers.epoch;
             }
             const int any_timeout = __syncthreads_or(timed_out);
-            __threadfence_system();
             if (any_timeout) {
                 for (size_t i = threadIdx.x; i < peers.row_words; i += blockDim.x) peers.own_row[i] = 0xffffffffu;
                 for (size_t i = threadIdx.x; i < peers.tree_words; i += blockDim.x) peers.own_tree[i] = 0xffffffffu;
@@ -578,7 +617,7 @@ __global__ void __launch_bounds__(32 * kTickWarps, 4) tick_check_kernel(const Ti
     if (a.timing && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        a.timing[3 * blockIdx.x + 2] = t;
+        a.timing[4 * blockIdx.x + 2] = t;
     }
 }
 
@@ -618,7 +657,7 @@ void rtpp_tick_plan_free(NodeStore *s) {
     if (!p) return;
     cudaFree(p->sc_start), cudaFree(p->group_sc), cudaFree(p->slot_id), cudaFree(p->slot_of_id), cudaFree(p->slot_xy);
     cudaFree(p->far_mask), cudaFree(p->valid_mask), cudaFree(p->far_off), cudaFree(p->ent), cudaFree(p->far_list), cudaFree(p->far_bits);
-    cudaFree(p->far_done), cudaFree(p->stats), cudaFree(p->row_scratch), cudaFree(p->tree_scratch);
+    cudaFree(p->far_done), cudaFree(p->stats), cudaFree(p->row_scratch), cudaFree(p->tree_scratch), cudaFree(p->group_cost), cudaFree(p->item_group);
     delete p;
     s->plan = nullptr;
 }
@@ -717,13 +756,15 @@ static int plan_build(rtpp_ctx *ctx, int divisor) {
     plan_geom(ctx, &g);
     MarchThresholds mt;
     rtpp_march_thresholds(divisor, &mt);
-    g.t3 = mt.t[3];
+    g.t3 = mt.t[3], g.mt = mt;
     const size_t n_slots = (size_t)p->n_slots;
     if ((rc = plan_grow(ctx, &p->slot_xy, &p->cap_slot_xy, n_slots + 32))) return rc;
     if ((rc = plan_grow(ctx, &p->far_mask, &p->cap_far, n_slots + 32))) return rc;
     if ((rc = plan_grow(ctx, &p->valid_mask, &p->cap_valid, n_slots + 32))) return rc;
     if ((rc = plan_grow(ctx, &p->far_off, &p->cap_far_off, n_slots + 32))) return rc;
     if ((rc = plan_grow(ctx, &p->ent, &p->cap_ent, n_slots * s->knn_k + 32))) return rc;
+    if ((rc = plan_grow(ctx, &p->group_cost, &p->cap_group_cost, (size_t)p->n_groups + 32))) return rc;
+    if ((rc = plan_grow(ctx, &p->item_group, &p->cap_item_group, (size_t)p->n_groups + 32))) return rc;
     // per-slot far counts live in far_off until the scan turns them into offsets; the scan's block totals need their own
     // scratch sized for n_slots elements (n_slots can exceed the node capacity the hash's scan_totals is sized for)
     void *totals = nullptr;
@@ -731,7 +772,7 @@ static int plan_build(rtpp_ctx *ctx, int divisor) {
     RTPP_CK(ctx, cudaMemsetAsync(p->stats, 0, 32, ctx->stream));
     const int eb = (p->n_groups + 7) / 8;
     plan_entries_kernel<<<eb, 256, 0, ctx->stream>>>(g, p->n_groups, 0, p->group_sc, p->slot_id, s->xy, p->slot_xy, s->knn_pos, s->sxy, p->ent, p->far_mask,
-                                                     p->valid_mask, p->far_off, nullptr, nullptr, p->stats);
+                                                     p->valid_mask, p->far_off, nullptr, nullptr, p->stats, p->group_cost);
     RTPP_LAUNCHED(ctx);
     if ((rc = rtpp_exclusive_scan(ctx, p->far_off, (int)n_slots, p->far_off, p->far_off, (int *)totals))) return rc;
     unsigned long long st[2] = {0, 0};
@@ -742,8 +783,18 @@ static int plan_build(rtpp_ctx *ctx, int divisor) {
     if ((rc = plan_grow(ctx, &p->far_bits, &p->cap_far_bits, (size_t)p->far_edges / 32 + 8))) return rc;
     if (p->far_edges > 0) {
         plan_entries_kernel<<<eb, 256, 0, ctx->stream>>>(g, p->n_groups, 1, p->group_sc, p->slot_id, s->xy, p->slot_xy, s->knn_pos, s->sxy, p->ent,
-                                                         p->far_mask, p->valid_mask, nullptr, p->far_off, p->far_list, p->stats);
+                                                         p->far_mask, p->valid_mask, nullptr, p->far_off, p->far_list, p->stats, nullptr);
         RTPP_LAUNCHED(ctx);
+    }
+    { // deal order: longest groups first (ties by index: the same permutation on every rank)
+        std::vector<int> &cost = p->h_cost, order((size_t)p->n_groups);
+        cost.resize((size_t)p->n_groups);
+        RTPP_CK(ctx, cudaMemcpyAsync(cost.data(), p->group_cost, cost.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < p->n_groups; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+        RTPP_CK(ctx, cudaMemcpyAsync(p->item_group, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     // a plan whose edges mostly leave the window (a sparse tree: k-NN radius beyond the 32-pixel halo) is not worth running
     static const double max_far = getenv("RTPP_TICK_MAX_FAR") ? atof(getenv("RTPP_TICK_MAX_FAR")) : 0.25;
@@ -786,9 +837,11 @@ static void tick_fill_args(rtpp_ctx *ctx, const PlaneView &pv, int divisor, uint
     a->tree_bits = d_tree_bits;
     a->n_groups = p->n_groups, a->k = p->order_k, a->scw = p->scw;
     a->group_sc = p->group_sc, a->far_off = p->far_off, a->slot_xy = p->slot_xy, a->ent = p->ent;
+    static const bool lpt = !(getenv("RTPP_TICK_LPT") && atoi(getenv("RTPP_TICK_LPT")) == 0);
+    a->item_group = lpt ? p->item_group : nullptr;
     a->far_mask = p->far_mask, a->valid_mask = p->valid_mask;
     a->row_bits = d_row_bits;
-    a->stride = world, a->first = rank, a->parts = parts, a->timing = nullptr;
+    a->stride = world, a->first = rank, a->parts = parts, a->timing = nullptr, a->item_log = nullptr;
     const size_t shared = (size_t)a->n_tree_words + (size_t)a->n_groups;
     const size_t mine = shared > (size_t)rank ? (shared - rank + world - 1) / world : 0;
     a->n_items = (unsigned)((size_t)a->n_far_words + mine);
@@ -811,25 +864,51 @@ static int tick_timing_begin(rtpp_ctx *ctx, int grid, TickArgs *a) {
     static const bool on = getenv("RTPP_TICK_TIMING") != nullptr;
     if (!on) return RTPP_OK;
     void *d = nullptr;
-    int rc = rtpp_scratch(ctx, 2, (size_t)grid * 24, &d);
+    int rc = rtpp_scratch(ctx, 2, (size_t)grid * 32, &d);
     if (rc) return rc;
+    RTPP_CK(ctx, cudaMemsetAsync(d, 0, (size_t)grid * 32, ctx->stream));
     a->timing = (unsigned long long *)d;
+    if (getenv("RTPP_TICK_ITEMS")) {
+        if ((rc = rtpp_scratch(ctx, 3, (size_t)(a->n_items + 1) * 8, &d))) return rc;
+        RTPP_CK(ctx, cudaMemsetAsync(d, 0, (size_t)(a->n_items + 1) * 8, ctx->stream));
+        a->item_log = (unsigned long long *)d;
+    }
     return RTPP_OK;
 }
 static int tick_timing_end(rtpp_ctx *ctx, int grid, TickArgs *a) {
     if (!a->timing) return RTPP_OK;
-    std::vector<unsigned long long> h((size_t)grid * 3);
+    std::vector<unsigned long long> h((size_t)grid * 4);
     RTPP_CK(ctx, cudaMemcpyAsync(h.data(), a->timing, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    unsigned long long t0 = ~0ull, s1 = 0, w0 = ~0ull, w1 = 0, e1 = 0;
-    double wsum = 0;
+    unsigned long long t0 = ~0ull, s1 = 0, w0 = ~0ull, w1 = 0, e1 = 0, longest = 0;
+    double wsum = 0, lsum = 0;
     for (int b = 0; b < grid; b++) {
-        t0 = std::min(t0, h[3 * b]), s1 = std::max(s1, h[3 * b]);
-        w0 = std::min(w0, h[3 * b + 1]), w1 = std::max(w1, h[3 * b + 1]), e1 = std::max(e1, h[3 * b + 2]);
+        t0 = std::min(t0, h[4 * b]), s1 = std::max(s1, h[4 * b]);
+        w0 = std::min(w0, h[4 * b + 1]), w1 = std::max(w1, h[4 * b + 1]), e1 = std::max(e1, h[4 * b + 2]);
+        longest = std::max(longest, h[4 * b + 3]), lsum += (double)(h[4 * b + 3] >> 32);
     }
-    for (int b = 0; b < grid; b++) wsum += (double)(h[3 * b + 1] - t0);
-    fprintf(stderr, "[rtpp tick timing] blocks %d items %u: last start +%.1f us, work done first +%.1f mean +%.1f last +%.1f us, exit +%.1f us\n", grid, a->n_items,
-            (s1 - t0) * 1e-3, (w0 - t0) * 1e-3, wsum / grid * 1e-3, (w1 - t0) * 1e-3, (e1 - t0) * 1e-3);
+    for (int b = 0; b < grid; b++) wsum += (double)(h[4 * b + 1] - t0);
+    if (a->item_log) { // raw dump for tools/tick_items.py: header, per-item records, the group item codes, the groups' cost estimates
+        TickPlan *p = ctx->nodes->plan;
+        std::vector<unsigned long long> it((size_t)a->n_items);
+        RTPP_CK(ctx, cudaMemcpyAsync(it.data(), a->item_log, it.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        const int ncodes = a->item_group ? p->n_groups : 0;
+        std::vector<int> codes((size_t)ncodes);
+        if (ncodes) RTPP_CK(ctx, cudaMemcpyAsync(codes.data(), a->item_group, codes.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        RTPP_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (FILE *f = fopen(getenv("RTPP_TICK_ITEMS"), "wb")) {
+            const long long hdr[8] = {(long long)a->n_items, a->n_far_words, a->n_tree_words, a->stride, a->first, ncodes, (long long)p->h_cost.size(), (long long)a->n_static};
+            fwrite(hdr, 8, 8, f);
+            fwrite(it.data(), 8, it.size(), f);
+            fwrite(codes.data(), 4, codes.size(), f);
+            fwrite(p->h_cost.data(), 4, p->h_cost.size(), f);
+            fclose(f);
+        }
+    }
+    const unsigned li = (unsigned)longest;
+    const char *kind = li < (unsigned)a->n_far_words ? "far word" : ((size_t)(li - a->n_far_words) * a->stride + a->first < (size_t)a->n_tree_words ? "tree word" : "window group");
+    fprintf(stderr, "[rtpp tick timing] blocks %d items %u: last start +%.1f us, work done first +%.1f mean +%.1f last +%.1f us, exit +%.1f us; longest item %.1f us (item %u, %s), mean of the blocks' longest %.1f us\n", grid, a->n_items,
+            (s1 - t0) * 1e-3, (w0 - t0) * 1e-3, wsum / grid * 1e-3, (w1 - t0) * 1e-3, (e1 - t0) * 1e-3, (longest >> 32) * 1e-3, li, kind, lsum / grid * 1e-3);
     return RTPP_OK;
 }
 
