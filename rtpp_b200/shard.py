@@ -37,6 +37,16 @@ def word_range(n_edges, rank, world_size):
     return w0, w1 - w0, e0, max(0, e1 - e0)
 
 
+def tick_items_of_rank(n_tree_words, n_groups, rank, world_size):
+    """The shared work items of ONE tick that `rank` takes in rtpp_tick_check_allgather_dev (csrc/tick.cu: shared item s is a tree
+    word for s < n_tree_words, else position s - n_tree_words of the plan's deal order; rank r takes s = r, r + world, ...).
+    Host-side mirror of the kernel's dealing, for tests and for sizing: returns (tree_words, group_positions) as ranges."""
+    shared = n_tree_words + n_groups
+    mine = range(rank, shared, world_size)
+    first_group = next((i for i, s in enumerate(mine) if s >= n_tree_words), len(mine)) if len(mine) else 0
+    return mine[:first_group], range(mine[first_group] - n_tree_words, n_groups, world_size) if first_group < len(mine) else range(0)
+
+
 def all_gather_words(local_words, n_edges):
     """All-gather the per-rank verdict words (int32 tensor on the collective's device) into the
     full word vector of the batch."""

@@ -39,3 +39,36 @@ def test_tie_rule_is_lowest_index_first(oracle):
     pts = np.array([[10, 10], [12, 10], [8, 10], [10, 12], [10, 8], [10, 10]], np.float32)
     idx, d2, cnt = oracle.knn(pts, np.array([[10.0, 10.0]]), 4)
     assert idx.tolist() == [[0, 5, 1, 2]] and d2[0].tolist() == [0.0, 0.0, 4.0, 4.0]
+
+
+def _tie_exposure(oracle, pts, q, k):
+    """Queries whose answer depends on a tie rule CGAL leaves unspecified (Orthogonal_k_neighbor_search sorts by distance
+    only): 'set' = the k-th and (k+1)-th nearest are equally far, so WHICH nodes are returned is the rule's choice;
+    'order' = two returned neighbours are equally far, so only their order is."""
+    idx, d2, cnt = oracle.knn(pts, q, k + 1)
+    full = cnt == k + 1
+    set_amb = full & (d2[:, k - 1] == d2[:, k])
+    order_amb = (np.diff(d2[:, :k], axis=1) == 0).any(1)
+    return int(set_amb.sum()), int((order_amb & ~set_amb).sum())
+
+
+def test_knn_tie_exposure_is_quantified(oracle):
+    """k-NN parity is pinned to the published definition, not to a CGAL run (CGAL needs Boost, absent here), so
+    the exposure to CGAL's unspecified tie order is counted instead of assumed away.  Planner workloads — binary32 sample
+    points queried with their own coordinates or with rand()-drawn points — have NO set-ambiguous query in 20 000 and a
+    handful of order-only ties at most; an integer lattice, the adversarial case the GPU tests also cover, is ambiguous for
+    most queries, and there the (d2, id) rule of this repository is what both the oracle and the kernels implement."""
+    rng = np.random.default_rng(12)
+    pts = _pts(rng, 100_000, 4096, 4096)
+    q = np.concatenate([pts[:10_000].astype(np.float64), rng.random((10_000, 2)) * 4096])
+    s, o = _tie_exposure(oracle, pts, q, 25)
+    assert s == 0 and o <= 5, (s, o)
+    # samples on integer pixels (rand() % shape, RTFMT.cpp:401-405): equal integer d2 are common — order ties, and set ties too
+    ipts = np.unique(rng.integers(0, 1000, (20_000, 2)), axis=0).astype(np.float32)
+    si, oi = _tie_exposure(oracle, ipts, ipts[:2000].astype(np.float64), 25)
+    assert si + oi > 500   # this IS the exposed case: RT-FMT's static 25-NN table on integer samples
+    xs, ys = np.meshgrid(np.arange(0, 64, dtype=np.float32) * 4, np.arange(0, 64, dtype=np.float32) * 4)
+    lat = np.stack([xs.ravel(), ys.ravel()], 1)
+    sl, ol = _tie_exposure(oracle, lat, lat[:1000].astype(np.float64), 25)
+    assert sl + ol > 900 and sl > 100   # (k = 25 is exactly the 5 x 5 block of an interior lattice point: set ties come from the border)
+    print(f"tie exposure: float samples set {s} order {o}; integer samples set {si} order {oi}; lattice set {sl} order {ol}")

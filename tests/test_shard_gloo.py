@@ -78,3 +78,20 @@ def test_partitions_cover_everything_once():
             assert tot == n
             ids = sorted(i for r in range(ws) for i in shard.instance_ids(n % 1000, r, ws))
             assert ids == list(range(n % 1000))
+
+
+def test_tick_items_are_dealt_once_over_the_ranks():
+    """The dealing of one tick's shared items (tree words, then window groups) over the ranks of rtpp_tick_check_allgather_dev:
+    every item goes to exactly one rank and the shares differ by at most one item."""
+    from rtpp_b200 import shard
+
+    for ntw, ng in ((0, 0), (1, 0), (0, 5), (31250, 32896), (7, 3), (1000, 1)):
+        for ws in (1, 2, 3, 4, 8):
+            tree, groups, sizes = [], [], []
+            for r in range(ws):
+                t, g = shard.tick_items_of_rank(ntw, ng, r, ws)
+                tree += list(t)
+                groups += list(g)
+                sizes.append(len(t) + len(g))
+            assert sorted(tree) == list(range(ntw)) and sorted(groups) == list(range(ng))
+            assert max(sizes) - min(sizes) <= 1
