@@ -533,7 +533,9 @@ def main():
 
     extras = {}
     if not args.no_extras:
-        extras = measure_extras(wl, torch, sweep, roofline_formula=(16 + 4 * probes_per_edge + 0.125), peak=peak, cpu_verdicts=cpu_verdicts)
+        l2g = roofline.get("same_run_peaks", {}).get("l2_sector_gather_gbs") if isinstance(roofline.get("same_run_peaks"), dict) else None
+        extras = measure_extras(wl, torch, sweep, roofline_formula=(16 + 4 * probes_per_edge + 0.125), peak=peak, cpu_verdicts=cpu_verdicts,
+                                l2_gather_gbs=l2g)
         if sharded_batch:
             extras["sharded_edge_batch"] = sharded_batch
 
@@ -552,7 +554,7 @@ def main():
     return 0
 
 
-def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdicts=None):
+def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdicts=None, l2_gather_gbs=None):
     """Neighbour queries/s and tick latencies on the resident C4 state (outside the timed region)."""
     ctx = wl.ctx
     out = {}
@@ -626,7 +628,7 @@ def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdi
     out.update(measure_cdrt(ctx))
     out.update(measure_amrrt(ctx))
     try:  # last: its edge batches load GAME0 into the ctx's planes (nothing after it uses the C4 planes)
-        out.update(measure_c1(ctx, torch, timed, peak or 6650.0))
+        out.update(measure_c1(ctx, torch, timed, peak or 6650.0, l2_gather_gbs))
     except Exception as exc:  # an extra must not cost the bench line
         out["c1_rtrrt_game0"] = {"error": repr(exc)}
     return out
@@ -678,6 +680,9 @@ def measure_dropin_class(ticks=24, dt=5000):
         pl.close()
     if len(trees) == 2:
         out["trees_match"] = bool(all(np.array_equal(a.view(np.uint8), b.view(np.uint8)) for a, b in zip(trees[0], trees[1])))
+    out["reference_class_note"] = ("the reference class runs on stand-ins for its two absent libraries: brute-force exact k-NN in place of CGAL's "
+                                   "kd-tree (rebuilt on the first query after every insert in the original) and a cv::Mat shim; at the ~500 nodes of this "
+                                   "scenario the stand-in k-NN is not slower than a rebuilt kd-tree would be, but this is not a CGAL timing")
     return out
 
 
@@ -806,7 +811,7 @@ def measure_fmt(ctx):
     return {"rtfmt_1e5": cr.c3_rtfmt(ctx, orc, check_rounds=40_000)}
 
 
-def measure_c1(ctx, torch, timed, peak):
+def measure_c1(ctx, torch, timed, peak, l2_gather_gbs=None):
     """BASELINE configs[0] at its stated size: RT-RRT* on GAME0 with 20 000 injected samples (tree compared with
     the CPU port after the first 3000 ticks; the full run is compared in tests/test_configs_gpu.py), then the 2^24 (node, one of
     its 25-NN) edge batch and the 2^20 long-edge batch through rtpp_edges_check_dev (E1: divisor 5, S|D), each with its own
@@ -819,6 +824,12 @@ def measure_c1(ctx, torch, timed, peak):
     batches = cr.c1_edge_batches(ctx, orc, tree[0], S, check=16, timed=lambda fn: timed(fn, 10))
     for r in batches.values():
         r["roofline_frac"] = r["algorithmic_GBs"] / peak
+        # SURVEY 8(d)'s second form for batches whose probes dominate: one 32-byte sector per probe against the L2 sector-gather rate
+        # measured in this run (rtpp_measure_peaks); at 8.6 (k-NN edges) and 204 (long edges) probes per edge this, not the 16 B of
+        # end points, is what the explicit-list kernel is up against
+        r["l2_sector_GBs"] = r["edges_per_s"] * r["mean_probes_per_edge"] * 32 / 1e9
+        if l2_gather_gbs:
+            r["l2_form_frac"] = r["l2_sector_GBs"] / l2_gather_gbs
     out["edge_batches"] = batches
     return {"c1_rtrrt_game0": out}
 
