@@ -615,22 +615,21 @@ def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdi
     out["rewire_to_quiescence_ms"] = best
     out["rewire_sweeps"] = sweeps
     out["rewire_schedule"] = "work list by cost bucket (near-far), blocks chase their improvements through shared-memory queues; wall time of the host call, best of 3"
-    out.update(measure_replanning(ctx, sweep))
-    try:
-        out["dropin_rtrrt_class"] = measure_dropin_class()
-    except Exception as exc:  # an extra must not cost the bench line
-        out["dropin_rtrrt_class"] = {"error": repr(exc)}
-    out.update(measure_fmt(ctx))
-    try:
-        out.update(measure_fmt_sweep(ctx))
-    except Exception as exc:  # an extra must not cost the bench line
-        out["rtfmt_sweep"] = {"error": repr(exc)}
-    out.update(measure_cdrt(ctx))
-    out.update(measure_amrrt(ctx))
-    try:  # last: its edge batches load GAME0 into the ctx's planes (nothing after it uses the C4 planes)
-        out.update(measure_c1(ctx, torch, timed, peak or 6650.0, l2_gather_gbs))
-    except Exception as exc:  # an extra must not cost the bench line
-        out["c1_rtrrt_game0"] = {"error": repr(exc)}
+
+    def leg(key, fn):  # an extra must not cost the bench line: a failing leg reports its error under its own key
+        try:
+            out.update(fn())
+        except Exception as exc:
+            out[key] = {"error": repr(exc)}
+
+    leg("replan", lambda: measure_replanning(ctx, sweep))
+    leg("dropin_rtrrt_class", lambda: {"dropin_rtrrt_class": measure_dropin_class()})
+    leg("rtfmt_1e5", lambda: measure_fmt(ctx))
+    leg("rtfmt_sweep", lambda: measure_fmt_sweep(ctx))
+    leg("cdrt", lambda: measure_cdrt(ctx))
+    leg("amrrt", lambda: measure_amrrt(ctx))
+    # last: its edge batches load GAME0 into the ctx's planes (nothing after it uses the C4 planes)
+    leg("c1_rtrrt_game0", lambda: measure_c1(ctx, torch, timed, peak or 6650.0, l2_gather_gbs))
     return out
 
 

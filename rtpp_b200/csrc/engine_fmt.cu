@@ -629,7 +629,10 @@ int rtpp_fmt_create(rtpp_ctx *ctx, int n_instances, int node_capacity, int cell_
     rc |= fmt_alloc(e, &v.sid, C), rc |= fmt_alloc(e, &v.cell_of, C), rc |= fmt_alloc(e, &v.cell_start, G), rc |= fmt_alloc(e, &v.cursor, G);
     rc |= fmt_alloc(e, &v.child_start, N * (node_capacity + 1)), rc |= fmt_alloc(e, &v.children, C), rc |= fmt_alloc(e, &v.frontier, 2 * C);
     rc |= fmt_alloc(e, &v.path, N * v.path_cap);
-    if (rc) return RTPP_ERR_NOMEM;
+    if (rc) {
+        rtpp_fmt_destroy(e); // frees what was allocated (cudaFree(nullptr) is a no-op)
+        RTPP_FAIL(ctx, RTPP_ERR_NOMEM, "engine buffers do not fit the device");
+    }
     *out = e;
     return RTPP_OK;
 }
