@@ -853,6 +853,15 @@ static void tick_fill_args(rtpp_ctx *ctx, const PlaneView &pv, int divisor, uint
     a->work_base = p->work_base;
     p->work_base += (a->n_items - a->n_static) + n_warps; // every warp draws one ticket past the end
 }
+// Last line of defence before a launch: every pointer the kernel dereferences unconditionally must be set.  (A refactoring once
+// dropped five assignments of tick_fill_args; the kernels ran on uninitialised pointers and faulted every GPU of a 4-GPU box.)
+static int tick_args_ok(rtpp_ctx *ctx, const TickArgs &a) {
+    const bool ok = a.pl.w && a.work && a.far_done && a.xy && a.cp && a.tree_bits && a.row_bits && a.group_sc && a.far_off && a.slot_xy && a.ent &&
+                    a.far_mask && a.valid_mask && (a.n_far == 0 || (a.far_list && a.far_bits)) && a.stride >= 1 && a.first >= 0 && a.first < a.stride &&
+                    a.k >= 1 && a.k <= 32 && a.n >= 1 && a.one == 1.0f;
+    if (!ok) RTPP_FAIL(ctx, RTPP_ERR_STATE, "internal: incomplete tick launch arguments");
+    return RTPP_OK;
+}
 static bool tick_use_bulk() {
     static const bool bulk = !(getenv("RTPP_TICK_BULK") && atoi(getenv("RTPP_TICK_BULK")) == 0);
     return bulk;
@@ -922,11 +931,12 @@ int rtpp_tick_window_run(rtpp_ctx *ctx, int divisor, int plane_mask, uint32_t *d
     if (rc) return rc;
     TickPlan *p = ctx->nodes->plan;
     if (!p->usable) return RTPP_OK;
-    TickArgs a;
+    TickArgs a{}; // zero first: a field the filler forgets is then null and caught by tick_args_ok, not a wild pointer
     const int grid = tick_grid(ctx, false, tick_use_bulk());
     tick_fill_args(ctx, pv, divisor, d_tree_bits, d_row_bits, 0, 1, grid, &a);
     TickPeers none;
     memset(&none, 0, sizeof(none));
+    if ((rc = tick_args_ok(ctx, a))) return rc;
     rc = tick_timing_begin(ctx, grid, &a);
     if (rc) return rc;
     if (tick_use_bulk()) tick_check_kernel<false, true><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, none);
@@ -1029,7 +1039,7 @@ int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, ui
     TickPlan *p = s->plan;
     if (!p->usable) RTPP_FAIL(ctx, RTPP_ERR_STATE, "the windowed tick plan does not apply to this node store");
     if (!p->canonical) RTPP_FAIL(ctx, RTPP_ERR_STATE, "a hash cell holds too many nodes for a rank-independent slot order");
-    TickArgs a;
+    TickArgs a{}; // zero first: a field the filler forgets is then null and caught by tick_args_ok, not a wild pointer
     const int grid = tick_grid(ctx, true, tick_use_bulk());
     tick_fill_args(ctx, pv, divisor, tree_all[rank], row_all[rank], rank, world, grid, &a);
     TickPeers peers;
@@ -1042,6 +1052,9 @@ int rtpp_tick_check_allgather_dev(rtpp_ctx *ctx, int divisor, int plane_mask, ui
     peers.own_row = row_all[rank], peers.own_tree = tree_all[rank];
     peers.row_words = (size_t)p->n_slots, peers.tree_words = ((size_t)(s->n - 1) + 31) / 32;
     peers.spin_limit = (long long)(ctx->peer_timeout_ms * 1e6 / 100.0) + 1; // one poll is ~100 ns (64 ns sleep + a system-scope load)
+    for (int r = 0; r < world; r++)
+        if (!tree_all[r] || !row_all[r] || !flags_all[r]) RTPP_FAIL(ctx, RTPP_ERR_INVALID, "a rank's result / flag buffer is NULL");
+    if ((rc = tick_args_ok(ctx, a))) return rc;
     rc = tick_timing_begin(ctx, grid, &a);
     if (rc) return rc;
     if (tick_use_bulk()) tick_check_kernel<true, true><<<grid, 32 * kTickWarps, 0, ctx->stream>>>(a, peers);
