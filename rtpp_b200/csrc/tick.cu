@@ -20,15 +20,19 @@
 // march finer than 16 steps for the plan's divisor — are known when the plan is built: they form a static FAR list (explicit
 // end points) checked with the general warp routine of edges.cu by the same launch; a window warp picks their verdict bits
 // up when it writes its rows.  The tree edges (parent -> child, any length) take the same general routine.
-// The launch is ONE resident wave of persistent warps drawing work items from a queue (one atomicAdd per item): the far
-// list's 32-edge words first (so nobody waits for them), then the tree's words (a hub's thousand-pixel edges sit at its
-// head and are marched warp-wide), then the window groups — no block-sized tail and no warp idling inside a block.  The first
-// four fifths of the items are dealt round-robin; the rest is drawn from a counter by whichever warp is free (item times differ).
+// The launch is ONE resident wave of persistent warps over one list of work items: the far list's 32-edge words first (so
+// nobody waits for them), then the tree's words (long edges are pre-filtered by their own lane, see edge_march.cuh, and the
+// survivors marched warp-wide), then the window groups, longest first (a cost estimate computed with the plan) — no block-sized
+// tail and no warp idling inside a block.  The first four fifths of the items are dealt round-robin (no atomic); the rest is
+// drawn from a counter by whichever warp is free, because item times differ.
 //
 // Multi-GPU (SURVEY 8(e) grain 2): with kPeers the tree words and window groups of ONE tick are dealt round-robin over the
 // ranks (the small far list is checked by every rank); a warp stores its verdict words into every rank's result buffers
-// over NVLink (CUDA IPC mappings), and the LAST block of the launch to retire signals the peers and waits for their signals
-// — the exchange is part of the launch: no collective call, no second kernel.
+// over NVLink (CUDA IPC mappings); every block publishes its stores with one system-scope fence and counts itself, and the
+// LAST block of the launch to retire signals the peers and waits — bounded, failing closed — for their signals: the
+// exchange is part of the launch, no collective call, no second kernel.
+// Profiling hooks (off unless the environment asks): RTPP_TICK_TIMING (per-block time stamps, longest item), RTPP_TICK_ITEMS
+// (per-item log for tools/tick_items.py), RTPP_TICK_PARTS / _STATIC_PCT / _LPT / _BULK (ablations).
 #include <stdlib.h>
 
 #include <algorithm>
