@@ -60,3 +60,34 @@ def test_product_never_touches_the_oracle():
 def test_sources_build_for_sm100a_only():
     mk = open(os.path.join(ROOT, "rtpp_b200", "csrc", "Makefile")).read()
     assert "arch=compute_100a,code=sm_100a" in mk and "-lineinfo" in mk and "-fmad=false" in mk
+
+
+def test_every_entry_point_rejects_a_null_handle():
+    """Error behaviour of the ABI: no exceptions, no crashes — every entry point whose first parameter is a
+    handle returns a negative status when it is NULL (all other arguments zero), without touching CUDA.  Run in a child process
+    so that a missing guard shows up as a failed test, not as a dead test session."""
+    import sys
+
+    src = open(os.path.join(ROOT, "include", "rtpp_gpu.h")).read()
+    decls = re.findall(r"RTPP_API\s+([\w\s\*]+?)\b(rtpp_\w+)\s*\(([^;]*?)\)\s*;", src, re.S)
+    probes = []
+    for ret, name, args in decls:
+        a = [x for x in args.replace("\n", " ").split(",") if x.strip() and x.strip() != "void"]
+        if ret.strip() == "int" and a and re.search(r"rtpp_\w+\s*\*", a[0]):
+            probes.append((name, len(a)))
+    assert len(probes) >= 80
+    import rtpp_b200
+
+    code = (
+        "import ctypes as C, sys\n"
+        f"lib = C.CDLL({rtpp_b200.lib_path()!r})\n"
+        f"for name, n in {probes!r}:\n"
+        "    fn = getattr(lib, name); fn.restype = C.c_int\n"
+        "    rc = fn(*([C.c_void_p(0)] * n))\n"
+        "    print(name, rc, flush=True)\n"
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    seen = dict(line.split() for line in out.stdout.strip().split("\n") if line)
+    assert out.returncode == 0, f"crashed after {list(seen)[-1] if seen else 'nothing'}: {out.stderr[-300:]}"
+    bad = {k: v for k, v in seen.items() if int(v) >= 0}
+    assert not bad and len(seen) == len(probes), bad
