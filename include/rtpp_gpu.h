@@ -289,7 +289,12 @@ RTPP_API int rtpp_engine_set_am_inputs(rtpp_engine *e, const int32_t *rand, cons
 RTPP_API int rtpp_engine_read_stats(rtpp_engine *e, long long *out16);
 RTPP_API int rtpp_engine_read_tree(rtpp_engine *e, int inst, int max_nodes, float *xy, int32_t *parent, float *cost,
                                    uint8_t *collision, int *n_out);
-/* path of the last GetPath: node ids root..entry then -2 for the goal point; *len_out = length */
+/* path of the last GetPath (RTRRT.cpp:356-437), *len_out = length:
+ *   path_collision = 0: node ids root..entry, then -2 for the goal point itself (cost = path_cost);
+ *   path_collision = 1, path_len > 0: no collision-free entry to the goal exists — the reference's fallback (:401-437): the chain
+ *     root..x of the node x nearest the goal among those within five collision-free levels of the root; no goal point in it,
+ *     path_cost = 3.4e38 as the reference returns;
+ *   path_len = 0 with path_cost = 2.4e38: a chain longer than 2000 nodes (the reference clears the path). */
 RTPP_API int rtpp_engine_read_path(rtpp_engine *e, int inst, int max_len, int32_t *ids, int *len_out);
 
 /* RT-FMT engine (one warp per planner instance, sequential-exact):
@@ -316,6 +321,8 @@ RTPP_API int rtpp_fmt_read_stats(rtpp_fmt_engine *e, long long *out16);
 /* state: 0 unvisited, 1 open, 2 open-new, 3 closed, +4 when also in V_toopen */
 RTPP_API int rtpp_fmt_read_tree(rtpp_fmt_engine *e, int inst, int max_nodes, int32_t *parent, float *cost, uint8_t *collision,
                                 uint8_t *state, int *n_out);
+/* RTFMT.cpp:285-391: path_ok = 1: ids root..entry then -2 (the goal); path_ok = 0 with path_len > 0: the depth-5 fallback chain
+ * root..nearest reachable node, as for rtpp_engine_read_path */
 RTPP_API int rtpp_fmt_read_path(rtpp_fmt_engine *e, int inst, int max_len, int32_t *ids, int *len_out);
 
 /* CDRT-RRT* engine (one warp per BImap planner, sequential-exact; reference CDRT2/lib/CDRT/CDRT.cpp).
