@@ -88,6 +88,20 @@ def all_gather_records(local_records, n_instances):
     return full
 
 
+def exchange_peer_handles(digest, handles):
+    """Set-up step of the fused multi-GPU calls: every rank contributes (a digest of what must be identical on all ranks —
+    the tick's slot order —, its list of 64-byte IPC handles) and gets everybody's, in rank order.  Raises on EVERY rank when
+    the digests differ, so that no rank goes on to launch a kernel that would wait for peers working on another plan."""
+    rank, ws = world()
+    everyone = [None] * ws
+    dist.all_gather_object(everyone, (digest, [bytes(h) for h in handles]))
+    if any(e[0] != everyone[0][0] for e in everyone):
+        raise RuntimeError("the ranks disagree on the tick's slot order (different node sets?)")
+    if any(len(e[1]) != len(handles) or any(len(h) != 64 for h in e[1]) for e in everyone):
+        raise RuntimeError("malformed peer handle list")
+    return everyone
+
+
 class PeerEdgeBatch:
     """Grain 2 without a collective on the data path: every rank checks its share of ONE edge batch (2048-edge blocks
     round-robin: edge cost varies with length, contiguous ranges are unbalanced) and its kernel stores the verdict words straight into every rank's result buffer over NVLink (CUDA IPC mappings of
@@ -198,10 +212,7 @@ class PeerTick:
             ctx._ck(ctx.L.rtpp_peer_alloc(ctx.h, C.c_size_t(max(nbytes, 4)), C.byref(ptr), h))
             mine.append(ptr.value)
             handles.append(bytes(h))
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, (digest, handles))
-        if any(e[0] != digest for e in everyone):
-            raise RuntimeError("the ranks disagree on the tick's slot order (different node sets?)")
+        everyone = exchange_peer_handles(digest, handles)
         self.own, self.opened = mine, []
         self.ptrs = [[0] * self.world for _ in range(5)]  # [buffer kind][rank]: tree0, row0, tree1, row1, flags
         for r in range(self.world):

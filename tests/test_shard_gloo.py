@@ -95,3 +95,41 @@ def test_tick_items_are_dealt_once_over_the_ranks():
                 sizes.append(len(t) + len(g))
             assert sorted(tree) == list(range(ntw)) and sorted(groups) == list(range(ng))
             assert max(sizes) - min(sizes) <= 1
+
+
+def _handle_worker(rank, ws, port, same_plan, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from rtpp_b200 import shard
+
+    handles = [bytes([rank * 16 + b]) * 64 for b in range(5)]
+    digest = "plan-A" if (same_plan or rank == 0) else "plan-B"
+    try:
+        got = shard.exchange_peer_handles(digest, handles)
+        q.put((rank, "ok", [[h[0] for h in e[1]] for e in got]))
+    except RuntimeError as exc:
+        q.put((rank, "raised", str(exc)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("same_plan", [True, False])
+def test_peer_handle_exchange_and_plan_agreement(same_plan):
+    """Set-up of the fused tick (shard.PeerTick): handles arrive in rank order on every rank; ranks whose plans differ ALL refuse
+    (a rank that went on alone would launch a kernel waiting for peers that never come)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 977 + int(same_plan)) % 2000
+    procs = [ctx.Process(target=_handle_worker, args=(r, 2, port, same_plan, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if same_plan:
+        want = [[0, 1, 2, 3, 4], [16, 17, 18, 19, 20]]
+        assert [r[1] for r in res] == ["ok", "ok"] and res[0][2] == want and res[1][2] == want
+    else:
+        assert [r[1] for r in res] == ["raised", "raised"] and "slot order" in res[0][2]
