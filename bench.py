@@ -582,6 +582,10 @@ def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdi
     out["knn_queries_per_s"] = n / (ms * 1e-3)
     out["knn_all_nodes_ms"] = ms
     out["knn_algorithmic_GBs"] = n * (16 + KNN * 20) / (ms * 1e-3) / 1e9  # 516 B per 25-NN query
+    try:  # the CPU side of the same queries (report both forms, state which), ids compared with the GPU's table
+        out["knn_cpu"] = measure_knn_cpu(wl.xy, wl.knn_idx.cpu().numpy().reshape(n, KNN))
+    except Exception as exc:  # an extra must not cost the bench line
+        out["knn_cpu"] = {"error": repr(exc)}
     # the same store queried at 1e6 uniform random points (binary64, as a planner's samples are: no shared cell between
     # consecutive queries), ids + squared distances out; device buffers
     import ctypes as C
@@ -631,6 +635,28 @@ def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdi
     # last: its edge batches load GAME0 into the ctx's planes (nothing after it uses the C4 planes)
     leg("c1_rtrrt_game0", lambda: measure_c1(ctx, torch, timed, peak or 6650.0, l2_gather_gbs))
     return out
+
+
+def measure_knn_cpu(xy, gpu_idx):
+    """Neighbour queries on the host cores over the C4 node set (every 5th node queries its 25-NN): the oracle's exact binary64
+    k-NN with its grid accelerator on all threads — the fair CPU form of what the kernels do — and the brute-force definition on
+    one thread (what the compiled reference runs on here in place of CGAL's kd-tree, which it rebuilds after every insert).  Both
+    id lists are compared with the rows of the GPU's table."""
+    from oracle import loader as orc
+
+    threads = os.cpu_count() or 1
+    ids = np.arange(0, len(xy), 5)
+    t0 = time.perf_counter()
+    gi, _, _ = orc.knn(xy, xy[ids].astype(np.float64), KNN, grid=(MAP_SIZE, MAP_SIZE, 16), nthreads=threads)
+    dt = time.perf_counter() - t0
+    qb = ids[:64]
+    t0 = time.perf_counter()
+    bi, _, _ = orc.knn(xy, xy[qb].astype(np.float64), KNN, nthreads=1)
+    dtb = time.perf_counter() - t0
+    return {"grid_queries_per_s": len(ids) / dt, "threads": threads, "kind": "port (oracle grid k-NN, exact binary64 (d2, id) order)",
+            "sample": f"{len(ids)} of the {len(xy)} node queries", "ids_match_gpu": bool(np.array_equal(gi, gpu_idx[ids])),
+            "brute_force_queries_per_s": len(qb) / dtb, "brute_force_threads": 1, "brute_force_sample": f"{len(qb)} queries",
+            "brute_force_ids_match_gpu": bool(np.array_equal(bi, gpu_idx[qb]))}
 
 
 def measure_dropin_class(ticks=24, dt=5000):
