@@ -920,8 +920,11 @@ static int tick_timing_end(rtpp_ctx *ctx, int grid, TickArgs *a) {
     }
     const unsigned li = (unsigned)longest;
     const char *kind = li < (unsigned)a->n_far_words ? "far word" : ((size_t)(li - a->n_far_words) * a->stride + a->first < (size_t)a->n_tree_words ? "tree word" : "window group");
-    fprintf(stderr, "[rtpp tick timing] blocks %d items %u: last start +%.1f us, work done first +%.1f mean +%.1f last +%.1f us, exit +%.1f us; longest item %.1f us (item %u, %s), mean of the blocks' longest %.1f us\n", grid, a->n_items,
-            (s1 - t0) * 1e-3, (w0 - t0) * 1e-3, wsum / grid * 1e-3, (w1 - t0) * 1e-3, (e1 - t0) * 1e-3, (longest >> 32) * 1e-3, li, kind, lsum / grid * 1e-3);
+    fprintf(stderr, "[rtpp tick timing] blocks %d items %u: last start +%.1f us, work done first +%.1f mean +%.1f last +%.1f us, exit +%.1f us", grid, a->n_items,
+            (s1 - t0) * 1e-3, (w0 - t0) * 1e-3, wsum / grid * 1e-3, (w1 - t0) * 1e-3, (e1 - t0) * 1e-3);
+    if (longest) // items are only timed by the multi-GPU kernels
+        fprintf(stderr, "; longest item %.1f us (item %u, %s), mean of the blocks' longest %.1f us", (longest >> 32) * 1e-3, li, kind, lsum / grid * 1e-3);
+    fprintf(stderr, "\n");
     return RTPP_OK;
 }
 
