@@ -44,6 +44,7 @@ def lib():
         _lib.orc_rtfmt_create.restype = C.c_void_p
         _lib.orc_amrrt_create.restype = C.c_void_p
         _lib.orc_rtrrt_clock_reads.restype = C.c_longlong
+        _lib.orc_rtrrt_knn_mode.restype = C.c_longlong
         _lib.orc_rtfmt_start.restype = C.c_longlong
         _lib.orc_amrrt_rand_pos.restype = C.c_longlong
         _lib.orc_amrrt_diffusivity.restype = C.c_float
@@ -136,6 +137,18 @@ def knn(pts, q, k, grid=None, nthreads=1):
     return idx, d2, cnt
 
 
+def knn_kdtree(pts, q, k, domain=(4096.0, 4096.0)):
+    """The kd-tree form of the oracle's index (sliding midpoint, bucket 10), single-threaded: must equal knn()."""
+    pts = _c(pts, np.float32).reshape(-1, 2)
+    q = _c(q, np.float64).reshape(-1, 2)
+    idx = np.zeros((len(q), k), np.int32)
+    d2 = np.zeros((len(q), k), np.float64)
+    cnt = np.zeros(len(q), np.int32)
+    lib().orc_knn_kdtree(_ptr(pts), len(pts), C.c_double(domain[0]), C.c_double(domain[1]), _ptr(q), C.c_longlong(len(q)), k, _ptr(idx), _ptr(d2),
+                         _ptr(cnt))
+    return idx, d2, cnt
+
+
 def tree_propagate(S, D, xy, parent, root, divisor, mask, cost, col):
     H, W = (S if S is not None else D).shape
     xy = _c(xy, np.float32).reshape(-1, 2)
@@ -215,6 +228,11 @@ class OrcRTRRT(_TreePlanner):
 
     def set_clock(self, dt_ns, n0=0):
         self.L.orc_rtrrt_set_clock(self.h, C.c_longlong(dt_ns), C.c_longlong(n0))
+
+    def knn_mode(self, mode=-1):
+        """mode 1: neighbour queries from a kd-tree rebuilt after every insert (CGAL's behaviour: the reference-shaped CPU cost),
+        0: the grid (default); -1: just read.  Returns the number of kd-tree builds so far.  Answers are the same in both modes."""
+        return int(self.L.orc_rtrrt_knn_mode(self.h, int(mode)))
 
     def presample(self, r, n_max):
         r = _c(r, np.int32)

@@ -227,17 +227,32 @@ class KnnIndex {
         xy_.push_back(x);
         xy_.push_back(y);
         cells_[(size_t)cy(y) * gw_ + cx(x)].push_back(id);
+        kd_dirty_ = true;
         return id;
     }
     double px(int i) const { return xy_[2 * i]; }
     double py(int i) const { return xy_[2 * i + 1]; }
     const double *data() const { return xy_.data(); }
 
+    // kd_rebuild(true): answer queries from a kd-tree (sliding-midpoint splits, bucket size 10: CGAL/Splitters.h:35,159-212)
+    // that is REBUILT on the first query after every insert — what CGAL's Kd_tree does (insert -> invalidate_build,
+    // Kd_tree.h:433-466; const_build on the next search, :418-425).  Same answers as the grid and as knn_brute (the answer is
+    // defined as the k smallest (d2, id)); only the cost differs.  Used for the "reference-shaped" CPU baseline.
+    void kd_rebuild(bool on) { kd_on_ = on, kd_dirty_ = true; }
+    long long kd_builds() const { return kd_builds_; }
+
     void query(double qx, double qy, int k, std::vector<Nbr> &out) const {
         out.clear();
         int n = size();
         int kk = std::min(k, n);
         if (kk <= 0) return;
+        if (kd_on_) {
+            if (kd_dirty_) kd_build();
+            std::vector<Nbr> &heap = out;
+            kd_search(0, qx, qy, kk, heap);
+            std::sort_heap(heap.begin(), heap.end());
+            return;
+        }
         int c0x = cx(qx), c0y = cy(qy);
         std::vector<Nbr> &heap = out; // max-heap on (d2,id)
         int maxr = std::max(gw_, gh_);
@@ -277,6 +292,74 @@ class KnnIndex {
     }
 
   private:
+    struct KdNode {
+        int lo, hi;       // leaf: ids kd_ids_[lo, hi)
+        int dim;          // -1 = leaf
+        double split;
+        int left, right;
+    };
+    void kd_build() const {
+        kd_ids_.resize((size_t)size());
+        for (int i = 0; i < size(); i++) kd_ids_[i] = i;
+        kd_nodes_.clear();
+        kd_nodes_.reserve((size_t)size() / 4 + 8);
+        kd_split(0, size());
+        kd_dirty_ = false, kd_builds_++;
+    }
+    int kd_split(int lo, int hi) const {
+        const int me = (int)kd_nodes_.size();
+        kd_nodes_.push_back({lo, hi, -1, 0.0, -1, -1});
+        if (hi - lo <= 10) return me;
+        double mn[2] = {HUGE_VAL, HUGE_VAL}, mx[2] = {-HUGE_VAL, -HUGE_VAL};
+        for (int i = lo; i < hi; i++)
+            for (int d = 0; d < 2; d++) {
+                const double v = xy_[2 * kd_ids_[i] + d];
+                mn[d] = std::min(mn[d], v), mx[d] = std::max(mx[d], v);
+            }
+        const int dim = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;
+        if (mx[dim] == mn[dim]) return me; // all points coincide: a (large) leaf
+        // midpoint of the tight box; both sides are non-empty because min < mid <= max, so no sliding is needed
+        const double mid = mn[dim] + (mx[dim] - mn[dim]) * 0.5;
+        const double cut = mid > mn[dim] ? mid : mx[dim];
+        int *b = kd_ids_.data() + lo, *e = kd_ids_.data() + hi;
+        int *m = std::partition(b, e, [&](int id) { return xy_[2 * id + dim] < cut; });
+        const int midx = lo + (int)(m - b);
+        kd_nodes_[me].dim = dim, kd_nodes_[me].split = cut;
+        const int l = kd_split(lo, midx);
+        const int r = kd_split(midx, hi);
+        kd_nodes_[me].left = l, kd_nodes_[me].right = r;
+        return me;
+    }
+    void kd_search(int node, double qx, double qy, int kk, std::vector<Nbr> &heap) const {
+        const KdNode &nd = kd_nodes_[node];
+        if (nd.dim < 0) {
+            for (int i = nd.lo; i < nd.hi; i++) {
+                const int id = kd_ids_[i];
+                Nbr nb{sqdist64(qx, qy, xy_[2 * id], xy_[2 * id + 1]), id};
+                if ((int)heap.size() < kk) {
+                    heap.push_back(nb);
+                    std::push_heap(heap.begin(), heap.end());
+                } else if (nb < heap.front()) {
+                    std::pop_heap(heap.begin(), heap.end());
+                    heap.back() = nb;
+                    std::push_heap(heap.begin(), heap.end());
+                }
+            }
+            return;
+        }
+        const double q = nd.dim ? qy : qx, diff = q - nd.split;
+        const int near = diff < 0 ? nd.left : nd.right, far = diff < 0 ? nd.right : nd.left;
+        kd_search(near, qx, qy, kk, heap);
+        // a point beyond the plane is at least |diff| away in this coordinate; rounding is monotone, so its computed d2 is
+        // >= diff*diff as computed here: pruning on strict > never drops a candidate that ties with the k-th
+        if ((int)heap.size() < kk || !(diff * diff > heap.front().d2)) kd_search(far, qx, qy, kk, heap);
+    }
+    bool kd_on_ = false;
+    mutable bool kd_dirty_ = true;
+    mutable long long kd_builds_ = 0;
+    mutable std::vector<int> kd_ids_;
+    mutable std::vector<KdNode> kd_nodes_;
+
     int cx(double x) const { return std::min(gw_ - 1, std::max(0, (int)std::floor(x / cell_))); }
     int cy(double y) const { return std::min(gh_ - 1, std::max(0, (int)std::floor(y / cell_))); }
     double cell_ = 16;

@@ -111,6 +111,25 @@ ORC_EXPORT void orc_knn_grid(const float *pts, int n, double W, double H, double
     });
 }
 
+// The same queries through the kd-tree form of the index (sliding-midpoint, bucket 10, built once here); for the equality test
+// against orc_knn_brute.  Single-threaded on purpose: the tree is built lazily on the first query.
+ORC_EXPORT void orc_knn_kdtree(const float *pts, int n, double W, double H, const double *q, long long nq, int k, int32_t *idx,
+                               double *d2, int32_t *count) {
+    KnnIndex ix;
+    ix.init(W, H, 64);
+    for (int i = 0; i < n; i++) ix.insert((double)pts[2 * i], (double)pts[2 * i + 1]);
+    ix.kd_rebuild(true);
+    std::vector<Nbr> out;
+    for (long long i = 0; i < nq; i++) {
+        ix.query(q[2 * i], q[2 * i + 1], k, out);
+        for (int j = 0; j < k; j++) {
+            idx[i * k + j] = j < (int)out.size() ? out[j].id : -1;
+            d2[i * k + j] = j < (int)out.size() ? out[j].d2 : HUGE_VAL;
+        }
+        if (count) count[i] = (int)out.size();
+    }
+}
+
 // R3 on flat arrays: BFS from root over the children implied by parent[]; every tree edge gets
 // cost[c] = cost[p] + {E(p,c), |p-c|} (RTRRT.cpp:121-135).  Unreached nodes keep their input
 // cost/col.  Returns the number of nodes reached.
@@ -196,6 +215,13 @@ ORC_EXPORT void *orc_rtrrt_create(const uint8_t *S, int rows, int cols, int divi
     return h;
 }
 ORC_EXPORT void orc_rtrrt_destroy(void *h) { delete (HRTRRT *)h; }
+// mode 1: neighbour queries from a kd-tree rebuilt on the first query after every insert, as CGAL's Kd_tree does (same answers as
+// the default grid; the cost profile of the reference).  Returns the number of rebuilds so far.
+ORC_EXPORT long long orc_rtrrt_knn_mode(void *h, int mode) {
+    KnnIndex &ix = ((HRTRRT *)h)->p.index;
+    if (mode >= 0) ix.kd_rebuild(mode == 1);
+    return ix.kd_builds();
+}
 ORC_EXPORT void orc_rtrrt_set_clock(void *h, long long dt_ns, long long n0) {
     ((HRTRRT *)h)->p.clk.dt_ns = dt_ns, ((HRTRRT *)h)->p.clk.n = n0;
 }

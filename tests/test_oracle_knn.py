@@ -72,3 +72,45 @@ def test_knn_tie_exposure_is_quantified(oracle):
     sl, ol = _tie_exposure(oracle, lat, lat[:1000].astype(np.float64), 25)
     assert sl + ol > 900 and sl > 100   # (k = 25 is exactly the 5 x 5 block of an interior lattice point: set ties come from the border)
     print(f"tie exposure: float samples set {s} order {o}; integer samples set {si} order {oi}; lattice set {sl} order {ol}")
+
+
+def test_kdtree_form_equals_the_definition(oracle):
+    """The reference-shaped index of the CPU baseline (kd-tree, sliding-midpoint splits, bucket 10, rebuilt after inserts:
+    SURVEY 8(d)) returns exactly the brute-force answer — ids, order and d2 bits — including ties and coincident points."""
+    rng = np.random.default_rng(3)
+    pts = _pts(rng, 30_000, 2729, 2729)
+    q = np.concatenate([pts[:1500].astype(np.float64), rng.random((1500, 2)) * 2729, np.array([[-50.0, -50.0], [5000.0, 10.0]])])
+    for k in (1, 25):
+        bi, bd, bc = oracle.knn(pts, q, k, nthreads=4)
+        ki, kd, kc = oracle.knn_kdtree(pts, q, k, (2729.0, 2729.0))
+        assert np.array_equal(bi, ki) and np.array_equal(bd.view(np.uint64), kd.view(np.uint64)) and np.array_equal(bc, kc)
+    xs, ys = np.meshgrid(np.arange(0, 48, dtype=np.float32) * 4, np.arange(0, 48, dtype=np.float32) * 4)
+    lat = np.stack([xs.ravel(), ys.ravel()], 1)
+    lat = np.concatenate([lat, lat[:100]])[rng.permutation(len(lat) + 100)]   # ties everywhere, 100 duplicated points
+    bi, bd, _ = oracle.knn(lat, lat[:600].astype(np.float64), 25)
+    ki, kd, _ = oracle.knn_kdtree(lat, lat[:600].astype(np.float64), 25, (192.0, 192.0))
+    assert np.array_equal(bi, ki) and np.array_equal(bd.view(np.uint64), kd.view(np.uint64))
+    same = np.tile(np.array([[5.0, 5.0]], np.float32), (40, 1))
+    assert np.array_equal(oracle.knn(same, same[:3].astype(np.float64), 25)[0], oracle.knn_kdtree(same, same[:3].astype(np.float64), 25, (16.0, 16.0))[0])
+
+
+def test_planner_loop_is_the_same_on_either_index(oracle):
+    """RT-RRT* on the grid index and on the kd-tree rebuilt after every insert: the same tree, byte for byte (only the CPU cost
+    differs, which is what bench.py reports as cpu_kdtree_rebuild_*)."""
+    S = oracle.load_map("MESS6")
+    trees = []
+    for mode in (0, 1):
+        o = oracle.OrcRTRRT(S)
+        o.knn_mode(mode)
+        o.set_clock(5000)
+        assert o.set_agent(720.0, 720.0) and o.set_goal(70.0, 70.0)
+        stream, pos = oracle.rand31(11, 400_000), 0
+        for _ in range(6):
+            o.update_tree()
+            pts, offs = o.presample(stream[pos:], 2048)
+            pos += int(offs[o.expand_rewiring(50, pts)])
+            o.get_path()
+        trees.append(o.dump())
+        assert (o.knn_mode(-1) > 100) == (mode == 1)
+        o.close()
+    assert all(np.array_equal(a.view(np.uint8), b.view(np.uint8)) for a, b in zip(*trees))

@@ -68,7 +68,28 @@ def c1_rtrrt(ctx, orc, n_samples=20_000, dt=1_000_000, max_ticks=40_000, seed=1,
         o.close()
         out["cpu_tick_ms_p50"] = float(np.median(tl) * 1e3)
         out["cpu_total_s"] = float(sum(tl))
-        out["cpu_kind"] = "port (oracle loops), 1 thread"
+        out["cpu_kind"] = "port (oracle loops, grid k-NN), 1 thread"
+        # the same ticks with the reference's index behaviour: a kd-tree rebuilt on the first query after every insert (CGAL,
+        # Kd_tree.h:433-466) — same tree, the reference-shaped cost (report both, state which)
+        o = orc.OrcRTRRT(S)
+        o.knn_mode(1)
+        o.set_clock(dt)
+        o.set_agent(550.0, 550.0)
+        o.set_goal(-1.0, -1.0)
+        pos2, tk = 0, []
+        for _ in range(check_ticks):
+            t0 = time.perf_counter()
+            o.update_tree()
+            pos2 += o.expand_rewiring(50, samples[pos2:])
+            o.get_path()
+            tk.append(time.perf_counter() - t0)
+        kd_tree = o.dump()
+        out["cpu_kdtree_rebuild_tick_ms_p50"] = float(np.median(tk) * 1e3)
+        out["cpu_kdtree_rebuild_total_s"] = float(sum(tk))
+        out["cpu_kdtree_rebuilds"] = o.knn_mode(-1)
+        out["cpu_kdtree_same_tree"] = bool(pos2 == pos and all(np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+                                                                for a, b in zip(cpu_tree, kd_tree)))
+        o.close()
         out["ticks_compared"] = check_ticks
         out["tree_matches_cpu"] = bool(pos == snap[1] and all(np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
                                                               for a, b in zip(cpu_tree, snap[0])))
