@@ -608,6 +608,11 @@ def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdi
     ms = timed(lambda: ctx.tree_propagate_dev(0, DIVISOR, 3), 5)
     out["propagate_1e6_tree_edges_ms"] = ms
     out["propagate_edges_per_s"] = (n - 1) / (ms * 1e-3)
+    if roofline_formula and peak:
+        # bytes(edge) = 40 (ids, coordinates, two cost|parent words) + the edge-check bytes (the step's mean is used for
+        # both); these kernels are latency / atomic bound by the survey's own analysis, the fraction says how far from streaming
+        out["propagate_algorithmic_GBs"] = (n - 1) * (40 + roofline_formula) / (ms * 1e-3) / 1e9
+        out["propagate_roofline_frac"] = out["propagate_algorithmic_GBs"] / peak
     best = None
     for _ in range(3):  # the first call also allocates the 100 MB edge-weight scratch; same start state every time
         ctx.tree_set(wl.parent, cost0, col0)
@@ -617,6 +622,9 @@ def measure_extras(wl, torch, sweep, roofline_formula=None, peak=None, cpu_verdi
         ms = (time.perf_counter() - t0) * 1e3
         best = ms if best is None else min(best, ms)
     out["rewire_to_quiescence_ms"] = best
+    if roofline_formula and peak:
+        out["rewire_algorithmic_GBs"] = n * KNN * (40 + roofline_formula) / (best * 1e-3) / 1e9  # every k-NN edge weighed and relaxed at least once
+        out["rewire_roofline_frac"] = out["rewire_algorithmic_GBs"] / peak
     out["rewire_sweeps"] = sweeps
     out["rewire_schedule"] = "work list by cost bucket (near-far), blocks chase their improvements through shared-memory queues; wall time of the host call, best of 3"
 
