@@ -16,8 +16,9 @@ the tick's work items go round-robin over the ranks and every rank ends with ALL
 (rtpp_tick_check_allgather_dev: the all-gather is peer stores over NVLink inside the launch); time = max over ranks.
 `e2e`: one replanning tick through the host-buffer C-ABI calls a planner class makes
 (rtpp_map_draw_dynamic + rtpp_tick_check): the obstacle poses go in, the verdict words come back to page-locked host
-memory, the tree stays resident.  The same edges as an explicit end-point list from the host (rtpp_edges_check, 416 MB H2D per
-step) are reported beside it.
+memory, the tree stays resident.  With N > 1 every rank uploads the poses and checks its share; rank 0 — the planner process —
+reads the whole tick's verdict words back (the variant in which every rank reads everything back is reported beside it).  The
+same edges as an explicit end-point list from the host (rtpp_edges_check, 416 MB H2D per step) are reported too.
 `roofline`: algorithmic bytes of the step (16 + 4 * probes + 1/8 per edge) / launch time against the measured
 HBM peak, with the physically moved bytes (ncu) and the instruction-issue form next to it.
 Extras (the explicit-list kernel, the other edge kernels, k-NN queries/s, propagate / relax latency, the four planners'
@@ -423,36 +424,48 @@ def main():
     pxy = np.ascontiguousarray(np.concatenate(wl.obstacles[1]).astype(np.int32))
     psz = np.ascontiguousarray(np.array([len(p) for p in wl.obstacles[1]], np.int32))
 
-    def e2e_step():
+    def e2e_step(read=True):
         # MainTask's DrawDObsmap (obstacle poses in) + the tick's collision pass (verdict words out)
         ctx.call("map_draw_dynamic", C.c_void_p(circ.ctypes.data), len(circ), C.c_void_p(pxy.ctypes.data), C.c_void_p(psz.ctypes.data), len(psz))
         if peer is None:
             ctx.call("tick_check", DIVISOR, 3, C.c_void_p(h_tree.data_ptr()), C.c_void_p(h_rows.data_ptr()))  # synchronous
         else:
             d_tree, d_rows = peer.check(3)
-            ctx.call("d2h", C.c_void_p(h_tree.data_ptr()), C.c_void_p(d_tree), C.c_size_t(h_tree.numel() * 4))
-            ctx.call("d2h", C.c_void_p(h_rows.data_ptr()), C.c_void_p(d_rows), C.c_size_t(h_rows.numel() * 4))
+            if read:
+                ctx.call("d2h", C.c_void_p(h_tree.data_ptr()), C.c_void_p(d_tree), C.c_size_t(h_tree.numel() * 4))
+                ctx.call("d2h", C.c_void_p(h_rows.data_ptr()), C.c_void_p(d_rows), C.c_size_t(h_rows.numel() * 4))
             ctx.sync()
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()  # returns after the verdict words are back on the host
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=wl.dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        peer.status()
-    e2e_s = float(t.item())
+    def e2e_time(readers):
+        """seconds per tick, max over ranks; `readers` = the ranks that copy the whole tick's verdict words to their host"""
+        read = rank in readers
+        for _ in range(3):
+            e2e_step(read)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step(read)  # returns after the verdict words are back on the host (readers) / the launch has retired
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=wl.dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            peer.status()
+        return float(t.item())
+
+    # N > 1: ONE planner process (rank 0) owns the result — it reads the whole tick's verdict words back; the other ranks are
+    # workers (poses in, their share of the tick).  The variant in which EVERY rank reads everything back (N copies of 4.3 MB
+    # through the box's PCIe complex at once) is timed next to it.
+    every_rank_s = e2e_time(set(range(world))) if world > 1 else None
+    e2e_s = e2e_time({0})
     same = bool(np.array_equal(h_tree.numpy(), gpu_tree.view(np.int32)) and np.array_equal(h_rows.numpy(), gpu_rows.view(np.int32)))
     e2e = {"value": wl.n_edges / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(circ.nbytes + pxy.nbytes + psz.nbytes),
            "d2h_bytes_per_step": int((h_tree.numel() + h_rows.numel()) * 4), "steps": e2e_steps, "matches_resident_run": same,
            "api": ("rtpp_map_draw_dynamic + rtpp_tick_check (host buffers): obstacle poses in, verdict words out (page-locked, written by the kernel), tree resident"
                    if peer is None else
-                   "per rank: rtpp_map_draw_dynamic + rtpp_tick_check_allgather_dev + D2H of the whole tick's verdict words (page-locked); max over ranks")}
+                   "every rank: rtpp_map_draw_dynamic + rtpp_tick_check_allgather_dev; rank 0 (the planner process) also copies the whole tick's "
+                   "verdict words to page-locked host memory; max over ranks")}
+    if every_rank_s:
+        e2e["every_rank_reads_back"] = {"value": wl.n_edges / every_rank_s, "note": "all ranks copy the whole result to their own host at the same time"}
     # the same edges as an explicit end-point list from the host (rtpp_edges_check): PCIe-bound by 16 B/edge
     h_edges = torch.empty((wl.n_edges, 4), dtype=torch.float32, pin_memory=True)
     h_edges.copy_(wl.edges)
